@@ -1,0 +1,116 @@
+/* mga_cbam.h -- C ABI of the B200-native mask-guided CBAM hot path.
+ *
+ * The reference (MarioPasc/MGA-YOLO) has no native code and no FFI for this path: it is
+ * ~200 eager ATen calls per forward.  These entry points are what a Python FFI (ctypes /
+ * torch custom op) for that path binds, one per reference function group:
+ *
+ *   mga_cbam_forward    replaces MaskCBAM.forward              mga_yolo/nn/modules/masked_cbam.py:154-171
+ *                        (= _masked_avg :87-102, _masked_max :104-121, _cam :123-130,
+ *                           _sam :132-148, alpha residual :150-152,166-171, and the
+ *                           deterministic ProbMaskGater clamp  probmaskgater.py:77,82-83)
+ *   mga_cbam_backward   replaces what torch autograd derives from those lines
+ *                        (closed form: SURVEY.md section 8a "Backward")
+ *   mga_mask_downsample replaces MaskUtils.downsample_mask      mga_yolo/utils/mask_utils.py:64-141
+ *                        and MaskUtils.downsample_mask_prob     mga_yolo/utils/mask_utils.py:14-48
+ *                        (nearest / area / maxpool / default "maxpool+close" / avgpool)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch caching allocator);
+ *     the library never allocates, frees or synchronises.
+ *   - tensors are dense NCHW; `stream` is a cudaStream_t passed as void*.
+ *   - return value: 0 = ok, otherwise an MGA_ERR_* code; mga_last_error() gives text.
+ *     Nothing throws.  There is no CPU implementation behind any entry point.
+ */
+#ifndef MGA_CBAM_H
+#define MGA_CBAM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGA_ABI_VERSION 1
+
+enum { MGA_OK = 0, MGA_ERR_ARG = 1, MGA_ERR_UNSUPPORTED = 2, MGA_ERR_CUDA = 3, MGA_ERR_WORKSPACE = 4 };
+
+/* element types of feature map / gradient / mask tensors (parameters are always fp32) */
+enum { MGA_F32 = 0, MGA_BF16 = 1, MGA_F16 = 2, MGA_U8 = 3 };
+
+/* mga_cbam_desc.flags */
+enum {
+    MGA_HAS_MASK = 1 << 0,         /* mask pointer is valid; otherwise vanilla CBAM (masked_cbam.py:90-91,107-108,137-138) */
+    MGA_SIGMOID_MASK = 1 << 1,     /* use_sigmoid_mask (masked_cbam.py:93-94,110-111,143-144) */
+    MGA_GATE_CLAMP = 1 << 2,       /* eval-mode ProbMaskGater: clamp mask to [0,1] first (probmaskgater.py:77) */
+    MGA_SAMCAM_ADD = 1 << 4,       /* sam_cam_fusion = add (build-side mode, parity unpinned); default multiply = reference */
+    MGA_PYRAMID_MULTIPLY = 1 << 6, /* mga_pyramid_fusion = multiply (build-side mode); default add = reference alpha-skip */
+    MGA_FORCE_SPLIT = 1 << 8       /* debugging: never take the cluster-resident fused kernels */
+};
+
+typedef struct mga_cbam_desc {
+    int32_t B, C, H, W; /* feature map (B,C,H,W) */
+    int32_t hidden;     /* max(1, C / r)            masked_cbam.py:53 */
+    int32_t ksize;      /* odd spatial kernel, <= 7 masked_cbam.py:47,61 */
+    int32_t dtype;      /* MGA_F32 / MGA_BF16 / MGA_F16: x, out, grad_out, grad_x */
+    int32_t mask_dtype; /* MGA_F32 / MGA_BF16 / MGA_F16: mask and grad_mask */
+    int32_t flags;
+    float tiny_mask_thr; /* masked_cbam.py:40,98 */
+    float eps;           /* masked_cbam.py:41,99 */
+} mga_cbam_desc;
+
+/* parameters, named after the reference state_dict (masked_cbam.py:54-64); all fp32 */
+typedef struct mga_cbam_params {
+    const float* w1;   /* cam_mlp.0.weight (hidden, C) */
+    const float* b1;   /* cam_mlp.0.bias   (hidden)    */
+    const float* w2;   /* cam_mlp.2.weight (C, hidden) */
+    const float* b2;   /* cam_mlp.2.bias   (C)         */
+    const float* wsam; /* sam_conv.weight  (1,3,k,k)   */
+    const float* beta; /* beta ()                      */
+} mga_cbam_params;
+
+typedef struct mga_cbam_grads {
+    float* w1;
+    float* b1;
+    float* w2;
+    float* b2;
+    float* wsam;
+    float* beta;
+} mga_cbam_grads;
+
+int mga_abi_version(void);
+const char* mga_last_error(void);
+
+/* bytes of the saved-for-backward context and of the transient scratch for this shape */
+int mga_cbam_workspace(const mga_cbam_desc* d, size_t* ctx_bytes, size_t* scratch_bytes);
+
+/* out = MaskCBAM([x, mask]); fills ctx (kept by the caller until backward). */
+int mga_cbam_forward(const mga_cbam_desc* d, const void* x, const void* mask, const mga_cbam_params* p,
+                     void* out, void* ctx, void* scratch, void* stream);
+
+/* grad_x, grad_mask (may be NULL), parameter gradients (overwritten, not accumulated). */
+int mga_cbam_backward(const mga_cbam_desc* d, const void* x, const void* mask, const void* grad_out,
+                      const mga_cbam_params* p, const void* ctx, void* grad_x, void* grad_mask,
+                      const mga_cbam_grads* gp, void* scratch, void* stream);
+
+/* read-back of small saved quantities for tests / logging: which = 0 s(B,C), 1 a(B,HW) */
+int mga_cbam_ctx_view(const mga_cbam_desc* d, const void* ctx, int which, const float** ptr, size_t* count);
+
+/* mask downsample methods (mask_utils.py:64-141 and :14-48) */
+enum {
+    MGA_DS_NEAREST = 0,       /* cv2.INTER_NEAREST */
+    MGA_DS_AREA = 1,          /* cv2.INTER_AREA on uint8, then > thresh (binary) */
+    MGA_DS_MAXPOOL = 2,       /* zero pad + block max */
+    MGA_DS_AVGPOOL = 3,       /* zero pad + block mean (float out) */
+    MGA_DS_AREA_RAW = 4       /* cv2.INTER_AREA on uint8, no threshold (downsample_mask_prob 'area') */
+};
+
+/* src: (B,H,W) uint8 {0,1}; dst: (B,ceil(H/s),ceil(W/s)) uint8 or float32 (out_dtype).
+ * close3x3 != 0 applies the 3x3 MORPH_CLOSE "bridge"; tmp must hold 2*B*nh*nw bytes then. */
+int mga_mask_downsample(const uint8_t* src, void* dst, void* tmp, int32_t B, int32_t H, int32_t W, int32_t stride,
+                        int32_t method, float thresh, int32_t close3x3, int32_t out_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGA_CBAM_H */

@@ -1,0 +1,82 @@
+"""ctypes binding of libmga_cbam.so (C ABI declared in include/mga_cbam.h).
+
+There is deliberately no CPU implementation behind these symbols: if the shared
+library is missing or does not export what the header declares, every op raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libmga_cbam.so"
+ABI_VERSION = 1
+
+# enums of include/mga_cbam.h
+F32, BF16, F16, U8 = 0, 1, 2, 3
+HAS_MASK, SIGMOID_MASK, GATE_CLAMP = 1 << 0, 1 << 1, 1 << 2
+SAMCAM_ADD, PYRAMID_MULTIPLY, FORCE_SPLIT = 1 << 4, 1 << 6, 1 << 8
+DS_NEAREST, DS_AREA, DS_MAXPOOL, DS_AVGPOOL, DS_AREA_RAW = 0, 1, 2, 3, 4
+
+EXPORTS = (
+    "mga_abi_version", "mga_last_error", "mga_cbam_workspace", "mga_cbam_forward", "mga_cbam_backward",
+    "mga_cbam_ctx_view", "mga_mask_downsample",
+)
+
+
+class Desc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("hidden", C.c_int32), ("ksize", C.c_int32), ("dtype", C.c_int32), ("mask_dtype", C.c_int32),
+        ("flags", C.c_int32), ("tiny_mask_thr", C.c_float), ("eps", C.c_float),
+    ]
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w1", "b1", "w2", "b2", "wsam", "beta")]
+
+
+Grads = Params  # same layout: six float pointers
+
+_lib = None
+
+
+class MgaLibraryError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library once; fail loudly if it is absent or incomplete."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise MgaLibraryError(
+            f"{LIB_PATH} is missing. Build it with `python -m mga_yolo_b200.build` (needs nvcc, sm_100a). "
+            "mga_yolo_b200 has no CPU or PyTorch fallback for the mask-guided CBAM path."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    missing = [s for s in EXPORTS if not hasattr(lib, s)]
+    if missing:
+        raise MgaLibraryError(f"{LIB_PATH} does not export {missing}; rebuild it")
+    lib.mga_abi_version.restype = C.c_int
+    lib.mga_last_error.restype = C.c_char_p
+    lib.mga_cbam_workspace.argtypes = [C.POINTER(Desc), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.mga_cbam_forward.argtypes = [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
+    lib.mga_cbam_backward.argtypes = [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.POINTER(Grads), C.c_void_p, C.c_void_p]
+    lib.mga_cbam_ctx_view.argtypes = [C.POINTER(Desc), C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    lib.mga_mask_downsample.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p]
+    for fn in (lib.mga_cbam_workspace, lib.mga_cbam_forward, lib.mga_cbam_backward, lib.mga_cbam_ctx_view, lib.mga_mask_downsample):
+        fn.restype = C.c_int
+    if lib.mga_abi_version() != ABI_VERSION:
+        raise MgaLibraryError(f"ABI mismatch: library {lib.mga_abi_version()} vs binding {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().mga_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

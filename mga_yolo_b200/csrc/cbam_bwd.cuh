@@ -1,0 +1,377 @@
+// cbam_bwd.cuh -- backward kernels of the split path (closed form, SURVEY.md section 8a "Backward").
+//
+//   B1 bwd_reduce1   over (x,g): T_p = sum_c g x q_c ; E_c = sum_p g x (a_p | 1) ; Gx_c = sum_p g x
+//   B2 bwd_conv      dpre = k1 T a(1-a); dcat = convT(dpre, Wsam); dWsam partials; sum_p a_p T_p
+//   B3 bwd_reduce2   over x      : Q_c = sum_p x (dcat1/C + [idx==c] dcat0)        (multiply mode only)
+//   B4 bwd_mlp       ds -> dz -> MLP backward -> per-channel coefficients for B5
+//   B5 bwd_dx        over (x,g)  : dx, and R_p = sum_c cA_c x -> dmask
+//   B6 bwd_wgrad     dW1 db1 dW2 db2 (batch sums), dWsam / dbeta (partial sums)
+#pragma once
+#include "common.cuh"
+
+namespace mga {
+
+// ------------------------------------------------------------------ B1
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBlock) bwd_reduce1_kernel(const T* __restrict__ x, const T* __restrict__ g, Shape sh, Ctx ctx,
+                                                             BwdScratch bs, int nT) {
+    __shared__ float sh_t[kWarpsPerBlock][32 * VEC];
+    const int b = blockIdx.y, tile = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int U = sh.S / VEC, C = sh.C;
+    const int u = tile * 32 + lane;
+    const bool act = u < U;
+    const bool multiply = !sh.samcam_add();
+    const float* sp = ctx.s + (size_t)b * C;
+
+    float av[VEC], tacc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { av[i] = 1.0f; tacc[i] = 0.0f; }
+    if (act && multiply) ldf<VEC>(ctx.a + (size_t)b * sh.S + (size_t)u * VEC, av);
+
+    const size_t base = ((size_t)b * C) * sh.S + (size_t)u * VEC;
+#pragma unroll 2
+    for (int c = w; c < C; c += kWarpsPerBlock) {
+        float e = 0.0f, gxs = 0.0f;
+        if (act) {
+            float xv[VEC], gv[VEC];
+            ldv<T, VEC>(x + base + (size_t)c * sh.S, xv);
+            ldv<T, VEC>(g + base + (size_t)c * sh.S, gv);
+            const float q = multiply ? __ldg(sp + c) : 1.0f;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float gx = gv[i] * xv[i];
+                tacc[i] = fmaf(gx, q, tacc[i]);
+                e = fmaf(gx, av[i], e);
+                gxs += gx;
+            }
+        }
+        e = warp_sum(e);
+        gxs = warp_sum(gxs);
+        if (lane == 0) {
+            const size_t o = ((size_t)b * nT + tile) * C + c;
+            bs.epart[o] = e;
+            bs.gxpart[o] = gxs;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) sh_t[w][lane * VEC + i] = tacc[i];
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * VEC; e += kBlock) {
+        const int p = tile * 32 * VEC + e;
+        if (p >= sh.S) continue;
+        float t = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kWarpsPerBlock; ++j) t += sh_t[j][e];
+        bs.T[(size_t)b * sh.S + p] = t;
+    }
+}
+
+// ------------------------------------------------------------------ B2
+constexpr int kBT_W = 32, kBT_H = 8;
+__global__ void __launch_bounds__(kBlock) bwd_conv_kernel(Shape sh, const float* __restrict__ wsam, Ctx ctx, BwdScratch bs) {
+    constexpr int TW = kBT_W + kMaxK - 1, TH = kBT_H + kMaxK - 1;
+    __shared__ float dpre[TH][TW + 1];
+    __shared__ float cat[3][TH][TW + 1];
+    __shared__ float wk[3 * kMaxK * kMaxK];
+    __shared__ float red[32];
+    const int k = sh.k, pad = k / 2, H = sh.H, W = sh.W, S = sh.S;
+    const int b = blockIdx.z, x0 = blockIdx.x * kBT_W, y0 = blockIdx.y * kBT_H;
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const float k1 = ctx.consts[1];
+    const bool has_mask = sh.has_mask();
+    const float* planes[3] = {ctx.pmax + (size_t)b * S, ctx.pavg + (size_t)b * S, ctx.m + (size_t)b * S};
+    const float* Tp = bs.T + (size_t)b * S;
+    const float* ap = ctx.a + (size_t)b * S;
+
+    for (int i = threadIdx.x; i < 3 * k * k; i += kBlock) wk[i] = wsam[i];
+    const int tw = kBT_W + k - 1, th = kBT_H + k - 1;
+    float at_acc = 0.0f;
+    for (int i = threadIdx.x; i < tw * th; i += kBlock) {
+        const int r = i / tw, c = i % tw;
+        const int yy = y0 + r - pad, xx = x0 + c - pad;
+        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        float dp = 0.0f;
+        if (in) {
+            const float a = ap[yy * W + xx], t = Tp[yy * W + xx];
+            dp = k1 * t * a * (1.0f - a);
+            const bool own = r >= pad && r < pad + kBT_H && c >= pad && c < pad + kBT_W;
+            if (own) at_acc = fmaf(a, t, at_acc);
+        }
+        dpre[r][c] = dp;
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) cat[pl][r][c] = (in && (pl < 2 || has_mask)) ? planes[pl][yy * W + xx] : 0.0f;
+    }
+    __syncthreads();
+
+    // conv2d_input: dcat[pl][y][x] = sum_ij dpre[y - i + pad][x - j + pad] * W[pl][i][j]
+    const int tx = threadIdx.x % kBT_W, ty = threadIdx.x / kBT_W;
+    const int ox = x0 + tx, oy = y0 + ty;
+    if (ox < W && oy < H) {
+        float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+        for (int i = 0; i < k; ++i)
+            for (int j = 0; j < k; ++j) {
+                const float dp = dpre[ty + 2 * pad - i][tx + 2 * pad - j];
+                d0 = fmaf(dp, wk[(0 * k + i) * k + j], d0);
+                d1 = fmaf(dp, wk[(1 * k + i) * k + j], d1);
+                d2 = fmaf(dp, wk[(2 * k + i) * k + j], d2);
+            }
+        const size_t o = (size_t)b * S + oy * W + ox;
+        const size_t plane = (size_t)sh.B * S;
+        bs.dcat[o] = d0;
+        bs.dcat[plane + o] = d1;
+        bs.dcat[2 * plane + o] = d2;
+    }
+    // conv2d_weight: dW[pl][i][j] = sum_{y,x in tile} cat[pl][y + i - pad][x + j - pad] * dpre[y][x]
+    const int ntap = 3 * k * k;
+    float* part = bs.convpart + (size_t)cta * (3 * kMaxK * kMaxK + 1);
+    if ((int)threadIdx.x < ntap) {
+        const int pl = threadIdx.x / (k * k), i = (threadIdx.x / k) % k, j = threadIdx.x % k;
+        float acc = 0.0f;
+        for (int yy = 0; yy < kBT_H; ++yy)
+            for (int xx = 0; xx < kBT_W; ++xx) acc = fmaf(cat[pl][yy + i][xx + j], dpre[yy + pad][xx + pad], acc);
+        part[threadIdx.x] = acc;
+    }
+    const float at = block_sum(at_acc, red);
+    if (threadIdx.x == 0) part[3 * kMaxK * kMaxK] = at;
+}
+
+// ------------------------------------------------------------------ B3 (multiply mode)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBlock) bwd_reduce2_kernel(const T* __restrict__ x, Shape sh, Ctx ctx, BwdScratch bs, int nT) {
+    const int b = blockIdx.y, tile = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int U = sh.S / VEC, C = sh.C;
+    const int u = tile * 32 + lane;
+    const bool act = u < U;
+    const size_t plane = (size_t)sh.B * sh.S;
+    float d0[VEC], d1[VEC];
+    int ix[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { d0[i] = 0.0f; d1[i] = 0.0f; ix[i] = -1; }
+    if (act) {
+        const size_t o = (size_t)b * sh.S + (size_t)u * VEC;
+        ldf<VEC>(bs.dcat + o, d0);
+        ldf<VEC>(bs.dcat + plane + o, d1);
+        ldi<VEC>(ctx.idx + o, ix);
+        const float invC = 1.0f / (float)C;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) d1[i] *= invC;
+    }
+    const size_t base = ((size_t)b * C) * sh.S + (size_t)u * VEC;
+#pragma unroll 4
+    for (int c = w; c < C; c += kWarpsPerBlock) {
+        float qv = 0.0f;
+        if (act) {
+            float xv[VEC];
+            ldv<T, VEC>(x + base + (size_t)c * sh.S, xv);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) qv = fmaf(xv[i], d1[i] + (ix[i] == c ? d0[i] : 0.0f), qv);
+        }
+        qv = warp_sum(qv);
+        if (lane == 0) bs.qpart[((size_t)b * nT + tile) * C + c] = qv;
+    }
+}
+
+// ------------------------------------------------------------------ B4 (one CTA per sample)
+__global__ void __launch_bounds__(kBlock) bwd_mlp_kernel(Shape sh, mga_cbam_params prm, Ctx ctx, BwdScratch bs, int nT) {
+    extern __shared__ float smem[];
+    __shared__ float red[32];
+    const int C = sh.C, Hd = sh.hidden, b = blockIdx.x;
+    float* s_dz = smem;          // C
+    float* s_dha = s_dz + C;     // Hd
+    float* s_dhm = s_dha + Hd;   // Hd
+    const bool multiply = !sh.samcam_add();
+    const bool has_mask = sh.has_mask();
+    const float k1 = ctx.consts[1];
+    float gx_tot = 0.0f, se_tot = 0.0f;
+    for (int c = threadIdx.x; c < C; c += kBlock) {
+        float e = 0.0f, q = 0.0f, gxs = 0.0f;
+        for (int t = 0; t < nT; ++t) {
+            const size_t o = ((size_t)b * nT + t) * C + c;
+            e += bs.epart[o];
+            gxs += bs.gxpart[o];
+            if (multiply) q += bs.qpart[o];
+        }
+        const float s = ctx.s[b * C + c];
+        const float ds = k1 * e + q;
+        const float dz = ds * s * (1.0f - s);
+        s_dz[c] = dz;
+        bs.dz[b * C + c] = dz;
+        gx_tot += gxs;
+        if (!multiply) se_tot = fmaf(s, e, se_tot);  // add mode: sum_c s_c sum_p g x
+    }
+    // per-sample piece of d alpha: sum g x gate - [pyramid add] sum g x, minus the part B2 owns (sum_p a_p T_p)
+    const float gsum = block_sum(gx_tot, red);
+    const float ssum = block_sum(se_tot, red);
+    if (threadIdx.x == 0) bs.alphapart[b] = ssum - (sh.pyramid_multiply() ? 0.0f : gsum);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int j = w; j < Hd; j += kWarpsPerBlock) {
+        float acc = 0.0f;
+        for (int c = lane; c < C; c += 32) acc = fmaf(s_dz[c], __ldg(prm.w2 + (size_t)c * Hd + j), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const float da = ctx.ha[b * Hd + j] > 0.0f ? acc : 0.0f;
+            const float dm = ctx.hm[b * Hd + j] > 0.0f ? acc : 0.0f;
+            s_dha[j] = da;
+            s_dhm[j] = dm;
+            bs.dha[b * Hd + j] = da;
+            bs.dhm[b * Hd + j] = dm;
+        }
+    }
+    __syncthreads();
+    const float use = has_mask ? ctx.use[b] : 0.0f;
+    const float den = has_mask ? ctx.den[b] : 1.0f;
+    const float pass = (has_mask && ctx.msum[b] >= sh.eps) ? 1.0f : 0.0f;  // clamp_min backward
+    const float invS = 1.0f / (float)sh.S;
+    float kacc = 0.0f;
+    for (int c = threadIdx.x; c < C; c += kBlock) {
+        float davg = 0.0f, dmx = 0.0f;
+        for (int j = 0; j < Hd; ++j) {
+            const float wv = __ldg(prm.w1 + (size_t)j * C + c);
+            davg = fmaf(s_dha[j], wv, davg);
+            dmx = fmaf(s_dhm[j], wv, dmx);
+        }
+        const int i = b * C + c;
+        const bool dead = has_mask && ctx.amax[i] < 0;
+        const float cA = has_mask ? use * davg / den : 0.0f;
+        bs.cA[i] = cA;
+        bs.cG[i] = ((1.0f - use) * davg + (dead ? dmx : 0.0f)) * invS;
+        bs.cM[i] = dead ? 0.0f : dmx;
+        kacc = fmaf(cA, ctx.apool[i] * pass, kacc);
+    }
+    const float ksum = block_sum(kacc, red);
+    if (threadIdx.x == 0) bs.kb[b] = ksum;
+}
+
+// ------------------------------------------------------------------ B5
+template <typename T, int VEC, typename TM>
+__global__ void __launch_bounds__(kBlock) bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ g, const TM* __restrict__ mask,
+                                                        T* __restrict__ dx, TM* __restrict__ dmask, Shape sh, Ctx ctx, BwdScratch bs) {
+    __shared__ float sh_r[kWarpsPerBlock][32 * VEC];
+    const int b = blockIdx.y, tile = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int U = sh.S / VEC, C = sh.C;
+    const int u = tile * 32 + lane;
+    const bool act = u < U;
+    const bool add = sh.samcam_add();
+    const bool has_mask = sh.has_mask();
+    const float k0 = ctx.consts[0], k1 = ctx.consts[1];
+    const size_t plane = (size_t)sh.B * sh.S;
+
+    float av[VEC], d0[VEC], d1[VEC], mv[VEC], racc[VEC];
+    int ix[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { av[i] = 0.0f; d0[i] = 0.0f; d1[i] = 0.0f; mv[i] = 0.0f; racc[i] = 0.0f; ix[i] = -1; }
+    if (act) {
+        const size_t o = (size_t)b * sh.S + (size_t)u * VEC;
+        ldf<VEC>(ctx.a + o, av);
+        ldf<VEC>(bs.dcat + o, d0);
+        ldf<VEC>(bs.dcat + plane + o, d1);
+        ldi<VEC>(ctx.idx + o, ix);
+        if (has_mask) ldf<VEC>(ctx.m + o, mv);
+        const float invC = 1.0f / (float)C;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) d1[i] *= invC;
+    }
+    const size_t base = ((size_t)b * C) * sh.S + (size_t)u * VEC;
+    if (act) {
+#pragma unroll 2
+        for (int c = w; c < C; c += kWarpsPerBlock) {
+            const int bc = b * C + c;
+            float xv[VEC], gv[VEC], ov[VEC];
+            ldv<T, VEC, true>(x + base + (size_t)c * sh.S, xv);
+            ldv<T, VEC, true>(g + base + (size_t)c * sh.S, gv);
+            const float s = __ldg(ctx.s + bc), cA = __ldg(bs.cA + bc), cG = __ldg(bs.cG + bc), cM = __ldg(bs.cM + bc);
+            const int am = __ldg(ctx.amax + bc);
+            const float q = add ? 1.0f : s;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float gate = add ? (s + av[i]) : (s * av[i]);
+                float v = gv[i] * fmaf(k1, gate, k0);
+                v = fmaf(q, d1[i] + (ix[i] == c ? d0[i] : 0.0f), v);
+                v = fmaf(cA, mv[i], v) + cG;
+                if (u * VEC + i == am) v += cM;
+                ov[i] = v;
+                racc[i] = fmaf(cA, xv[i], racc[i]);
+            }
+            stv<T, VEC, true>(dx + base + (size_t)c * sh.S, ov);
+        }
+    }
+    if (!has_mask || dmask == nullptr) return;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) sh_r[w][lane * VEC + i] = racc[i];
+    __syncthreads();
+    const float kb = bs.kb[b];
+    for (int e = threadIdx.x; e < 32 * VEC; e += kBlock) {
+        const int p = tile * 32 * VEC + e;
+        if (p >= sh.S) continue;
+        float r = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kWarpsPerBlock; ++j) r += sh_r[j][e];
+        const size_t o = (size_t)b * sh.S + p;
+        float dm = (r - kb) + bs.dcat[2 * plane + o];
+        if (sh.sigmoid_mask()) {
+            const float m = ctx.m[o];
+            dm *= m * (1.0f - m);
+        }
+        if (sh.gate_clamp()) {
+            const float raw = to_f<TM>(mask[o]);
+            if (!(raw >= 0.0f && raw <= 1.0f)) dm = 0.0f;
+        }
+        dmask[o] = from_f<TM>(dm);
+    }
+}
+
+// ------------------------------------------------------------------ B6
+__global__ void __launch_bounds__(kBlock) bwd_wgrad_kernel(Shape sh, Ctx ctx, BwdScratch bs, mga_cbam_grads gp, int nConvCta) {
+    const int C = sh.C, Hd = sh.hidden, B = sh.B;
+    const int n_w1 = Hd * C, n_b1 = Hd, n_w2 = C * Hd, n_b2 = C, n_sam = 3 * sh.k * sh.k;
+    const int total = n_w1 + n_b1 + n_w2 + n_b2 + n_sam + 1;
+    int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= total) return;
+    if (i < n_w1) {  // dW1[j][c] = sum_b dha[b][j] avg[b][c] + dhm[b][j] mx[b][c]
+        const int j = i / C, c = i % C;
+        float acc = 0.0f;
+        for (int b = 0; b < B; ++b)
+            acc = fmaf(bs.dha[b * Hd + j], ctx.avg[b * C + c], fmaf(bs.dhm[b * Hd + j], ctx.mx[b * C + c], acc));
+        gp.w1[i] = acc;
+        return;
+    }
+    i -= n_w1;
+    if (i < n_b1) {
+        float acc = 0.0f;
+        for (int b = 0; b < B; ++b) acc += bs.dha[b * Hd + i] + bs.dhm[b * Hd + i];
+        gp.b1[i] = acc;
+        return;
+    }
+    i -= n_b1;
+    if (i < n_w2) {  // dW2[c][j] = sum_b dz[b][c] (ha + hm)[b][j]
+        const int c = i / Hd, j = i % Hd;
+        float acc = 0.0f;
+        for (int b = 0; b < B; ++b) acc = fmaf(bs.dz[b * C + c], ctx.ha[b * Hd + j] + ctx.hm[b * Hd + j], acc);
+        gp.w2[i] = acc;
+        return;
+    }
+    i -= n_w2;
+    if (i < n_b2) {
+        float acc = 0.0f;
+        for (int b = 0; b < B; ++b) acc += bs.dz[b * C + i];
+        gp.b2[i] = 2.0f * acc;
+        return;
+    }
+    i -= n_b2;
+    constexpr int kStride = 3 * kMaxK * kMaxK + 1;
+    if (i < n_sam) {
+        float acc = 0.0f;
+        for (int t = 0; t < nConvCta; ++t) acc += bs.convpart[(size_t)t * kStride + i];
+        gp.wsam[i] = acc;
+        return;
+    }
+    // d beta = sigmoid(beta) * d alpha ; d alpha = sum_p a_p T_p (B2) + per-sample pieces (B4)
+    float acc = 0.0f;
+    for (int t = 0; t < nConvCta; ++t) acc += bs.convpart[(size_t)t * kStride + (kStride - 1)];
+    for (int b = 0; b < B; ++b) acc += bs.alphapart[b];
+    gp.beta[0] = ctx.consts[3] * acc;
+}
+
+}  // namespace mga

@@ -1,0 +1,278 @@
+// cbam_fwd.cuh -- forward kernels of the split (one kernel per phase) path.
+//
+// Phases (reference lines in mga_yolo/nn/modules/masked_cbam.py):
+//   F0 mask_prep     m = sigmoid(clamp(mask)), sum(m), use/den        :93-99 (+ probmaskgater.py:77)
+//   F1 cam_pool      per (b,c): sum x*m, sum x, masked max + arg max  :100-101,116-117
+//   F2 cam_mlp       blend/fall-back, shared MLP, sigmoid -> s        :102,118-121,128-129
+//   F3 sam_reduce    per pixel: max_c / mean_c of x*q                 :135-136
+//   F4 sam_conv      a = sigmoid(conv7x7([pmax,pavg,m]))              :146-147
+//   F5 rescale       out = x*(k0 + k1*gate)                           :130,148,166-171
+#pragma once
+#include "common.cuh"
+
+namespace mga {
+
+// ------------------------------------------------------------------ F0
+template <typename TM>
+__global__ void __launch_bounds__(kBlock) mask_prep_kernel(const TM* __restrict__ mask, Shape sh, Ctx ctx) {
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    const int S = sh.S;
+    const TM* mp = mask + (size_t)b * S;
+    float* mo = ctx.m + (size_t)b * S;
+    float acc = 0.0f;
+    for (int p = threadIdx.x; p < S; p += kBlock) {
+        float v = to_f<TM>(mp[p]);
+        if (sh.gate_clamp()) v = fminf(fmaxf(v, 0.0f), 1.0f);
+        if (sh.sigmoid_mask()) v = sigmoidf_acc(v);
+        mo[p] = v;
+        acc += v;
+    }
+    const float tot = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        ctx.msum[b] = tot;
+        ctx.use[b] = (tot / (float)S >= sh.tiny_thr) ? 1.0f : 0.0f;
+        ctx.den[b] = fmaxf(tot, sh.eps);
+    }
+}
+
+// ------------------------------------------------------------------ F1
+// LANES threads cooperate on one (b,c) plane; 256/LANES planes per CTA.
+template <typename T, int VEC, int LANES>
+__global__ void __launch_bounds__(kBlock) cam_pool_kernel(const T* __restrict__ x, Shape sh, Ctx ctx, FwdScratch fs) {
+    constexpr int kGroups = kBlock / LANES;
+    const int grp = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+    const int planes = sh.B * sh.C;
+    int pl = blockIdx.x * kGroups + grp;
+    const bool active = pl < planes;
+    if (!active) pl = planes - 1;  // keep every lane alive for the shuffles
+    const int b = pl / sh.C;
+    const int U = sh.S / VEC;
+    const T* xp = x + (size_t)pl * sh.S;
+    const float* mp = ctx.m + (size_t)b * sh.S;
+    const bool has_mask = sh.has_mask();
+
+    float sxm = 0.0f, sx = 0.0f, best = -INFINITY;
+    int bidx = -1;
+#pragma unroll 4
+    for (int u = lane; u < U; u += LANES) {
+        float v[VEC], mv[VEC];
+        ldv<T, VEC>(xp + (size_t)u * VEC, v);
+        if (has_mask) {
+            ldf<VEC>(mp + (size_t)u * VEC, mv);
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) mv[i] = 1.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            sx += v[i];
+            sxm = fmaf(v[i], mv[i], sxm);
+            const bool ok = has_mask ? (mv[i] > 0.5f) : true;
+            if (ok && v[i] > best) { best = v[i]; bidx = u * VEC + i; }
+        }
+    }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o, LANES);
+        sxm += __shfl_xor_sync(0xffffffffu, sxm, o, LANES);
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o, LANES);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o, LANES);
+        // larger value wins; on a tie the lower pixel index wins (first maximum in scan order)
+        const bool take = (oi >= 0) && (bidx < 0 || ob > best || (ob == best && oi < bidx));
+        if (take) { best = ob; bidx = oi; }
+    }
+    if (active && lane == 0) {
+        fs.sxm[pl] = sxm;
+        fs.sx[pl] = sx;
+        fs.best[pl] = best;
+        fs.bidx[pl] = bidx;
+    }
+}
+
+// ------------------------------------------------------------------ F2 (one CTA per sample)
+__global__ void __launch_bounds__(kBlock) cam_mlp_kernel(Shape sh, mga_cbam_params prm, Ctx ctx, FwdScratch fs) {
+    extern __shared__ float smem[];
+    const int C = sh.C, Hd = sh.hidden, b = blockIdx.x;
+    float* s_avg = smem;            // C
+    float* s_mx = s_avg + C;        // C
+    float* s_ha = s_mx + C;         // Hd
+    float* s_hm = s_ha + Hd;        // Hd
+    const bool has_mask = sh.has_mask();
+    const float use = has_mask ? ctx.use[b] : 0.0f;
+    const float den = has_mask ? ctx.den[b] : 1.0f;
+    const float invS = 1.0f / (float)sh.S;
+
+    for (int c = threadIdx.x; c < C; c += kBlock) {
+        const int i = b * C + c;
+        const float G = fs.sx[i] * invS;
+        const float A = has_mask ? fs.sxm[i] / den : G;
+        const float avg = has_mask ? (A * use + G * (1.0f - use)) : G;
+        const int bi = fs.bidx[i];
+        const bool dead = bi < 0;  // no pixel with m > 0.5 (masked_cbam.py:118-121)
+        const float mx = dead ? G : fs.best[i];
+        s_avg[c] = avg;
+        s_mx[c] = mx;
+        ctx.avg[i] = avg;
+        ctx.mx[i] = mx;
+        ctx.apool[i] = A;
+        ctx.amax[i] = dead ? -1 : bi;
+    }
+    if (b == 0 && threadIdx.x == 0) {
+        const float beta = prm.beta[0];
+        const float alpha = softplusf_acc(beta);
+        ctx.consts[0] = sh.pyramid_multiply() ? 0.0f : 1.0f - alpha;
+        ctx.consts[1] = alpha;
+        ctx.consts[2] = alpha;
+        ctx.consts[3] = sigmoidf_acc(beta);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int j = w; j < Hd; j += kWarpsPerBlock) {
+        const float* wr = prm.w1 + (size_t)j * C;
+        float pa = 0.0f, pm = 0.0f;
+        for (int c = lane; c < C; c += 32) {
+            const float wv = __ldg(wr + c);
+            pa = fmaf(wv, s_avg[c], pa);
+            pm = fmaf(wv, s_mx[c], pm);
+        }
+        pa = warp_sum(pa);
+        pm = warp_sum(pm);
+        if (lane == 0) {
+            const float bb = prm.b1[j];
+            const float ha = fmaxf(pa + bb, 0.0f), hm = fmaxf(pm + bb, 0.0f);
+            s_ha[j] = ha;
+            s_hm[j] = hm;
+            ctx.ha[b * Hd + j] = ha;
+            ctx.hm[b * Hd + j] = hm;
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kBlock) {
+        const float* wr = prm.w2 + (size_t)c * Hd;
+        float za = 0.0f, zm = 0.0f;
+        for (int j = 0; j < Hd; ++j) {
+            const float wv = __ldg(wr + j);
+            za = fmaf(wv, s_ha[j], za);
+            zm = fmaf(wv, s_hm[j], zm);
+        }
+        const float bb = prm.b2[c];
+        const float z = (za + bb) + (zm + bb);  // b2 enters twice (masked_cbam.py:128)
+        ctx.s[b * C + c] = sigmoidf_acc(z);
+    }
+}
+
+// ------------------------------------------------------------------ F3
+// CTA = (sample b, tile of 32 units); warp w owns channels w, w+8, ...; lanes own units.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBlock) sam_reduce_kernel(const T* __restrict__ x, Shape sh, Ctx ctx) {
+    __shared__ float sh_max[kWarpsPerBlock][32 * VEC];
+    __shared__ float sh_sum[kWarpsPerBlock][32 * VEC];
+    __shared__ int sh_idx[kWarpsPerBlock][32 * VEC];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int U = sh.S / VEC, C = sh.C;
+    const int u = blockIdx.x * 32 + lane;
+    const bool act = u < U;
+    const bool use_q = !sh.samcam_add();
+    const float* sp = ctx.s + (size_t)b * C;
+
+    float vmax[VEC], vsum[VEC];
+    int vidx[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { vmax[i] = -INFINITY; vsum[i] = 0.0f; vidx[i] = 0; }
+    if (act) {
+        const T* xp = x + ((size_t)b * C) * sh.S + (size_t)u * VEC;
+#pragma unroll 4
+        for (int c = w; c < C; c += kWarpsPerBlock) {
+            float v[VEC];
+            ldv<T, VEC>(xp + (size_t)c * sh.S, v);
+            const float q = use_q ? __ldg(sp + c) : 1.0f;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float y = v[i] * q;
+                vsum[i] += y;
+                if (y > vmax[i]) { vmax[i] = y; vidx[i] = c; }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        sh_max[w][lane * VEC + i] = vmax[i];
+        sh_sum[w][lane * VEC + i] = vsum[i];
+        sh_idx[w][lane * VEC + i] = vidx[i];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * VEC; e += kBlock) {
+        const int p = blockIdx.x * 32 * VEC + e;
+        if (p >= sh.S) continue;
+        float bm = sh_max[0][e], bs = sh_sum[0][e];
+        int bi = sh_idx[0][e];
+#pragma unroll
+        for (int j = 1; j < kWarpsPerBlock; ++j) {
+            const float om = sh_max[j][e];
+            const int oi = sh_idx[j][e];
+            bs += sh_sum[j][e];
+            if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }  // torch.max: first maximal channel
+        }
+        const size_t o = (size_t)b * sh.S + p;
+        ctx.pmax[o] = bm;
+        ctx.pavg[o] = bs / (float)C;
+        ctx.idx[o] = bi;
+    }
+}
+
+// ------------------------------------------------------------------ F4
+// 32x8 output tile per CTA, the three input planes (+halo, zero padded) staged in shared memory.
+__global__ void __launch_bounds__(kBlock) sam_conv_kernel(Shape sh, const float* __restrict__ wsam, Ctx ctx) {
+    __shared__ float tile[3][kConvTH + kMaxK - 1][kConvTW + kMaxK - 1 + 1];
+    __shared__ float wk[3 * kMaxK * kMaxK];
+    const int k = sh.k, pad = k / 2, H = sh.H, W = sh.W;
+    const int b = blockIdx.z, x0 = blockIdx.x * kConvTW, y0 = blockIdx.y * kConvTH;
+    const float* planes[3] = {ctx.pmax + (size_t)b * sh.S, ctx.pavg + (size_t)b * sh.S, ctx.m + (size_t)b * sh.S};
+    const bool has_mask = sh.has_mask();
+    for (int i = threadIdx.x; i < 3 * k * k; i += kBlock) wk[i] = wsam[i];
+    const int tw = kConvTW + k - 1, th = kConvTH + k - 1;
+    for (int i = threadIdx.x; i < 3 * tw * th; i += kBlock) {
+        const int pl = i / (tw * th), r = (i / tw) % th, c = i % tw;
+        const int yy = y0 + r - pad, xx = x0 + c - pad;
+        float v = 0.0f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W && (pl < 2 || has_mask)) v = planes[pl][yy * W + xx];
+        tile[pl][r][c] = v;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x % kConvTW, ty = threadIdx.x / kConvTW;
+    const int ox = x0 + tx, oy = y0 + ty;
+    if (ox < W && oy < H) {
+        float acc = 0.0f;
+        for (int pl = 0; pl < 3; ++pl)
+            for (int i = 0; i < k; ++i)
+#pragma unroll 7
+                for (int j = 0; j < k; ++j) acc = fmaf(tile[pl][ty + i][tx + j], wk[(pl * k + i) * k + j], acc);
+        ctx.a[(size_t)b * sh.S + oy * W + ox] = sigmoidf_acc(acc);
+    }
+}
+
+// ------------------------------------------------------------------ F5
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBlock) rescale_kernel(const T* __restrict__ x, T* __restrict__ out, Shape sh, Ctx ctx) {
+    const int U = sh.S / VEC;
+    const size_t total = (size_t)sh.B * sh.C * U;
+    const float k0 = ctx.consts[0], k1 = ctx.consts[1];
+    const bool add = sh.samcam_add();
+    for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < total; i += (size_t)gridDim.x * kBlock) {
+        const int pl = (int)(i / U), u = (int)(i % U);
+        const int b = pl / sh.C;
+        float v[VEC], av[VEC];
+        ldv<T, VEC, true>(x + i * VEC, v);
+        ldf<VEC>(ctx.a + (size_t)b * sh.S + (size_t)u * VEC, av);
+        const float s = __ldg(ctx.s + pl);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const float gate = add ? (s + av[e]) : (s * av[e]);
+            v[e] = v[e] * fmaf(k1, gate, k0);
+        }
+        stv<T, VEC, true>(out + i * VEC, v);
+    }
+}
+
+}  // namespace mga

@@ -1,0 +1,232 @@
+// common.cuh -- shared device helpers for the mask-guided CBAM kernels (sm_100a).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <type_traits>
+
+#include "mga_cbam.h"
+
+namespace mga {
+
+constexpr int kWarp = 32;
+constexpr int kBlock = 256;          // threads per CTA for the streaming kernels
+constexpr int kWarpsPerBlock = kBlock / kWarp;
+constexpr int kSMs = 148;            // B200
+constexpr int kMaxK = 7;             // largest spatial-attention kernel that is built
+constexpr int kConvTW = 32, kConvTH = 8;  // output tile of the plane-convolution kernels
+
+// ---------------------------------------------------------------- element conversion
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+template <typename T> struct VecOf { static constexpr int V = 16 / sizeof(T); };  // elements per 128-bit access
+
+// 128-bit (or scalar) global load of VEC consecutive elements into fp32 registers.
+// kStream = true uses the no-L1-allocate path for data that is touched once.
+template <typename T, int VEC, bool kStream = false>
+__device__ __forceinline__ void ldv(const T* __restrict__ p, float (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+        v[0] = to_f<T>(p[0]);
+    } else if constexpr (sizeof(T) == 4) {
+        static_assert(VEC == 4, "fp32 vector is 4 wide");
+        float4 t;
+        if constexpr (kStream) {
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(p));
+        } else {
+            t = __ldg(reinterpret_cast<const float4*>(p));
+        }
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        static_assert(VEC == 8, "16-bit vector is 8 wide");
+        uint4 t;
+        if constexpr (kStream) {
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+        } else {
+            t = __ldg(reinterpret_cast<const uint4*>(p));
+        }
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) {
+                v[2 * i] = __uint_as_float(w[i] << 16);
+                v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+            } else {
+                const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+                const float2 f = __half22float2(h);
+                v[2 * i] = f.x;
+                v[2 * i + 1] = f.y;
+            }
+        }
+    }
+}
+
+template <typename T, int VEC, bool kStream = false>
+__device__ __forceinline__ void stv(T* __restrict__ p, const float (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+        p[0] = from_f<T>(v[0]);
+    } else if constexpr (sizeof(T) == 4) {
+        float4 t = make_float4(v[0], v[1], v[2], v[3]);
+        if constexpr (kStream) __stcs(reinterpret_cast<float4*>(p), t);
+        else *reinterpret_cast<float4*>(p) = t;
+    } else {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                w[i] = *reinterpret_cast<uint32_t*>(&h);
+            } else {
+                __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+        }
+        uint4 t = make_uint4(w[0], w[1], w[2], w[3]);
+        if constexpr (kStream) __stcs(reinterpret_cast<uint4*>(p), t);
+        else *reinterpret_cast<uint4*>(p) = t;
+    }
+}
+
+// fp32 / int32 planes (mask, attention map, indices) read VEC at a time
+template <int VEC>
+__device__ __forceinline__ void ldf(const float* __restrict__ p, float (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+        v[0] = __ldg(p);
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC / 4; ++i) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void ldi(const int* __restrict__ p, int (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+        v[0] = __ldg(p);
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC / 4; ++i) {
+            const int4 t = __ldg(reinterpret_cast<const int4*>(p) + i);
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void stf(float* __restrict__ p, const float (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+        p[0] = v[0];
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC / 4; ++i)
+            reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void sti(int* __restrict__ p, const int (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+        p[0] = v[0];
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC / 4; ++i)
+            reinterpret_cast<int4*>(p)[i] = make_int4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+}
+
+// ---------------------------------------------------------------- math
+__device__ __forceinline__ float sigmoidf_acc(float v) { return 1.0f / (1.0f + expf(-v)); }  // same form ATen uses
+__device__ __forceinline__ float softplusf_acc(float b) { return b > 20.0f ? b : log1pf(expf(b)); }  // F.softplus threshold=20
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum for kBlock threads; result valid in every thread
+__device__ __forceinline__ float block_sum(float v, float* sh /* >= 32 floats */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    float r = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0.0f;
+    r = warp_sum(r);
+    return r;
+}
+
+// ---------------------------------------------------------------- shapes, context and scratch layouts
+struct Shape {
+    int B, C, H, W, S, hidden, k;
+    int flags;
+    float tiny_thr, eps;
+    __host__ __device__ bool has_mask() const { return flags & MGA_HAS_MASK; }
+    __host__ __device__ bool sigmoid_mask() const { return flags & MGA_SIGMOID_MASK; }
+    __host__ __device__ bool gate_clamp() const { return flags & MGA_GATE_CLAMP; }
+    __host__ __device__ bool samcam_add() const { return flags & MGA_SAMCAM_ADD; }
+    __host__ __device__ bool pyramid_multiply() const { return flags & MGA_PYRAMID_MULTIPLY; }
+};
+
+// saved-for-backward context (device pointers into the caller's ctx buffer)
+struct Ctx {
+    float* consts;  // [0]=k0 [1]=k1 [2]=alpha [3]=sigmoid(beta)
+    float* m;       // (B,S) mask after clamp/sigmoid; zeros without a mask
+    float* a;       // (B,S) spatial attention map
+    float* pmax;    // (B,S) channel max of x*q
+    float* pavg;    // (B,S) channel mean of x*q
+    int* idx;       // (B,S) arg max channel
+    float* s;       // (B,C) channel attention
+    float* avg;     // (B,C) pooled descriptor 1 (after fall-back blend)
+    float* mx;      // (B,C) pooled descriptor 2 (after fall-back)
+    float* apool;   // (B,C) masked average A (before blend)
+    int* amax;      // (B,C) arg max pixel of the masked max, -1 when no pixel was valid
+    float* use;     // (B)   1 when mean(mask) >= tiny_thr
+    float* den;     // (B)   clamp_min(sum(mask), eps)
+    float* msum;    // (B)   sum(mask)
+    float* ha;      // (B,hidden) relu(W1 avg + b1)
+    float* hm;      // (B,hidden) relu(W1 mx + b1)
+};
+
+struct FwdScratch {
+    float* sxm;   // (B,C) sum x*m
+    float* sx;    // (B,C) sum x
+    float* best;  // (B,C) masked max
+    int* bidx;    // (B,C) its pixel
+};
+
+struct BwdScratch {
+    float* T;        // (B,S)   sum_c g*x*q
+    float* dcat;     // (3,B,S) gradient wrt [pmax, pavg, m] planes
+    float* epart;    // (B,nT,C) partial sum_p g*x*(a or 1)
+    float* gxpart;   // (B,nT,C) partial sum_p g*x
+    float* qpart;    // (B,nT,C) partial sum_p x*dy1            (multiply mode)
+    float* cA;       // (B,C) use*davg/den
+    float* cG;       // (B,C) ((1-use)*davg + dead*dmx)/S
+    float* cM;       // (B,C) (1-dead)*dmx
+    float* kb;       // (B)   sum_c cA*A*[msum>=eps]
+    float* dz;       // (B,C)
+    float* dha;      // (B,hidden)
+    float* dhm;      // (B,hidden)
+    float* convpart; // (nConvCta, 3*k*k + 1)  dWsam partials + sum a*T
+    float* alphapart;// (B) per-sample pieces of d alpha that come from per-channel sums
+};
+
+// records a message for mga_last_error() and returns `code` (defined in mga_cbam.cu)
+int fail(int code, const char* fmt, ...);
+
+inline __host__ size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+}  // namespace mga

@@ -1,0 +1,161 @@
+"""`MaskGuidedCBAM` -- the nn.Module face of the B200 mask-guided CBAM path.
+
+Drop-in for the reference block `MaskCBAM` (mga_yolo/nn/modules/masked_cbam.py:10-174):
+same constructor arguments, same state_dict keys and shapes
+(`beta`, `cam_mlp.0.{weight,bias}`, `cam_mlp.2.{weight,bias}`, `sam_conv.weight`), same
+`forward(x)` polymorphism (`Tensor` or `[feature, mask]`), same `.alpha` property that
+MGATrainer logs (mga_yolo/model/trainer.py:274-321).  The north-star keyword names
+(`reduction_ratio`, `sam_cam_fusion`, `mga_pyramid_fusion`) are accepted too.
+
+The forward/backward math does not live here: it is one call into the CUDA library
+through `ops.mask_guided_cbam`.  CPU tensors raise -- there is no fallback.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Sequence, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, ops
+
+_GATE_MODES = ("deterministic", "gumbel", "hard_st", "bernoulli_detach")
+# sam_cam_fusion: how the channel gate s and the spatial gate a combine
+#   multiply -> x*s*a with a computed from x*s            (== reference, masked_cbam.py:166-168)
+#   add      -> x*s + x*a' with a' computed from x        (build-side definition, parity unpinned)
+# mga_pyramid_fusion: how the refined feature re-enters the pyramid
+#   add      -> x + alpha*(R - x)                         (== reference, masked_cbam.py:169-171)
+#   multiply -> alpha*R                                   (build-side definition, parity unpinned)
+SAM_CAM_FUSIONS = ("multiply", "add")
+PYRAMID_FUSIONS = ("add", "multiply")
+
+
+class MaskGate(nn.Module):
+    """Mask pre-gate used when the MGA_PROB_MODE environment switch is on
+    (probmaskgater.py:27-98).  The deterministic branch (eval mode, or mode
+    'deterministic') is only a clamp to [0,1] and is fused into the CUDA kernels; the
+    sampling branches run here as a few elementwise torch ops on the (B,1,H,W) map."""
+
+    def __init__(self, mode: str = "gumbel", tau: float = 1.0, p_min: float = 0.0, threshold: float = 0.5):
+        super().__init__()
+        if tau <= 0:
+            raise ValueError("tau must be > 0")
+        self.mode, self.tau, self.p_min, self.threshold = mode, float(tau), float(p_min), float(threshold)
+
+    def is_deterministic(self) -> bool:
+        return (not self.training) or self.mode == "deterministic" or self.mode not in _GATE_MODES
+
+    def sample(self, mask: torch.Tensor) -> torch.Tensor:
+        p = (mask if mask.dim() == 4 else mask.unsqueeze(1)).float().clamp(0.0, 1.0)
+        if self.p_min > 0:
+            p = p.clamp_min(self.p_min)
+        if self.mode == "bernoulli_detach":
+            return torch.bernoulli(p.detach())
+        lo, hi = 1e-6, 1.0 - 1e-6
+        u1 = torch.rand_like(p).clamp_(lo, hi)
+        u2 = torch.rand_like(p).clamp_(lo, hi)
+        noise = torch.log(-torch.log(u2)) - torch.log(-torch.log(u1))  # difference of two Gumbels = logistic
+        pc = p.clamp(lo, hi)
+        soft = torch.sigmoid((torch.log(pc) - torch.log1p(-pc) + noise) / self.tau)
+        if self.mode == "hard_st":
+            return (soft > self.threshold).float() + (soft - soft.detach())
+        return soft
+
+
+class MaskGuidedCBAM(nn.Module):
+    def __init__(
+        self,
+        channels: int,
+        r: Optional[int] = None,
+        spatial_k: int = 7,
+        use_sigmoid_mask: bool = True,
+        tiny_mask_thr: float = 1e-4,
+        eps: float = 1e-6,
+        *,
+        reduction_ratio: Optional[int] = None,
+        sam_cam_fusion: str = "multiply",
+        mga_pyramid_fusion: str = "add",
+    ) -> None:
+        super().__init__()
+        if r is not None and reduction_ratio is not None and r != reduction_ratio:
+            raise ValueError("pass either r or reduction_ratio, not two different values")
+        r = reduction_ratio if r is None and reduction_ratio is not None else (16 if r is None else r)
+        assert r > 0 and channels > 0
+        if sam_cam_fusion not in SAM_CAM_FUSIONS:
+            raise ValueError(f"sam_cam_fusion must be one of {SAM_CAM_FUSIONS} (concat: not built yet), got {sam_cam_fusion!r}")
+        if mga_pyramid_fusion not in PYRAMID_FUSIONS:
+            raise ValueError(f"mga_pyramid_fusion must be one of {PYRAMID_FUSIONS} (concat: not built yet), got {mga_pyramid_fusion!r}")
+        self.C = channels
+        self.r = r
+        self.k = spatial_k if spatial_k % 2 == 1 else spatial_k + 1
+        self.use_sigmoid_mask = use_sigmoid_mask
+        self.tiny_thr = tiny_mask_thr
+        self.eps = eps
+        self.sam_cam_fusion = sam_cam_fusion
+        self.mga_pyramid_fusion = mga_pyramid_fusion
+
+        # parameter containers only -- created in the reference's order (masked_cbam.py:53-64) so that
+        # the same torch seed gives the same initial weights; they are never called as layers.
+        hidden = max(1, channels // r)
+        self.cam_mlp = nn.Sequential(nn.Linear(channels, hidden, bias=True), nn.ReLU(inplace=True), nn.Linear(hidden, channels, bias=True))
+        self.sam_conv = nn.Conv2d(3, 1, kernel_size=self.k, padding=self.k // 2, bias=False)
+        self.beta = nn.Parameter(torch.zeros((), dtype=torch.float32))
+
+        # any non-empty MGA_PROB_MODE string switches the gate on, like os.getenv(..., False) does (masked_cbam.py:67)
+        if os.getenv("MGA_PROB_MODE", False):
+            approach = os.getenv("MGA_PROB_APPROACH", "gumbel")
+            if approach not in _GATE_MODES:
+                raise ValueError(f"MGA_PROB_APPROACH must be one of {set(_GATE_MODES)}, got {approach}")
+            self.gater = MaskGate(mode=approach, tau=1.0, p_min=0.0, threshold=0.5)
+
+    @property
+    def alpha(self) -> torch.Tensor:
+        return F.softplus(self.beta)
+
+    def _flags(self) -> int:
+        f = 0
+        if self.use_sigmoid_mask:
+            f |= _lib.SIGMOID_MASK
+        if self.sam_cam_fusion == "add":
+            f |= _lib.SAMCAM_ADD
+        if self.mga_pyramid_fusion == "multiply":
+            f |= _lib.PYRAMID_MULTIPLY
+        return f
+
+    def forward(self, x: Union[torch.Tensor, Sequence[torch.Tensor]]) -> torch.Tensor:
+        if isinstance(x, (list, tuple)):
+            assert len(x) == 2, "MaskGuidedCBAM expects [feature, mask]"
+            feat, mask = x
+        else:
+            feat, mask = x, None
+        assert isinstance(feat, torch.Tensor) and feat.dim() == 4
+        flags = self._flags()
+        if mask is not None:
+            if os.getenv("MGA_PROB_MODE", False) and hasattr(self, "gater"):
+                if self.gater.is_deterministic():
+                    flags |= _lib.GATE_CLAMP  # clamp fused into the kernels
+                    if self.gater.p_min > 0:
+                        mask = mask.float().clamp_min(self.gater.p_min)
+                else:
+                    mask = self.gater.sample(mask)
+            if not mask.is_floating_point():
+                mask = mask.to(torch.float32)  # binary uint8/bool maps (use_sigmoid_mask=False)
+            elif mask.dtype == torch.float64:
+                mask = mask.float()
+        lin1, lin2 = self.cam_mlp[0], self.cam_mlp[2]
+        return ops.mask_guided_cbam(
+            feat, mask, lin1.weight, lin1.bias, lin2.weight, lin2.bias, self.sam_conv.weight, self.beta,
+            flags=flags, tiny_mask_thr=self.tiny_thr, eps=self.eps,
+        )
+
+    def extra_repr(self) -> str:  # pragma: no cover
+        return (f"channels={self.C}, r={self.r}, spatial_k={self.k}, use_sigmoid_mask={self.use_sigmoid_mask}, "
+                f"tiny_mask_thr={self.tiny_thr}, eps={self.eps}, sam_cam_fusion={self.sam_cam_fusion}, "
+                f"mga_pyramid_fusion={self.mga_pyramid_fusion}, alpha={self.alpha.item():.4f}")
+
+
+class MaskCBAM(MaskGuidedCBAM):
+    """Name used by the reference's model YAML / parse_model (configs/models/yolov8_cbam.yaml:67-72,
+    ultralytics/nn/tasks.py:1733-1739)."""

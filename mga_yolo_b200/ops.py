@@ -1,0 +1,189 @@
+"""Torch-facing operators of the mask-guided CBAM path.
+
+`torch.ops.mga.cbam_fwd / cbam_bwd / mask_downsample` are registered for the CUDA
+dispatch key only, so CPU tensors fail inside the dispatcher ("no CPU fallback").
+Each op is a thin shim: it allocates outputs with the caching allocator and hands raw
+device pointers + the current stream to the C ABI (include/mga_cbam.h).
+
+Replaces, on the reference side, the body of MaskCBAM.forward
+(mga_yolo/nn/modules/masked_cbam.py:154-171) and its autograd graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from functools import lru_cache
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
+
+_LIBDEF = torch.library.Library("mga", "DEF")
+_LIBDEF.define(
+    "cbam_fwd(Tensor x, Tensor? mask, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor wsam, Tensor beta, "
+    "int flags, float tiny_thr, float eps) -> (Tensor, Tensor)"
+)
+_LIBDEF.define(
+    "cbam_bwd(Tensor grad_out, Tensor x, Tensor? mask, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor wsam, Tensor beta, "
+    "Tensor ctx, int flags, float tiny_thr, float eps, bool need_mask_grad) -> (Tensor, Tensor?, Tensor)"
+)
+_LIBDEF.define("mask_downsample(Tensor src, int stride, int method, float thresh, bool close3x3, bool out_float) -> Tensor")
+
+
+@lru_cache(maxsize=256)
+def _desc(B, Cc, H, W, hidden, k, dt, mdt, flags, tiny, eps):
+    d = _lib.Desc(B, Cc, H, W, hidden, k, dt, mdt, flags, tiny, eps)
+    lib = _lib.load()
+    cb, sb = C.c_size_t(0), C.c_size_t(0)
+    _lib.check(lib.mga_cbam_workspace(C.byref(d), C.byref(cb), C.byref(sb)), "mga_cbam_workspace")
+    return d, int(cb.value), int(sb.value)
+
+
+def _prep(x, mask, w1, wsam, flags, tiny, eps):
+    if x.dim() != 4:
+        raise RuntimeError(f"feature map must be (B,C,H,W), got {tuple(x.shape)}")
+    if x.dtype not in _DT:
+        raise RuntimeError(f"unsupported feature dtype {x.dtype} (float32 / bfloat16 / float16)")
+    B, Cc, H, W = x.shape
+    hidden, k = w1.shape[0], wsam.shape[-1]
+    if tuple(w1.shape) != (hidden, Cc) or tuple(wsam.shape) != (1, 3, k, k):
+        raise RuntimeError(f"parameter shapes do not match C={Cc}: w1 {tuple(w1.shape)}, wsam {tuple(wsam.shape)}")
+    mdt = _lib.F32
+    if mask is not None:
+        if mask.dtype not in _DT:
+            raise RuntimeError(f"unsupported mask dtype {mask.dtype}")
+        if mask.numel() != B * H * W or tuple(mask.shape[-2:]) != (H, W):
+            # the reference fails in mask.expand(b,c,h,w) (masked_cbam.py:96) for any other size
+            raise RuntimeError(f"mask {tuple(mask.shape)} does not match feature map {tuple(x.shape)}")
+        mdt = _DT[mask.dtype]
+        flags |= _lib.HAS_MASK
+    else:
+        flags &= ~_lib.HAS_MASK
+    return _desc(B, Cc, H, W, hidden, k, _DT[x.dtype], mdt, flags, float(tiny), float(eps))
+
+
+def _params(w1, b1, w2, b2, wsam, beta):
+    ts = [t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous() for t in (w1, b1, w2, b2, wsam, beta)]
+    return ts, _lib.Params(*(t.data_ptr() for t in ts))
+
+
+def _stream(x) -> int:
+    return torch.cuda.current_stream(x.device).cuda_stream
+
+
+def _cbam_fwd_cuda(x, mask, w1, b1, w2, b2, wsam, beta, flags, tiny_thr, eps):
+    lib = _lib.load()
+    x = x.contiguous()
+    mask = None if mask is None else mask.contiguous()
+    d, ctx_bytes, scratch_bytes = _prep(x, mask, w1, wsam, flags, tiny_thr, eps)
+    keep, prm = _params(w1, b1, w2, b2, wsam, beta)
+    with torch.cuda.device(x.device):
+        out = torch.empty_like(x)
+        ctx = torch.empty(ctx_bytes, dtype=torch.uint8, device=x.device)
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=x.device)
+        rc = lib.mga_cbam_forward(C.byref(d), x.data_ptr(), None if mask is None else mask.data_ptr(), C.byref(prm),
+                                  out.data_ptr(), ctx.data_ptr(), scratch.data_ptr(), _stream(x))
+    _lib.check(rc, "mga_cbam_forward")
+    return out, ctx
+
+
+def _cbam_bwd_cuda(grad_out, x, mask, w1, b1, w2, b2, wsam, beta, ctx, flags, tiny_thr, eps, need_mask_grad):
+    lib = _lib.load()
+    x = x.contiguous()
+    grad_out = grad_out.contiguous()
+    if grad_out.dtype != x.dtype:
+        grad_out = grad_out.to(x.dtype)
+    mask = None if mask is None else mask.contiguous()
+    d, _, scratch_bytes = _prep(x, mask, w1, wsam, flags, tiny_thr, eps)
+    keep, prm = _params(w1, b1, w2, b2, wsam, beta)
+    hidden, Cc, k = w1.shape[0], x.shape[1], wsam.shape[-1]
+    n = [hidden * Cc, hidden, Cc * hidden, Cc, 3 * k * k, 1]
+    with torch.cuda.device(x.device):
+        dx = torch.empty_like(x)
+        dmask = torch.empty_like(mask) if (mask is not None and need_mask_grad) else None
+        flat = torch.empty(sum(n), dtype=torch.float32, device=x.device)
+        offs = [0]
+        for v in n:
+            offs.append(offs[-1] + v)
+        gp = _lib.Grads(*(flat.data_ptr() + 4 * o for o in offs[:-1]))
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=x.device)
+        rc = lib.mga_cbam_backward(C.byref(d), x.data_ptr(), None if mask is None else mask.data_ptr(), grad_out.data_ptr(),
+                                   C.byref(prm), ctx.data_ptr(), dx.data_ptr(), None if dmask is None else dmask.data_ptr(),
+                                   C.byref(gp), scratch.data_ptr(), _stream(x))
+    _lib.check(rc, "mga_cbam_backward")
+    return dx, dmask, flat
+
+
+def _mask_downsample_cuda(src, stride, method, thresh, close3x3, out_float):
+    lib = _lib.load()
+    if src.dtype != torch.uint8:
+        raise RuntimeError("mask_downsample expects a uint8 {0,1} mask (mask_utils.py:26-27,81-82 binarise first)")
+    squeeze = src.dim() == 2
+    s3 = (src[None] if squeeze else src).contiguous()
+    if s3.dim() != 3:
+        raise RuntimeError(f"mask must be (H,W) or (B,H,W), got {tuple(src.shape)}")
+    B, H, W = s3.shape
+    if stride <= 1:
+        out = s3.float() if out_float else s3.clone()
+        return out[0] if squeeze else out
+    nh, nw = -(-H // stride), -(-W // stride)
+    with torch.cuda.device(src.device):
+        out = torch.empty((B, nh, nw), dtype=torch.float32 if out_float else torch.uint8, device=src.device)
+        tmp = torch.empty(2 * B * nh * nw, dtype=torch.uint8, device=src.device) if close3x3 else None
+        rc = lib.mga_mask_downsample(s3.data_ptr(), out.data_ptr(), None if tmp is None else tmp.data_ptr(), B, H, W, stride,
+                                     method, float(thresh), int(close3x3), _lib.F32 if out_float else _lib.U8, _stream(src))
+    _lib.check(rc, "mga_mask_downsample")
+    return out[0] if squeeze else out
+
+
+_LIBIMPL = torch.library.Library("mga", "IMPL")
+_LIBIMPL.impl("cbam_fwd", _cbam_fwd_cuda, "CUDA")
+_LIBIMPL.impl("cbam_bwd", _cbam_bwd_cuda, "CUDA")
+_LIBIMPL.impl("mask_downsample", _mask_downsample_cuda, "CUDA")
+
+
+class _CbamFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mask, w1, b1, w2, b2, wsam, beta, flags, tiny_thr, eps):
+        if not x.is_cuda:
+            raise RuntimeError("mga_yolo_b200: the mask-guided CBAM path runs on CUDA tensors only (no CPU fallback)")
+        out, saved = torch.ops.mga.cbam_fwd(x, mask, w1, b1, w2, b2, wsam, beta, flags, tiny_thr, eps)
+        ctx.save_for_backward(x, mask, w1, b1, w2, b2, wsam, beta, saved)
+        ctx.cfg = (flags, tiny_thr, eps)
+        ctx.param_shapes = tuple(t.shape for t in (w1, b1, w2, b2, wsam, beta))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, mask, w1, b1, w2, b2, wsam, beta, saved = ctx.saved_tensors
+        flags, tiny_thr, eps = ctx.cfg
+        need_mask = mask is not None and ctx.needs_input_grad[1]
+        dx, dmask, flat = torch.ops.mga.cbam_bwd(grad_out, x, mask, w1, b1, w2, b2, wsam, beta, saved, flags, tiny_thr, eps, need_mask)
+        grads, o = [], 0
+        for shp in ctx.param_shapes:
+            n = 1
+            for v in shp:
+                n *= v
+            grads.append(flat[o:o + n].view(shp))
+            o += n
+        return (dx, dmask, *grads, None, None, None)
+
+
+def mask_guided_cbam(x: torch.Tensor, mask: Optional[torch.Tensor], w1, b1, w2, b2, wsam, beta, *, flags: int,
+                     tiny_mask_thr: float = 1e-4, eps: float = 1e-6) -> torch.Tensor:
+    """Functional entry: out = MaskCBAM([x, mask]) with the given parameters (autograd-aware)."""
+    return _CbamFn.apply(x, mask, w1, b1, w2, b2, wsam, beta, int(flags), float(tiny_mask_thr), float(eps))
+
+
+def ctx_view(x_shape: Tuple[int, int, int, int], dtype, hidden: int, k: int, flags: int, ctx: torch.Tensor, which: int,
+             tiny=1e-4, eps=1e-6, mask_dtype=torch.float32) -> torch.Tensor:
+    """Copy a small saved quantity out of a forward context (tests / logging): 0 s(B,C), 1 a(B,HW)."""
+    lib = _lib.load()
+    B, Cc, H, W = x_shape
+    d, _, _ = _desc(B, Cc, H, W, hidden, k, _DT[dtype], _DT[mask_dtype], flags, float(tiny), float(eps))
+    ptr, cnt = C.c_void_p(0), C.c_size_t(0)
+    _lib.check(lib.mga_cbam_ctx_view(C.byref(d), ctx.data_ptr(), which, C.byref(ptr), C.byref(cnt)), "mga_cbam_ctx_view")
+    off = (ptr.value - ctx.data_ptr())
+    return ctx[off:off + 4 * cnt.value].view(torch.float32).clone()

@@ -52,8 +52,8 @@ class CbamParams:
     wsam: torch.Tensor  # sam_conv.weight (1, 3, k, k)
     beta: torch.Tensor  # ()
 
-    def to(self, dtype) -> "CbamParams":
-        return CbamParams(*(t.detach().to(dtype) for t in (self.w1, self.b1, self.w2, self.b2, self.wsam, self.beta)))
+    def to(self, dtype=None, device=None) -> "CbamParams":
+        return CbamParams(*(t.detach().to(dtype=dtype, device=device) for t in (self.w1, self.b1, self.w2, self.b2, self.wsam, self.beta)))
 
     @staticmethod
     def from_state_dict(sd: Dict[str, torch.Tensor]) -> "CbamParams":
@@ -119,20 +119,20 @@ def cbam_forward(
         avg = A * use[:, None] + G * (1.0 - use[:, None])
         valid = m > 0.5  # masked_cbam.py:116
         low = _very_low(feature_dtype or dt)
-        xm = torch.where(valid[:, None, :], xf, torch.full((), low, dtype=dt))
+        xm = torch.where(valid[:, None, :], xf, torch.full((), low, dtype=dt, device=x.device))
         mraw, amax_hw = xm.max(dim=2)  # first max index (adaptive_max_pool2d scan order)
-        dead = torch.isclose(mraw, torch.full((), low, dtype=dt))  # masked_cbam.py:120
+        dead = torch.isclose(mraw, torch.full((), low, dtype=dt, device=x.device))  # masked_cbam.py:120
         mx = torch.where(dead, G, mraw)
     else:
-        m = torch.zeros(B, S, dtype=dt)
+        m = torch.zeros(B, S, dtype=dt, device=x.device)
         pre_gate = None
         G = xf.mean(dim=2)
         avg = G
         mx, amax_hw = xf.max(dim=2)
-        dead = torch.zeros(B, C, dtype=torch.bool)
-        use = torch.zeros(B, dtype=dt)
-        den = torch.ones(B, dtype=dt)
-        msum = torch.zeros(B, dtype=dt)
+        dead = torch.zeros(B, C, dtype=torch.bool, device=x.device)
+        use = torch.zeros(B, dtype=dt, device=x.device)
+        den = torch.ones(B, dtype=dt, device=x.device)
+        msum = torch.zeros(B, dtype=dt, device=x.device)
         A = G
 
     # shared MLP on both descriptors, summed (masked_cbam.py:128): b2 enters twice
@@ -155,7 +155,7 @@ def cbam_forward(
     else:
         gate = s[:, :, None] + a[:, None, :]
     alpha = F.softplus(p.beta)
-    k0 = (1.0 - alpha) if mga_pyramid_fusion == "add" else torch.zeros((), dtype=dt)
+    k0 = (1.0 - alpha) if mga_pyramid_fusion == "add" else torch.zeros((), dtype=dt, device=x.device)
     k1 = alpha
     out = (xf * (k0 + k1 * gate)).reshape(B, C, H, W)
 

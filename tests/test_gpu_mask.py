@@ -1,0 +1,60 @@
+"""GPU mask downsample, bit-exact against the cv2 outputs the reference produced
+(tests/golden/mask_downsample.npz) and against the numpy oracle at full image size."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mask_oracle as mo
+from tests._golden import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bit_exact_vs_reference_goldens(monkeypatch):
+    from mga_yolo_b200 import MaskUtils
+
+    dev = torch.device("cuda:0")
+    z = np.load(GOLDEN / "mask_downsample.npz")
+    n = 0
+    for si in range(len(z["sizes"])):
+        src = torch.from_numpy(z[f"src{si}"]).to(dev)
+        for s in z["strides"]:
+            for method, bridge in (("nearest", "1"), ("area", "1"), ("area", "0"), ("maxpool", "1"),
+                                   ("skeleton_bresenham", "1"), ("skeleton_bresenham", "0")):
+                monkeypatch.setenv("MGA_MASK_METHOD", method)
+                monkeypatch.setenv("MGA_MASK_BRIDGE", bridge)
+                got = MaskUtils.downsample_mask(src, int(s))
+                ref = torch.from_numpy(z[f"bin{si}_{s}_{method}_{bridge}"])
+                assert got.dtype == torch.uint8 and torch.equal(got.cpu(), ref), (si, int(s), method, bridge)
+                n += 1
+            for method in ("avgpool", "nearest", "area"):
+                got = MaskUtils.downsample_mask_prob(src, int(s), method)
+                ref = torch.from_numpy(z[f"prob{si}_{s}_{method}"])
+                assert got.dtype == torch.float32 and torch.equal(got.cpu(), ref), (si, int(s), method)
+                n += 1
+    assert n == len(z["sizes"]) * len(z["strides"]) * 9
+
+
+@pytest.mark.parametrize("hw", [(640, 640), (1280, 1280), (608, 352)])
+def test_batched_full_size_vs_oracle(hw, monkeypatch):
+    from mga_yolo_b200 import MaskUtils
+
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(hw[0])
+    B = 4
+    H, W = hw
+    src = (rng.random((B, H, W)) > 0.5).astype(np.uint8)
+    src[:, : H // 2] &= (rng.random((B, H // 2, W)) > 0.7)
+    d = torch.from_numpy(src).to(dev)
+    for s in (8, 16, 32):
+        for method, bridge in (("nearest", True), ("area", True), ("maxpool", False), ("skeleton_bresenham", True)):
+            monkeypatch.setenv("MGA_MASK_METHOD", method)
+            monkeypatch.setenv("MGA_MASK_BRIDGE", "1" if bridge else "0")
+            got = MaskUtils.downsample_mask(d, s).cpu().numpy()
+            for b in range(B):
+                assert np.array_equal(got[b], mo.downsample_mask(src[b], s, method, bridge)), (hw, s, method, b)
+        got = MaskUtils.downsample_mask_prob(d, s, "avgpool").cpu().numpy()
+        for b in range(B):
+            assert np.array_equal(got[b], mo.downsample_mask_prob(src[b], s, "avgpool"))
+    multi = MaskUtils.masks_multi(d)
+    assert [tuple(m.shape) for m in multi] == [(B, 1, -(-H // s), -(-W // s)) for s in (8, 16, 32)]
