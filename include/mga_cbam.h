@@ -81,6 +81,16 @@ typedef struct mga_cbam_grads {
 int mga_abi_version(void);
 const char* mga_last_error(void);
 
+/* launch accounting (not part of the reference surface; used by bench.py):
+ *   mga_launch_count  - kernels launched by this library in this process so far
+ *   mga_profile_*     - when enabled, every launch is bracketed by CUDA events on its stream;
+ *                       read (name, milliseconds) per launch after synchronising.  Not usable
+ *                       while a CUDA graph is being captured. */
+unsigned long long mga_launch_count(void);
+int mga_profile_enable(int on);
+int mga_profile_count(void);
+int mga_profile_read(int index, const char** name, float* ms);
+
 /* bytes of the saved-for-backward context and of the transient scratch for this shape */
 int mga_cbam_workspace(const mga_cbam_desc* d, size_t* ctx_bytes, size_t* scratch_bytes);
 

@@ -323,10 +323,30 @@ __global__ void __launch_bounds__(kBlock) bwd_dx_kernel(const T* __restrict__ x,
 }
 
 // ------------------------------------------------------------------ B6
-__global__ void __launch_bounds__(kBlock) bwd_wgrad_kernel(Shape sh, Ctx ctx, BwdScratch bs, mga_cbam_grads gp, int nConvCta) {
+// blocks [0,nMlpBlocks): one thread per MLP-gradient element, summing over the batch;
+// blocks after that: one block per spatial-conv tap (and one for d beta), summing the per-CTA partials.
+__global__ void __launch_bounds__(kBlock) bwd_wgrad_kernel(Shape sh, Ctx ctx, BwdScratch bs, mga_cbam_grads gp, int nConvCta, int nMlpBlocks,
+                                                           int nAlphaPart) {
+    __shared__ float red[32];
     const int C = sh.C, Hd = sh.hidden, B = sh.B;
-    const int n_w1 = Hd * C, n_b1 = Hd, n_w2 = C * Hd, n_b2 = C, n_sam = 3 * sh.k * sh.k;
-    const int total = n_w1 + n_b1 + n_w2 + n_b2 + n_sam + 1;
+    constexpr int kStride = 3 * kMaxK * kMaxK + 1;
+    if ((int)blockIdx.x >= nMlpBlocks) {
+        const int t = blockIdx.x - nMlpBlocks;  // tap index, or 3*k*k for d beta
+        const int n_sam = 3 * sh.k * sh.k;
+        const int col = (t < n_sam) ? t : (kStride - 1);
+        float acc = 0.0f;
+        for (int r = threadIdx.x; r < nConvCta; r += kBlock) acc += bs.convpart[(size_t)r * kStride + col];
+        if (t == n_sam)
+            for (int r = threadIdx.x; r < nAlphaPart; r += kBlock) acc += bs.alphapart[r];
+        const float tot = block_sum(acc, red);
+        if (threadIdx.x == 0) {
+            if (t < n_sam) gp.wsam[t] = tot;
+            else gp.beta[0] = ctx.consts[3] * tot;  // d beta = sigmoid(beta) * d alpha
+        }
+        return;
+    }
+    const int n_w1 = Hd * C, n_b1 = Hd, n_w2 = C * Hd, n_b2 = C;
+    const int total = n_w1 + n_b1 + n_w2 + n_b2;
     int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= total) return;
     if (i < n_w1) {  // dW1[j][c] = sum_b dha[b][j] avg[b][c] + dhm[b][j] mx[b][c]
@@ -353,25 +373,9 @@ __global__ void __launch_bounds__(kBlock) bwd_wgrad_kernel(Shape sh, Ctx ctx, Bw
         return;
     }
     i -= n_w2;
-    if (i < n_b2) {
-        float acc = 0.0f;
-        for (int b = 0; b < B; ++b) acc += bs.dz[b * C + i];
-        gp.b2[i] = 2.0f * acc;
-        return;
-    }
-    i -= n_b2;
-    constexpr int kStride = 3 * kMaxK * kMaxK + 1;
-    if (i < n_sam) {
-        float acc = 0.0f;
-        for (int t = 0; t < nConvCta; ++t) acc += bs.convpart[(size_t)t * kStride + i];
-        gp.wsam[i] = acc;
-        return;
-    }
-    // d beta = sigmoid(beta) * d alpha ; d alpha = sum_p a_p T_p (B2) + per-sample pieces (B4)
     float acc = 0.0f;
-    for (int t = 0; t < nConvCta; ++t) acc += bs.convpart[(size_t)t * kStride + (kStride - 1)];
-    for (int b = 0; b < B; ++b) acc += bs.alphapart[b];
-    gp.beta[0] = ctx.consts[3] * acc;
+    for (int b = 0; b < B; ++b) acc += bs.dz[b * C + i];
+    gp.b2[i] = 2.0f * acc;
 }
 
 }  // namespace mga

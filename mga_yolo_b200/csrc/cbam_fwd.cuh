@@ -13,27 +13,30 @@
 namespace mga {
 
 // ------------------------------------------------------------------ F0
+// grid (tiles of kMaskTile pixels, B): writes m and one partial sum per tile; cam_mlp finalises use/den.
+constexpr int kMaskTile = 4 * kBlock;
 template <typename TM>
-__global__ void __launch_bounds__(kBlock) mask_prep_kernel(const TM* __restrict__ mask, Shape sh, Ctx ctx) {
+__global__ void __launch_bounds__(kBlock) mask_prep_kernel(const TM* __restrict__ mask, Shape sh, Ctx ctx, FwdScratch fs) {
     __shared__ float red[32];
-    const int b = blockIdx.x;
+    const int b = blockIdx.y;
     const int S = sh.S;
     const TM* mp = mask + (size_t)b * S;
     float* mo = ctx.m + (size_t)b * S;
     float acc = 0.0f;
-    for (int p = threadIdx.x; p < S; p += kBlock) {
-        float v = to_f<TM>(mp[p]);
-        if (sh.gate_clamp()) v = fminf(fmaxf(v, 0.0f), 1.0f);
-        if (sh.sigmoid_mask()) v = sigmoidf_acc(v);
-        mo[p] = v;
-        acc += v;
+    const int p0 = blockIdx.x * kMaskTile;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int p = p0 + i * kBlock + threadIdx.x;
+        if (p < S) {
+            float v = to_f<TM>(mp[p]);
+            if (sh.gate_clamp()) v = fminf(fmaxf(v, 0.0f), 1.0f);
+            if (sh.sigmoid_mask()) v = sigmoidf_acc(v);
+            mo[p] = v;
+            acc += v;
+        }
     }
     const float tot = block_sum(acc, red);
-    if (threadIdx.x == 0) {
-        ctx.msum[b] = tot;
-        ctx.use[b] = (tot / (float)S >= sh.tiny_thr) ? 1.0f : 0.0f;
-        ctx.den[b] = fmaxf(tot, sh.eps);
-    }
+    if (threadIdx.x == 0) fs.mpart[(size_t)b * gridDim.x + blockIdx.x] = tot;
 }
 
 // ------------------------------------------------------------------ F1
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(kBlock) cam_pool_kernel(const T* __restrict__ 
 }
 
 // ------------------------------------------------------------------ F2 (one CTA per sample)
-__global__ void __launch_bounds__(kBlock) cam_mlp_kernel(Shape sh, mga_cbam_params prm, Ctx ctx, FwdScratch fs) {
+__global__ void __launch_bounds__(kBlock) cam_mlp_kernel(Shape sh, mga_cbam_params prm, Ctx ctx, FwdScratch fs, int nMaskTiles) {
     extern __shared__ float smem[];
     const int C = sh.C, Hd = sh.hidden, b = blockIdx.x;
     float* s_avg = smem;            // C
@@ -99,8 +102,18 @@ __global__ void __launch_bounds__(kBlock) cam_mlp_kernel(Shape sh, mga_cbam_para
     float* s_ha = s_mx + C;         // Hd
     float* s_hm = s_ha + Hd;        // Hd
     const bool has_mask = sh.has_mask();
-    const float use = has_mask ? ctx.use[b] : 0.0f;
-    const float den = has_mask ? ctx.den[b] : 1.0f;
+    float use = 0.0f, den = 1.0f;
+    if (has_mask) {
+        float tot = 0.0f;
+        for (int t = 0; t < nMaskTiles; ++t) tot += fs.mpart[(size_t)b * nMaskTiles + t];  // same order in every thread
+        use = (tot / (float)sh.S >= sh.tiny_thr) ? 1.0f : 0.0f;
+        den = fmaxf(tot, sh.eps);
+        if (threadIdx.x == 0) {
+            ctx.msum[b] = tot;
+            ctx.use[b] = use;
+            ctx.den[b] = den;
+        }
+    }
     const float invS = 1.0f / (float)sh.S;
 
     for (int c = threadIdx.x; c < C; c += kBlock) {

@@ -205,6 +205,7 @@ struct FwdScratch {
     float* sx;    // (B,C) sum x
     float* best;  // (B,C) masked max
     int* bidx;    // (B,C) its pixel
+    float* mpart; // (B,nMaskTiles) partial sums of the mask
 };
 
 struct BwdScratch {

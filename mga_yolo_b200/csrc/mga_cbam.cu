@@ -2,8 +2,11 @@
 #include <cstdio>
 #include <cstring>
 #include <type_traits>
+#include <algorithm>
+#include <vector>
 
 #include "cbam_bwd.cuh"
+#include "cbam_fused.cuh"
 #include "cbam_fwd.cuh"
 #include "common.cuh"
 
@@ -18,6 +21,35 @@ int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+
+// ------------------------------------------------------------------ launch accounting / per-kernel CUDA-event timing
+// Every kernel launch of the library goes through a LaunchScope: it bumps the launch counter
+// (bench.py's "gpu_launches") and, when profiling is switched on, brackets the launch with
+// CUDA events on the launching stream so bench.py can report the dominant kernel's duration.
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+static bool g_prof_on = false;
+static unsigned long long g_launches = 0;
+
+struct LaunchScope {
+    cudaStream_t st;
+    int rec = -1;
+    LaunchScope(const char* name, cudaStream_t s) : st(s) {
+        ++g_launches;
+        if (g_prof_on) {
+            ProfRec r{name, nullptr, nullptr};
+            cudaEventCreate(&r.a);
+            cudaEventCreate(&r.b);
+            cudaEventRecord(r.a, st);
+            g_prof.push_back(r);
+            rec = (int)g_prof.size() - 1;
+        }
+    }
+    ~LaunchScope() {
+        if (rec >= 0) cudaEventRecord(g_prof[rec].b, st);
+    }
+};
+#define MGA_LAUNCH(name, st, ...) do { LaunchScope _ls(name, st); __VA_ARGS__; } while (0)
 
 static int check_launch(const char* what) {
     const cudaError_t e = cudaGetLastError();
@@ -83,6 +115,7 @@ static size_t carve_fwd(const Shape& s, void* base, FwdScratch* f) {
     f->sx = k.take<float>(BC);
     f->best = k.take<float>(BC);
     f->bidx = k.take<int>(BC);
+    f->mpart = k.take<float>((size_t)s.B * ((s.S + kMaskTile - 1) / kMaskTile));
     return k.off;
 }
 
@@ -116,29 +149,120 @@ static int pick_vec(const Shape& s, int dtype, std::initializer_list<const void*
     return v;
 }
 
+// ------------------------------------------------------------------ cluster-resident fused path: geometry + launch
+static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// Smallest cluster size whose per-CTA slice (+ work buffers) fits in shared memory.  false -> use the split path.
+static bool fused_geometry(const Shape& sh, int esize, bool bwd, FusedGeom* out) {
+    const int vec = 16 / esize;
+    if (sh.S % vec) return false;
+    const int U = sh.S / vec, C = sh.C, pad = kMaxK / 2;  // the fused conv always runs 7x7 with zero-padded weights
+    for (int CS = 1; CS <= 16; CS *= 2) {
+        FusedGeom g{};
+        g.CS = CS;
+        g.nUmax = (U + CS - 1) / CS;
+        if (g.nUmax > 256) continue;
+        if (CS > 1 && (CS - 1) * g.nUmax >= U + g.nUmax) continue;
+        g.rsU = g.nUmax | 1;
+        g.UT = std::min(8, pow2ceil((g.nUmax + 31) / 32));
+        g.CG = kFW / g.UT;
+        g.NJ = C < kFB ? std::max(1, kFB / C) : 1;
+        g.NG = std::min(4, C);
+        g.rowsPerGroup = (C + g.NG - 1) / g.NG;
+        const int nPmax = g.nUmax * vec;
+        g.tileRows = (nPmax + sh.W - 2) / sh.W + 1 + 2 * pad;
+        const int TW = sh.W + 2 * pad;
+        size_t off = 128;  // mbarriers (unused by the cp.async load path)
+        g.off_misc = (int)off;
+        off += 1024;
+        g.off_chan = (int)off;
+        const size_t chan_f = bwd ? ((size_t)(12 + g.UT) * C + 4 * sh.hidden + 16) : ((size_t)7 * C + 2 * sh.hidden);
+        off += align256(chan_f * 4);
+        g.off_pix = (int)off;
+        off += align256((size_t)(bwd ? 3 : 1) * nPmax * 4);
+        g.off_tile = (int)off;
+        g.plane_floats = g.tileRows * TW;
+        // scratch aliases the pmax/pavg planes: pool partials [NJ][4][C], optionally the staged DSMEM gather [CS][4][C]
+        size_t scratch_f = std::max<size_t>((size_t)2 * g.plane_floats, (size_t)4 * g.NJ * C);
+        if ((size_t)4 * C * CS <= 4096) scratch_f = std::max<size_t>(scratch_f, (size_t)4 * C * CS);
+        g.scratch_floats = (int)scratch_f;
+        off += align256(((size_t)g.plane_floats + scratch_f) * 4);
+        g.off_xs = (int)off;
+        off += (size_t)C * g.rsU * 16;
+        if (off > (size_t)kSmemLimit) continue;
+        g.smem_bytes = (int)off;
+        *out = g;
+        return true;
+    }
+    return false;
+}
+
+template <typename K, typename... Args>
+static int launch_cluster(const char* name, K kernel, const FusedGeom& gm, int nClusters, cudaStream_t st, Args... args) {
+    static thread_local const void* configured[16] = {};
+    bool done = false;
+    for (const void* c : configured) done |= (c == (const void*)kernel);
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return fail(MGA_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+        for (auto& c : configured)
+            if (!c) { c = (const void*)kernel; break; }
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(nClusters * gm.CS));
+    cfg.blockDim = dim3(kFB);
+    cfg.dynamicSmemBytes = (size_t)gm.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)gm.CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    {
+        LaunchScope ls(name, st);
+        e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    }
+    if (e != cudaSuccess) return fail(MGA_ERR_CUDA, "%s: launch (cluster %d, %d B smem): %s", name, gm.CS, gm.smem_bytes, cudaGetErrorString(e));
+    return MGA_OK;
+}
+
+template <typename T>
+static int forward_fused(const Shape& sh, const FusedGeom& gm, const T* x, const void* mask, int mask_dtype, const mga_cbam_params& p, T* out,
+                         Ctx ctx, cudaStream_t st) {
+    return launch_cluster("fused_fwd", fused_fwd_kernel<T>, gm, sh.B, st, x, mask, mask_dtype, out, sh, p, ctx, gm);
+}
+
 // ------------------------------------------------------------------ forward
 template <typename T, int VEC>
 static int forward_split(const Shape& sh, const T* x, const void* mask, int mask_dtype, const mga_cbam_params& p, T* out, Ctx ctx,
                          FwdScratch fs, cudaStream_t st) {
     const int U = sh.S / VEC;
+    const int nMaskTiles = (sh.S + kMaskTile - 1) / kMaskTile;
+    const dim3 gmask(nMaskTiles, sh.B);
     if (sh.has_mask()) {
-        if (mask_dtype == MGA_F32) mask_prep_kernel<float><<<sh.B, kBlock, 0, st>>>(static_cast<const float*>(mask), sh, ctx);
-        else if (mask_dtype == MGA_BF16) mask_prep_kernel<__nv_bfloat16><<<sh.B, kBlock, 0, st>>>(static_cast<const __nv_bfloat16*>(mask), sh, ctx);
-        else mask_prep_kernel<__half><<<sh.B, kBlock, 0, st>>>(static_cast<const __half*>(mask), sh, ctx);
+        MGA_LAUNCH("mask_prep", st,
+            if (mask_dtype == MGA_F32) mask_prep_kernel<float><<<gmask, kBlock, 0, st>>>(static_cast<const float*>(mask), sh, ctx, fs);
+            else if (mask_dtype == MGA_BF16) mask_prep_kernel<__nv_bfloat16><<<gmask, kBlock, 0, st>>>(static_cast<const __nv_bfloat16*>(mask), sh, ctx, fs);
+            else mask_prep_kernel<__half><<<gmask, kBlock, 0, st>>>(static_cast<const __half*>(mask), sh, ctx, fs));
     }
     const int planes = sh.B * sh.C;
-    if (U >= 128) cam_pool_kernel<T, VEC, 32><<<(planes + 7) / 8, kBlock, 0, st>>>(x, sh, ctx, fs);
-    else if (U >= 48) cam_pool_kernel<T, VEC, 16><<<(planes + 15) / 16, kBlock, 0, st>>>(x, sh, ctx, fs);
-    else cam_pool_kernel<T, VEC, 8><<<(planes + 31) / 32, kBlock, 0, st>>>(x, sh, ctx, fs);
+    MGA_LAUNCH("cam_pool", st,
+        if (U >= 128) cam_pool_kernel<T, VEC, 32><<<(planes + 7) / 8, kBlock, 0, st>>>(x, sh, ctx, fs);
+        else if (U >= 48) cam_pool_kernel<T, VEC, 16><<<(planes + 15) / 16, kBlock, 0, st>>>(x, sh, ctx, fs);
+        else cam_pool_kernel<T, VEC, 8><<<(planes + 31) / 32, kBlock, 0, st>>>(x, sh, ctx, fs));
     const size_t mlp_smem = (2 * (size_t)sh.C + 2 * sh.hidden) * sizeof(float);
-    cam_mlp_kernel<<<sh.B, kBlock, mlp_smem, st>>>(sh, p, ctx, fs);
+    MGA_LAUNCH("cam_mlp", st, cam_mlp_kernel<<<sh.B, kBlock, mlp_smem, st>>>(sh, p, ctx, fs, nMaskTiles));
     const dim3 gtile((U + 31) / 32, sh.B);
-    sam_reduce_kernel<T, VEC><<<gtile, kBlock, 0, st>>>(x, sh, ctx);
+    MGA_LAUNCH("sam_reduce", st, (sam_reduce_kernel<T, VEC><<<gtile, kBlock, 0, st>>>(x, sh, ctx)));
     const dim3 gconv((sh.W + kConvTW - 1) / kConvTW, (sh.H + kConvTH - 1) / kConvTH, sh.B);
-    sam_conv_kernel<<<gconv, kBlock, 0, st>>>(sh, p.wsam, ctx);
+    MGA_LAUNCH("sam_conv", st, sam_conv_kernel<<<gconv, kBlock, 0, st>>>(sh, p.wsam, ctx));
     const size_t total = (size_t)planes * U;
     const int grid = (int)std::min<size_t>((total + kBlock - 1) / kBlock, (size_t)kSMs * 32);
-    rescale_kernel<T, VEC><<<grid, kBlock, 0, st>>>(x, out, sh, ctx);
+    MGA_LAUNCH("rescale", st, (rescale_kernel<T, VEC><<<grid, kBlock, 0, st>>>(x, out, sh, ctx)));
     return check_launch("mga_cbam_forward");
 }
 
@@ -146,6 +270,9 @@ template <typename T>
 static int forward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, const void* mask, const mga_cbam_params& p, void* out,
                      Ctx ctx, FwdScratch fs, cudaStream_t st) {
     const int vec = pick_vec(sh, d->dtype, {x, out});
+    FusedGeom gm;
+    if (vec > 1 && !(d->flags & MGA_FORCE_SPLIT) && fused_geometry(sh, (int)sizeof(T), false, &gm))
+        return forward_fused<T>(sh, gm, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, st);
     if (vec == 1) return forward_split<T, 1>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
     return forward_split<T, VecOf<T>::V>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
 }
@@ -157,16 +284,17 @@ static int backward_split(const Shape& sh, const T* x, const TM* mask, const T* 
     const int U = sh.S / VEC;
     const int nT = (U + 31) / 32;
     const dim3 gtile(nT, sh.B);
-    bwd_reduce1_kernel<T, VEC><<<gtile, kBlock, 0, st>>>(x, g, sh, ctx, bs, nT);
+    MGA_LAUNCH("bwd_reduce1", st, (bwd_reduce1_kernel<T, VEC><<<gtile, kBlock, 0, st>>>(x, g, sh, ctx, bs, nT)));
     const dim3 gconv((sh.W + kBT_W - 1) / kBT_W, (sh.H + kBT_H - 1) / kBT_H, sh.B);
     const int nconv = gconv.x * gconv.y * gconv.z;
-    bwd_conv_kernel<<<gconv, kBlock, 0, st>>>(sh, p.wsam, ctx, bs);
-    if (!sh.samcam_add()) bwd_reduce2_kernel<T, VEC><<<gtile, kBlock, 0, st>>>(x, sh, ctx, bs, nT);
+    MGA_LAUNCH("bwd_conv", st, bwd_conv_kernel<<<gconv, kBlock, 0, st>>>(sh, p.wsam, ctx, bs));
+    if (!sh.samcam_add()) MGA_LAUNCH("bwd_reduce2", st, (bwd_reduce2_kernel<T, VEC><<<gtile, kBlock, 0, st>>>(x, sh, ctx, bs, nT)));
     const size_t mlp_smem = ((size_t)sh.C + 2 * sh.hidden) * sizeof(float);
-    bwd_mlp_kernel<<<sh.B, kBlock, mlp_smem, st>>>(sh, p, ctx, bs, nT);
-    bwd_dx_kernel<T, VEC, TM><<<gtile, kBlock, 0, st>>>(x, g, mask, dx, dmask, sh, ctx, bs);
-    const int nw = 2 * sh.C * sh.hidden + sh.C + sh.hidden + 3 * sh.k * sh.k + 1;
-    bwd_wgrad_kernel<<<(nw + kBlock - 1) / kBlock, kBlock, 0, st>>>(sh, ctx, bs, gp, nconv);
+    MGA_LAUNCH("bwd_mlp", st, bwd_mlp_kernel<<<sh.B, kBlock, mlp_smem, st>>>(sh, p, ctx, bs, nT));
+    MGA_LAUNCH("bwd_dx", st, (bwd_dx_kernel<T, VEC, TM><<<gtile, kBlock, 0, st>>>(x, g, mask, dx, dmask, sh, ctx, bs)));
+    const int nw = 2 * sh.C * sh.hidden + sh.C + sh.hidden;
+    const int nMlpBlocks = (nw + kBlock - 1) / kBlock;
+    MGA_LAUNCH("bwd_wgrad", st, bwd_wgrad_kernel<<<nMlpBlocks + 3 * sh.k * sh.k + 1, kBlock, 0, st>>>(sh, ctx, bs, gp, nconv, nMlpBlocks, sh.B));
     return check_launch("mga_cbam_backward");
 }
 
@@ -199,6 +327,30 @@ extern "C" {
 
 int mga_abi_version(void) { return MGA_ABI_VERSION; }
 const char* mga_last_error(void) { return g_err; }
+
+unsigned long long mga_launch_count(void) { return g_launches; }
+
+/* debug: device buffer of 16 uint64 per CTA that the fused kernels stamp with %globaltimer per phase (NULL = off) */
+int mga_debug_timeline(void* device_buffer) {
+    unsigned long long* p = static_cast<unsigned long long*>(device_buffer);
+    const cudaError_t e = cudaMemcpyToSymbol(g_timeline, &p, sizeof(p));
+    return e == cudaSuccess ? MGA_OK : fail(MGA_ERR_CUDA, "mga_debug_timeline: %s", cudaGetErrorString(e));
+}
+
+int mga_profile_enable(int on) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = on != 0;
+    return MGA_OK;
+}
+int mga_profile_count(void) { return (int)g_prof.size(); }
+int mga_profile_read(int i, const char** name, float* ms) {
+    if (i < 0 || i >= (int)g_prof.size() || !name || !ms) return fail(MGA_ERR_ARG, "bad profile record index");
+    *name = g_prof[i].name;
+    const cudaError_t e = cudaEventElapsedTime(ms, g_prof[i].a, g_prof[i].b);
+    if (e != cudaSuccess) return fail(MGA_ERR_CUDA, "profile record %d: %s", i, cudaGetErrorString(e));
+    return MGA_OK;
+}
 
 int mga_cbam_workspace(const mga_cbam_desc* d, size_t* ctx_bytes, size_t* scratch_bytes) {
     Shape sh;

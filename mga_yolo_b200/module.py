@@ -122,6 +122,8 @@ class MaskGuidedCBAM(nn.Module):
             f |= _lib.SAMCAM_ADD
         if self.mga_pyramid_fusion == "multiply":
             f |= _lib.PYRAMID_MULTIPLY
+        if os.getenv("MGA_FORCE_SPLIT", ""):  # debugging / tests: one kernel per phase instead of the cluster-resident kernels
+            f |= _lib.FORCE_SPLIT
         return f
 
     def forward(self, x: Union[torch.Tensor, Sequence[torch.Tensor]]) -> torch.Tensor:
