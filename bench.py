@@ -246,10 +246,24 @@ def build_plans(levels, B, dtype, flags, dev, nsets):
 
 
 def run_step(plans, stream):
+    """Serial step on one stream: forward of P3,P4,P5 then backward of P5,P4,P3 (training order)."""
     for pl in plans:
         pl.fwd(stream)
     for pl in reversed(plans):
         pl.bwd(stream)
+
+
+def run_step_streams(plans, main, sides):
+    """Same step with one stream per pyramid level (the three levels are independent): all forwards
+    run concurrently, join, then all backwards run concurrently, join."""
+    streams = [main] + list(sides)
+    for phase in ("fwd", "bwd"):
+        for s in sides:
+            s.wait_stream(main)
+        for pl, s in zip(plans, streams):
+            getattr(pl, phase)(s.cuda_stream)
+        for s in sides:
+            main.wait_stream(s)
 
 
 def gpu_arm(args, rank, world, local_rank):
@@ -268,7 +282,7 @@ def gpu_arm(args, rank, world, local_rank):
 
     def flags_of(scf):
         f = _lib.SAMCAM_ADD if scf == "add" else 0
-        return f | (_lib.FORCE_SPLIT if args.force_split else 0)
+        return f | (_lib.FORCE_SPLIT if args.force_split else 0) | (_lib.USE_FUSED if args.use_fused else 0)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -279,6 +293,14 @@ def gpu_arm(args, rank, world, local_rank):
         sets = build_plans(levels, B, dtype, flags_of(scf), dev, nsets=2)
         stream = torch.cuda.current_stream(dev)
         sptr = stream.cuda_stream
+        sides = [torch.cuda.Stream(dev) for _ in levels[1:]] if not args.one_stream else []
+
+        def step_on(plans, main):
+            if sides:
+                run_step_streams(plans, main, sides)
+            else:
+                run_step(plans, main.cuda_stream)
+
         # warm-up (un-graphed) also gives launches per step
         torch.cuda.synchronize(dev)
         n0 = lib.mga_launch_count()
@@ -293,7 +315,7 @@ def gpu_arm(args, rank, world, local_rank):
                 for plans, _flat in sets:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        run_step(plans, torch.cuda.current_stream(dev).cuda_stream)
+                        step_on(plans, torch.cuda.current_stream(dev))
                     graphs.append(g)
             except Exception as e:  # pragma: no cover
                 print(f"[bench] CUDA graph capture failed ({e}); timing direct launches", file=sys.stderr)
@@ -303,7 +325,7 @@ def gpu_arm(args, rank, world, local_rank):
             if graphs is not None:
                 graphs[i & 1].replay()
             else:
-                run_step(sets[i & 1][0], sptr)
+                step_on(sets[i & 1][0], stream)
             if world > 1:
                 dist.all_reduce(sets[i & 1][1])  # the only collective: flat weight-gradient buffer
 
@@ -349,6 +371,7 @@ def gpu_arm(args, rank, world, local_rank):
                 per_kernel.setdefault((j, nm), []).append(v)
         klist = [{"i": j, "kernel": nm, "ms": sum(v) / len(v)} for (j, nm), v in sorted(per_kernel.items())]
         return {"ms": ms, "launches_per_step": int(launches_per_step), "graph": graphs is not None, "kernels": klist,
+                "streams": 1 + len(sides),
                 "wall": (t_wall0, t_wall1), "sets": sets}
 
     main = measure(args.sam_cam_fusion, args.steps, args.warmup)
@@ -413,7 +436,8 @@ def gpu_arm(args, rank, world, local_rank):
         "config": {"workload": desc_txt, "levels_CHW": levels, "batch_per_gpu": B, "global_batch": B * world,
                    "sam_cam_fusion": args.sam_cam_fusion, "mga_pyramid_fusion": "add", "parallelism": f"dp{world} (batch sharded; all-reduce of {sum(LevelPlan.n_params(c) for c,_,_ in levels)} fp32 weight grads)",
                    "l2": "two rotating input/output sets per level (2 x 0.73 GB touched per pair of steps) >> 126 MB L2",
-                   "cuda_graph": main["graph"], "algorithmic_bytes_per_step": alg_bytes},
+                   "cuda_graph": main["graph"], "streams": main["streams"], "algorithmic_bytes_per_step": alg_bytes,
+                   "step_order": "forward of all levels (one stream per level), join, backward of all levels, join"},
         "gpu_launches": main["launches_per_step"] * args.steps,
         "launches_per_step": main["launches_per_step"],
         "roofline": roofline,
@@ -538,9 +562,11 @@ def main():
     ap.add_argument("--sam-cam-fusion", default="multiply", choices=["multiply", "add"],
                     help="multiply = the reference's MaskCBAM (parity pinned); add = BASELINE's build-side variant")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--one-stream", action="store_true", help="run the three levels back to back on one stream")
     ap.add_argument("--no-variant", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--force-split", action="store_true", help="never use the cluster-resident fused kernels")
+    ap.add_argument("--use-fused", action="store_true", help="opt in to the experimental cluster-resident fused forward kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

@@ -8,13 +8,15 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libmga_cbam.so"
+import os as _os
+
+LIB_PATH = Path(__file__).resolve().parent / _os.environ.get("MGA_LIBNAME", "libmga_cbam.so")
 ABI_VERSION = 1
 
 # enums of include/mga_cbam.h
 F32, BF16, F16, U8 = 0, 1, 2, 3
 HAS_MASK, SIGMOID_MASK, GATE_CLAMP = 1 << 0, 1 << 1, 1 << 2
-SAMCAM_ADD, PYRAMID_MULTIPLY, FORCE_SPLIT = 1 << 4, 1 << 6, 1 << 8
+SAMCAM_ADD, PYRAMID_MULTIPLY, FORCE_SPLIT, USE_FUSED = 1 << 4, 1 << 6, 1 << 8, 1 << 9
 DS_NEAREST, DS_AREA, DS_MAXPOOL, DS_AVGPOOL, DS_AREA_RAW = 0, 1, 2, 3, 4
 
 EXPORTS = (

@@ -16,7 +16,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
-LIB = PKG / "libmga_cbam.so"
+LIB = PKG / os.environ.get("MGA_LIBNAME", "libmga_cbam.so")
 SOURCES = ("mga_cbam.cu", "mask_ops.cu")
 ARCH = ("-gencode", "arch=compute_100a,code=sm_100a")
 
@@ -45,6 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     common = [nvcc, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", str(INCLUDE), "-I", str(CSRC)]
     if verbose:
         common += ["-Xptxas", "-v"]
+    common += [f"-D{d}" for d in os.environ.get("MGA_DEFINES", "").split() if d]
 
     def compile_one(src: str) -> Path:
         obj = objdir / (src + ".o")

@@ -12,52 +12,89 @@
 namespace mga {
 
 // ------------------------------------------------------------------ B1
-template <typename T, int VEC>
-__global__ void __launch_bounds__(kBlock) bwd_reduce1_kernel(const T* __restrict__ x, const T* __restrict__ g, Shape sh, Ctx ctx,
-                                                             BwdScratch bs, int nT) {
-    __shared__ float sh_t[kWarpsPerBlock][32 * VEC];
+// CTA = (sample b, tile of 32*UPT units); warp w owns channels w, w+8, ...; a lane owns UPT units.
+template <typename T, int VEC, int UPT>
+__global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce1_kernel(const T* __restrict__ x, const T* __restrict__ g, Shape sh, Ctx ctx,
+                                                                            BwdScratch bs, int nT) {
+    constexpr int TP = 32 * VEC * UPT;
+    __shared__ float sh_t[kWarpsPerBlock][TP];
     const int b = blockIdx.y, tile = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int U = sh.S / VEC, C = sh.C;
-    const int u = tile * 32 + lane;
-    const bool act = u < U;
+    const int ubase = tile * 32 * UPT + lane;
     const bool multiply = !sh.samcam_add();
     const float* sp = ctx.s + (size_t)b * C;
 
-    float av[VEC], tacc[VEC];
+    float av[UPT][VEC], tacc[UPT][VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { av[i] = 1.0f; tacc[i] = 0.0f; }
-    if (act && multiply) ldf<VEC>(ctx.a + (size_t)b * sh.S + (size_t)u * VEC, av);
-
-    const size_t base = ((size_t)b * C) * sh.S + (size_t)u * VEC;
-#pragma unroll 2
-    for (int c = w; c < C; c += kWarpsPerBlock) {
-        float e = 0.0f, gxs = 0.0f;
-        if (act) {
-            float xv[VEC], gv[VEC];
-            ldv<T, VEC>(x + base + (size_t)c * sh.S, xv);
-            ldv<T, VEC>(g + base + (size_t)c * sh.S, gv);
-            const float q = multiply ? __ldg(sp + c) : 1.0f;
+    for (int k = 0; k < UPT; ++k) {
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const float gx = gv[i] * xv[i];
-                tacc[i] = fmaf(gx, q, tacc[i]);
-                e = fmaf(gx, av[i], e);
-                gxs += gx;
+        for (int i = 0; i < VEC; ++i) { av[k][i] = 1.0f; tacc[k][i] = 0.0f; }
+        const int u = ubase + k * 32;
+        if (u < U && multiply) ldf<VEC>(ctx.a + (size_t)b * sh.S + (size_t)u * VEC, av[k]);
+    }
+    const size_t base = ((size_t)b * C) * sh.S;
+    // channels are taken KB at a time: all loads of a batch are issued before anything consumes them
+    constexpr int KB0 = VEC == 8 ? MGA_KB2 / 2 : MGA_KB2;
+    constexpr int KB = KB0 / UPT > 0 ? KB0 / UPT : 1;
+    for (int c0 = w; c0 < C; c0 += kWarpsPerBlock * KB) {
+        float xv[KB][UPT][VEC], gv[KB][UPT][VEC], e[KB], gxs[KB];
+#pragma unroll
+        for (int kc = 0; kc < KB; ++kc) {
+            const int c = c0 + kc * kWarpsPerBlock;
+#pragma unroll
+            for (int k = 0; k < UPT; ++k) {
+                const int u = ubase + k * 32;
+                if (u < U && c < C) {
+                    ldv<T, VEC>(x + base + (size_t)c * sh.S + (size_t)u * VEC, xv[kc][k]);
+                    ldv<T, VEC>(g + base + (size_t)c * sh.S + (size_t)u * VEC, gv[kc][k]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) { xv[kc][k][i] = 0.0f; gv[kc][k][i] = 0.0f; }
+                }
             }
         }
-        e = warp_sum(e);
-        gxs = warp_sum(gxs);
+#pragma unroll
+        for (int kc = 0; kc < KB; ++kc) {
+            const int c = c0 + kc * kWarpsPerBlock;
+            const float q = (multiply && c < C) ? __ldg(sp + c) : 1.0f;
+            e[kc] = 0.0f; gxs[kc] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < UPT; ++k)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float gx = gv[kc][k][i] * xv[kc][k][i];
+                    tacc[k][i] = fmaf(gx, q, tacc[k][i]);
+                    e[kc] = fmaf(gx, av[k][i], e[kc]);
+                    gxs[kc] += gx;
+                }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int kc = 0; kc < KB; ++kc) {
+                e[kc] += __shfl_xor_sync(0xffffffffu, e[kc], o);
+                gxs[kc] += __shfl_xor_sync(0xffffffffu, gxs[kc], o);
+            }
+        }
         if (lane == 0) {
-            const size_t o = ((size_t)b * nT + tile) * C + c;
-            bs.epart[o] = e;
-            bs.gxpart[o] = gxs;
+#pragma unroll
+            for (int kc = 0; kc < KB; ++kc) {
+                const int c = c0 + kc * kWarpsPerBlock;
+                if (c < C) {
+                    const size_t o = ((size_t)b * nT + tile) * C + c;
+                    bs.epart[o] = e[kc];
+                    bs.gxpart[o] = gxs[kc];
+                }
+            }
         }
     }
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) sh_t[w][lane * VEC + i] = tacc[i];
+    for (int k = 0; k < UPT; ++k)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) sh_t[w][(k * 32 + lane) * VEC + i] = tacc[k][i];
     __syncthreads();
-    for (int e = threadIdx.x; e < 32 * VEC; e += kBlock) {
-        const int p = tile * 32 * VEC + e;
+    for (int e = threadIdx.x; e < TP; e += kBlock) {
+        const int p = tile * TP + e;
         if (p >= sh.S) continue;
         float t = 0.0f;
 #pragma unroll
@@ -136,38 +173,68 @@ __global__ void __launch_bounds__(kBlock) bwd_conv_kernel(Shape sh, const float*
 }
 
 // ------------------------------------------------------------------ B3 (multiply mode)
-template <typename T, int VEC>
-__global__ void __launch_bounds__(kBlock) bwd_reduce2_kernel(const T* __restrict__ x, Shape sh, Ctx ctx, BwdScratch bs, int nT) {
+template <typename T, int VEC, int UPT>
+__global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce2_kernel(const T* __restrict__ x, Shape sh, Ctx ctx, BwdScratch bs, int nT) {
     const int b = blockIdx.y, tile = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int U = sh.S / VEC, C = sh.C;
-    const int u = tile * 32 + lane;
-    const bool act = u < U;
+    const int ubase = tile * 32 * UPT + lane;
     const size_t plane = (size_t)sh.B * sh.S;
-    float d0[VEC], d1[VEC];
-    int ix[VEC];
+    float d0[UPT][VEC], d1[UPT][VEC];
+    int ix[UPT][VEC];
+    const float invC = 1.0f / (float)C;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { d0[i] = 0.0f; d1[i] = 0.0f; ix[i] = -1; }
-    if (act) {
-        const size_t o = (size_t)b * sh.S + (size_t)u * VEC;
-        ldf<VEC>(bs.dcat + o, d0);
-        ldf<VEC>(bs.dcat + plane + o, d1);
-        ldi<VEC>(ctx.idx + o, ix);
-        const float invC = 1.0f / (float)C;
+    for (int k = 0; k < UPT; ++k) {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) d1[i] *= invC;
-    }
-    const size_t base = ((size_t)b * C) * sh.S + (size_t)u * VEC;
-#pragma unroll 4
-    for (int c = w; c < C; c += kWarpsPerBlock) {
-        float qv = 0.0f;
-        if (act) {
-            float xv[VEC];
-            ldv<T, VEC>(x + base + (size_t)c * sh.S, xv);
+        for (int i = 0; i < VEC; ++i) { d0[k][i] = 0.0f; d1[k][i] = 0.0f; ix[k][i] = -1; }
+        const int u = ubase + k * 32;
+        if (u < U) {
+            const size_t o = (size_t)b * sh.S + (size_t)u * VEC;
+            ldf<VEC>(bs.dcat + o, d0[k]);
+            ldf<VEC>(bs.dcat + plane + o, d1[k]);
+            ldi<VEC>(ctx.idx + o, ix[k]);
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) qv = fmaf(xv[i], d1[i] + (ix[i] == c ? d0[i] : 0.0f), qv);
+            for (int i = 0; i < VEC; ++i) d1[k][i] *= invC;
         }
-        qv = warp_sum(qv);
-        if (lane == 0) bs.qpart[((size_t)b * nT + tile) * C + c] = qv;
+    }
+    const size_t base = ((size_t)b * C) * sh.S;
+    constexpr int KB0 = VEC == 8 ? MGA_KB1 / 2 : MGA_KB1;
+    constexpr int KB = KB0 / UPT > 0 ? KB0 / UPT : 1;
+    for (int c0 = w; c0 < C; c0 += kWarpsPerBlock * KB) {
+        float xv[KB][UPT][VEC], qv[KB];
+#pragma unroll
+        for (int kc = 0; kc < KB; ++kc) {
+            const int c = c0 + kc * kWarpsPerBlock;
+#pragma unroll
+            for (int k = 0; k < UPT; ++k) {
+                const int u = ubase + k * 32;
+                if (u < U && c < C) ldv<T, VEC>(x + base + (size_t)c * sh.S + (size_t)u * VEC, xv[kc][k]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) xv[kc][k][i] = 0.0f;
+                }
+            }
+        }
+#pragma unroll
+        for (int kc = 0; kc < KB; ++kc) {
+            const int c = c0 + kc * kWarpsPerBlock;
+            qv[kc] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < UPT; ++k)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) qv[kc] = fmaf(xv[kc][k][i], d1[k][i] + (ix[k][i] == c ? d0[k][i] : 0.0f), qv[kc]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int kc = 0; kc < KB; ++kc) qv[kc] += __shfl_xor_sync(0xffffffffu, qv[kc], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int kc = 0; kc < KB; ++kc) {
+                const int c = c0 + kc * kWarpsPerBlock;
+                if (c < C) bs.qpart[((size_t)b * nT + tile) * C + c] = qv[kc];
+            }
+        }
     }
 }
 
@@ -183,21 +250,41 @@ __global__ void __launch_bounds__(kBlock) bwd_mlp_kernel(Shape sh, mga_cbam_para
     const bool has_mask = sh.has_mask();
     const float k1 = ctx.consts[1];
     float gx_tot = 0.0f, se_tot = 0.0f;
-    for (int c = threadIdx.x; c < C; c += kBlock) {
-        float e = 0.0f, q = 0.0f, gxs = 0.0f;
-        for (int t = 0; t < nT; ++t) {
-            const size_t o = ((size_t)b * nT + t) * C + c;
-            e += bs.epart[o];
-            gxs += bs.gxpart[o];
-            if (multiply) q += bs.qpart[o];
+    {
+        // sum the per-tile partials: thread = (channel, tile part) so that every thread has independent loads in flight
+        float* s_e = s_dhm + Hd;       // [parts][C]
+        float* s_g = s_e + kBlock;     // [parts][C]
+        float* s_q = s_g + kBlock;     // [parts][C]
+        const int parts = C < kBlock ? kBlock / C : 1;
+        for (int c0 = 0; c0 < C; c0 += kBlock) {
+            const int c = c0 + (int)threadIdx.x % (C < kBlock ? C : kBlock), part = C < kBlock ? (int)threadIdx.x / C : 0;
+            float e = 0.0f, q = 0.0f, gxs = 0.0f;
+            if (c < C && part < parts) {
+#pragma unroll 4
+                for (int t = part; t < nT; t += parts) {
+                    const size_t o = ((size_t)b * nT + t) * C + c;
+                    e += __ldg(bs.epart + o);
+                    gxs += __ldg(bs.gxpart + o);
+                    if (multiply) q += __ldg(bs.qpart + o);
+                }
+            }
+            if (part < parts && c < C) { s_e[part * (C < kBlock ? C : kBlock) + (c - c0)] = e; s_g[part * (C < kBlock ? C : kBlock) + (c - c0)] = gxs; s_q[part * (C < kBlock ? C : kBlock) + (c - c0)] = q; }
+            __syncthreads();
+            const int cc = c0 + (int)threadIdx.x;
+            if ((int)threadIdx.x < (C < kBlock ? C : kBlock) && cc < C) {
+                const int pitch = C < kBlock ? C : kBlock;
+                float es = 0.0f, qs = 0.0f, gs = 0.0f;
+                for (int pp = 0; pp < parts; ++pp) { es += s_e[pp * pitch + threadIdx.x]; gs += s_g[pp * pitch + threadIdx.x]; qs += s_q[pp * pitch + threadIdx.x]; }
+                const float s = ctx.s[b * C + cc];
+                const float ds = k1 * es + qs;
+                const float dz = ds * s * (1.0f - s);
+                s_dz[cc] = dz;
+                bs.dz[b * C + cc] = dz;
+                gx_tot += gs;
+                if (!multiply) se_tot = fmaf(s, es, se_tot);  // add mode: sum_c s_c sum_p g x
+            }
+            __syncthreads();
         }
-        const float s = ctx.s[b * C + c];
-        const float ds = k1 * e + q;
-        const float dz = ds * s * (1.0f - s);
-        s_dz[c] = dz;
-        bs.dz[b * C + c] = dz;
-        gx_tot += gxs;
-        if (!multiply) se_tot = fmaf(s, e, se_tot);  // add mode: sum_c s_c sum_p g x
     }
     // per-sample piece of d alpha: sum g x gate - [pyramid add] sum g x, minus the part B2 owns (sum_p a_p T_p)
     const float gsum = block_sum(gx_tot, red);
@@ -208,6 +295,7 @@ __global__ void __launch_bounds__(kBlock) bwd_mlp_kernel(Shape sh, mga_cbam_para
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int j = w; j < Hd; j += kWarpsPerBlock) {
         float acc = 0.0f;
+#pragma unroll 8
         for (int c = lane; c < C; c += 32) acc = fmaf(s_dz[c], __ldg(prm.w2 + (size_t)c * Hd + j), acc);
         acc = warp_sum(acc);
         if (lane == 0) {
@@ -227,6 +315,7 @@ __global__ void __launch_bounds__(kBlock) bwd_mlp_kernel(Shape sh, mga_cbam_para
     float kacc = 0.0f;
     for (int c = threadIdx.x; c < C; c += kBlock) {
         float davg = 0.0f, dmx = 0.0f;
+#pragma unroll 8
         for (int j = 0; j < Hd; ++j) {
             const float wv = __ldg(prm.w1 + (size_t)j * C + c);
             davg = fmaf(s_dha[j], wv, davg);
@@ -246,7 +335,7 @@ __global__ void __launch_bounds__(kBlock) bwd_mlp_kernel(Shape sh, mga_cbam_para
 
 // ------------------------------------------------------------------ B5
 template <typename T, int VEC, typename TM>
-__global__ void __launch_bounds__(kBlock) bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ g, const TM* __restrict__ mask,
+__global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ g, const TM* __restrict__ mask,
                                                         T* __restrict__ dx, TM* __restrict__ dmask, Shape sh, Ctx ctx, BwdScratch bs) {
     __shared__ float sh_r[kWarpsPerBlock][32 * VEC];
     const int b = blockIdx.y, tile = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -275,26 +364,38 @@ __global__ void __launch_bounds__(kBlock) bwd_dx_kernel(const T* __restrict__ x,
     }
     const size_t base = ((size_t)b * C) * sh.S + (size_t)u * VEC;
     if (act) {
-#pragma unroll 2
-        for (int c = w; c < C; c += kWarpsPerBlock) {
-            const int bc = b * C + c;
-            float xv[VEC], gv[VEC], ov[VEC];
-            ldv<T, VEC, true>(x + base + (size_t)c * sh.S, xv);
-            ldv<T, VEC, true>(g + base + (size_t)c * sh.S, gv);
-            const float s = __ldg(ctx.s + bc), cA = __ldg(bs.cA + bc), cG = __ldg(bs.cG + bc), cM = __ldg(bs.cM + bc);
-            const int am = __ldg(ctx.amax + bc);
-            const float q = add ? 1.0f : s;
+        constexpr int KB = VEC == 8 ? MGA_KB2 / 2 : MGA_KB2;  // channels per batch: 2*KB independent 128-bit loads in flight per thread
+        for (int c0 = w; c0 < C; c0 += kWarpsPerBlock * KB) {
+            float xv[KB][VEC], gv[KB][VEC];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const float gate = add ? (s + av[i]) : (s * av[i]);
-                float v = gv[i] * fmaf(k1, gate, k0);
-                v = fmaf(q, d1[i] + (ix[i] == c ? d0[i] : 0.0f), v);
-                v = fmaf(cA, mv[i], v) + cG;
-                if (u * VEC + i == am) v += cM;
-                ov[i] = v;
-                racc[i] = fmaf(cA, xv[i], racc[i]);
+            for (int k = 0; k < KB; ++k) {
+                const int c = c0 + k * kWarpsPerBlock;
+                if (c < C) {
+                    ldv<T, VEC, true>(x + base + (size_t)c * sh.S, xv[k]);
+                    ldv<T, VEC, true>(g + base + (size_t)c * sh.S, gv[k]);
+                }
             }
-            stv<T, VEC, true>(dx + base + (size_t)c * sh.S, ov);
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                const int c = c0 + k * kWarpsPerBlock;
+                if (c >= C) continue;
+                const int bc = b * C + c;
+                float ov[VEC];
+                const float s = __ldg(ctx.s + bc), cA = __ldg(bs.cA + bc), cG = __ldg(bs.cG + bc), cM = __ldg(bs.cM + bc);
+                const int am = __ldg(ctx.amax + bc);
+                const float q = add ? 1.0f : s;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float gate = add ? (s + av[i]) : (s * av[i]);
+                    float v = gv[k][i] * fmaf(k1, gate, k0);
+                    v = fmaf(q, d1[i] + (ix[i] == c ? d0[i] : 0.0f), v);
+                    v = fmaf(cA, mv[i], v) + cG;
+                    if (u * VEC + i == am) v += cM;
+                    ov[i] = v;
+                    racc[i] = fmaf(cA, xv[k][i], racc[i]);
+                }
+                stv<T, VEC, true>(dx + base + (size_t)c * sh.S, ov);
+            }
         }
     }
     if (!has_mask || dmask == nullptr) return;
@@ -352,15 +453,17 @@ __global__ void __launch_bounds__(kBlock) bwd_wgrad_kernel(Shape sh, Ctx ctx, Bw
     if (i < n_w1) {  // dW1[j][c] = sum_b dha[b][j] avg[b][c] + dhm[b][j] mx[b][c]
         const int j = i / C, c = i % C;
         float acc = 0.0f;
+#pragma unroll 8
         for (int b = 0; b < B; ++b)
-            acc = fmaf(bs.dha[b * Hd + j], ctx.avg[b * C + c], fmaf(bs.dhm[b * Hd + j], ctx.mx[b * C + c], acc));
+            acc = fmaf(__ldg(bs.dha + b * Hd + j), __ldg(ctx.avg + b * C + c), fmaf(__ldg(bs.dhm + b * Hd + j), __ldg(ctx.mx + b * C + c), acc));
         gp.w1[i] = acc;
         return;
     }
     i -= n_w1;
     if (i < n_b1) {
         float acc = 0.0f;
-        for (int b = 0; b < B; ++b) acc += bs.dha[b * Hd + i] + bs.dhm[b * Hd + i];
+#pragma unroll 8
+        for (int b = 0; b < B; ++b) acc += __ldg(bs.dha + b * Hd + i) + __ldg(bs.dhm + b * Hd + i);
         gp.b1[i] = acc;
         return;
     }
@@ -368,13 +471,15 @@ __global__ void __launch_bounds__(kBlock) bwd_wgrad_kernel(Shape sh, Ctx ctx, Bw
     if (i < n_w2) {  // dW2[c][j] = sum_b dz[b][c] (ha + hm)[b][j]
         const int c = i / Hd, j = i % Hd;
         float acc = 0.0f;
-        for (int b = 0; b < B; ++b) acc = fmaf(bs.dz[b * C + c], ctx.ha[b * Hd + j] + ctx.hm[b * Hd + j], acc);
+#pragma unroll 8
+        for (int b = 0; b < B; ++b) acc = fmaf(__ldg(bs.dz + b * C + c), __ldg(ctx.ha + b * Hd + j) + __ldg(ctx.hm + b * Hd + j), acc);
         gp.w2[i] = acc;
         return;
     }
     i -= n_w2;
     float acc = 0.0f;
-    for (int b = 0; b < B; ++b) acc += bs.dz[b * C + i];
+#pragma unroll 8
+    for (int b = 0; b < B; ++b) acc += __ldg(bs.dz + b * C + i);
     gp.b2[i] = 2.0f * acc;
 }
 

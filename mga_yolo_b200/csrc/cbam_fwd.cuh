@@ -40,11 +40,14 @@ __global__ void __launch_bounds__(kBlock) mask_prep_kernel(const TM* __restrict_
 }
 
 // ------------------------------------------------------------------ F1
-// LANES threads cooperate on one (b,c) plane; 256/LANES planes per CTA.
-template <typename T, int VEC, int LANES>
+// TPP threads cooperate on one (b,c) plane (TPP = 32..256, chosen so that a thread owns ~6 units):
+// every thread issues its loads four units at a time, so a whole plane is in flight at once.
+template <typename T, int VEC, int TPP>
 __global__ void __launch_bounds__(kBlock) cam_pool_kernel(const T* __restrict__ x, Shape sh, Ctx ctx, FwdScratch fs) {
-    constexpr int kGroups = kBlock / LANES;
-    const int grp = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+    constexpr int kGroups = kBlock / TPP;
+    constexpr int kWarpsPerPlane = TPP / 32;
+    __shared__ float red[4][kWarpsPerBlock];
+    const int grp = threadIdx.x / TPP, lt = threadIdx.x % TPP;
     const int planes = sh.B * sh.C;
     int pl = blockIdx.x * kGroups + grp;
     const bool active = pl < planes;
@@ -57,35 +60,55 @@ __global__ void __launch_bounds__(kBlock) cam_pool_kernel(const T* __restrict__ 
 
     float sxm = 0.0f, sx = 0.0f, best = -INFINITY;
     int bidx = -1;
-#pragma unroll 4
-    for (int u = lane; u < U; u += LANES) {
-        float v[VEC], mv[VEC];
-        ldv<T, VEC>(xp + (size_t)u * VEC, v);
-        if (has_mask) {
-            ldf<VEC>(mp + (size_t)u * VEC, mv);
-        } else {
+    for (int u0 = lt; u0 < U; u0 += 4 * TPP) {
+        float v[4][VEC], mv[4][VEC];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) mv[i] = 1.0f;
+        for (int q = 0; q < 4; ++q) {
+            const int u = u0 + q * TPP;
+            if (u < U) {
+                ldv<T, VEC, true>(xp + (size_t)u * VEC, v[q]);
+                if (has_mask) ldf<VEC>(mp + (size_t)u * VEC, mv[q]);
+            }
         }
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            sx += v[i];
-            sxm = fmaf(v[i], mv[i], sxm);
-            const bool ok = has_mask ? (mv[i] > 0.5f) : true;
-            if (ok && v[i] > best) { best = v[i]; bidx = u * VEC + i; }
+        for (int q = 0; q < 4; ++q) {
+            const int u = u0 + q * TPP;
+            if (u < U) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float m = has_mask ? mv[q][i] : 1.0f;
+                    sx += v[q][i];
+                    sxm = fmaf(v[q][i], m, sxm);
+                    if ((!has_mask || m > 0.5f) && v[q][i] > best) { best = v[q][i]; bidx = u * VEC + i; }
+                }
+            }
         }
     }
+    // larger value wins; on a tie the lower pixel index wins (first maximum in scan order)
 #pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, o, LANES);
-        sxm += __shfl_xor_sync(0xffffffffu, sxm, o, LANES);
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o, LANES);
-        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o, LANES);
-        // larger value wins; on a tie the lower pixel index wins (first maximum in scan order)
-        const bool take = (oi >= 0) && (bidx < 0 || ob > best || (ob == best && oi < bidx));
-        if (take) { best = ob; bidx = oi; }
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sxm += __shfl_xor_sync(0xffffffffu, sxm, o);
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if ((oi >= 0) && (bidx < 0 || ob > best || (ob == best && oi < bidx))) { best = ob; bidx = oi; }
     }
-    if (active && lane == 0) {
+    if constexpr (kWarpsPerPlane > 1) {
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) { red[0][w] = sx; red[1][w] = sxm; red[2][w] = best; red[3][w] = __int_as_float(bidx); }
+        __syncthreads();
+        if (lt == 0) {
+            const int w0 = grp * kWarpsPerPlane;
+            for (int j = 1; j < kWarpsPerPlane; ++j) {
+                sx += red[0][w0 + j];
+                sxm += red[1][w0 + j];
+                const float ob = red[2][w0 + j];
+                const int oi = __float_as_int(red[3][w0 + j]);
+                if ((oi >= 0) && (bidx < 0 || ob > best || (ob == best && oi < bidx))) { best = ob; bidx = oi; }
+            }
+        }
+    }
+    if (active && lt == 0) {
         fs.sxm[pl] = sxm;
         fs.sx[pl] = sx;
         fs.best[pl] = best;
@@ -105,7 +128,8 @@ __global__ void __launch_bounds__(kBlock) cam_mlp_kernel(Shape sh, mga_cbam_para
     float use = 0.0f, den = 1.0f;
     if (has_mask) {
         float tot = 0.0f;
-        for (int t = 0; t < nMaskTiles; ++t) tot += fs.mpart[(size_t)b * nMaskTiles + t];  // same order in every thread
+#pragma unroll 8
+        for (int t = 0; t < nMaskTiles; ++t) tot += __ldg(fs.mpart + (size_t)b * nMaskTiles + t);  // same order in every thread
         use = (tot / (float)sh.S >= sh.tiny_thr) ? 1.0f : 0.0f;
         den = fmaxf(tot, sh.eps);
         if (threadIdx.x == 0) {
@@ -144,6 +168,7 @@ __global__ void __launch_bounds__(kBlock) cam_mlp_kernel(Shape sh, mga_cbam_para
     for (int j = w; j < Hd; j += kWarpsPerBlock) {
         const float* wr = prm.w1 + (size_t)j * C;
         float pa = 0.0f, pm = 0.0f;
+#pragma unroll 8
         for (int c = lane; c < C; c += 32) {
             const float wv = __ldg(wr + c);
             pa = fmaf(wv, s_avg[c], pa);
@@ -164,6 +189,7 @@ __global__ void __launch_bounds__(kBlock) cam_mlp_kernel(Shape sh, mga_cbam_para
     for (int c = threadIdx.x; c < C; c += kBlock) {
         const float* wr = prm.w2 + (size_t)c * Hd;
         float za = 0.0f, zm = 0.0f;
+#pragma unroll 8
         for (int j = 0; j < Hd; ++j) {
             const float wv = __ldg(wr + j);
             za = fmaf(wv, s_ha[j], za);
@@ -176,60 +202,81 @@ __global__ void __launch_bounds__(kBlock) cam_mlp_kernel(Shape sh, mga_cbam_para
 }
 
 // ------------------------------------------------------------------ F3
-// CTA = (sample b, tile of 32 units); warp w owns channels w, w+8, ...; lanes own units.
-template <typename T, int VEC>
-__global__ void __launch_bounds__(kBlock) sam_reduce_kernel(const T* __restrict__ x, Shape sh, Ctx ctx) {
-    __shared__ float sh_max[kWarpsPerBlock][32 * VEC];
-    __shared__ float sh_sum[kWarpsPerBlock][32 * VEC];
-    __shared__ int sh_idx[kWarpsPerBlock][32 * VEC];
+// CTA = (sample b, tile of 32*UPT units); warp w owns channels w, w+8, ...; a lane owns UPT units (lane, lane+32, ..).
+// UPT = 2 halves the number of CTAs (and their fixed prologue/epilogue cost) when there are plenty of tiles.
+template <typename T, int VEC, int UPT>
+__global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) sam_reduce_kernel(const T* __restrict__ x, Shape sh, Ctx ctx) {
+    constexpr int TP = 32 * VEC * UPT;  // pixels per tile
+    __shared__ float sh_max[kWarpsPerBlock][TP];
+    __shared__ float sh_sum[kWarpsPerBlock][TP];
+    __shared__ int sh_idx[kWarpsPerBlock][TP];
     const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int U = sh.S / VEC, C = sh.C;
-    const int u = blockIdx.x * 32 + lane;
-    const bool act = u < U;
+    const int ubase = blockIdx.x * 32 * UPT + lane;
     const bool use_q = !sh.samcam_add();
     const float* sp = ctx.s + (size_t)b * C;
 
-    float vmax[VEC], vsum[VEC];
-    int vidx[VEC];
+    float vmax[UPT][VEC], vsum[UPT][VEC];
+    int vidx[UPT][VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { vmax[i] = -INFINITY; vsum[i] = 0.0f; vidx[i] = 0; }
-    if (act) {
-        const T* xp = x + ((size_t)b * C) * sh.S + (size_t)u * VEC;
-#pragma unroll 4
-        for (int c = w; c < C; c += kWarpsPerBlock) {
-            float v[VEC];
-            ldv<T, VEC>(xp + (size_t)c * sh.S, v);
+    for (int k = 0; k < UPT; ++k)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { vmax[k][i] = -INFINITY; vsum[k][i] = 0.0f; vidx[k][i] = 0; }
+    const T* xp = x + ((size_t)b * C) * sh.S;
+    constexpr int KB = (VEC == 8 ? MGA_KB1 / 2 : MGA_KB1) / UPT > 0 ? (VEC == 8 ? MGA_KB1 / 2 : MGA_KB1) / UPT : 1;
+    for (int c0 = w; c0 < C; c0 += kWarpsPerBlock * KB) {
+        float v[KB][UPT][VEC];
+#pragma unroll
+        for (int kc = 0; kc < KB; ++kc) {
+            const int c = c0 + kc * kWarpsPerBlock;
+#pragma unroll
+            for (int k = 0; k < UPT; ++k) {
+                const int u = ubase + k * 32;
+                if (c < C && u < U) ldv<T, VEC>(xp + (size_t)c * sh.S + (size_t)u * VEC, v[kc][k]);
+            }
+        }
+#pragma unroll
+        for (int kc = 0; kc < KB; ++kc) {
+            const int c = c0 + kc * kWarpsPerBlock;
+            if (c >= C) continue;
             const float q = use_q ? __ldg(sp + c) : 1.0f;
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const float y = v[i] * q;
-                vsum[i] += y;
-                if (y > vmax[i]) { vmax[i] = y; vidx[i] = c; }
+            for (int k = 0; k < UPT; ++k) {
+                if (ubase + k * 32 >= U) continue;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float y = v[kc][k][i] * q;
+                    vsum[k][i] += y;
+                    if (y > vmax[k][i]) { vmax[k][i] = y; vidx[k][i] = c; }
+                }
             }
         }
     }
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        sh_max[w][lane * VEC + i] = vmax[i];
-        sh_sum[w][lane * VEC + i] = vsum[i];
-        sh_idx[w][lane * VEC + i] = vidx[i];
-    }
+    for (int k = 0; k < UPT; ++k)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const int e = (k * 32 + lane) * VEC + i;
+            sh_max[w][e] = vmax[k][i];
+            sh_sum[w][e] = vsum[k][i];
+            sh_idx[w][e] = vidx[k][i];
+        }
     __syncthreads();
-    for (int e = threadIdx.x; e < 32 * VEC; e += kBlock) {
-        const int p = blockIdx.x * 32 * VEC + e;
+    for (int e = threadIdx.x; e < TP; e += kBlock) {
+        const int p = blockIdx.x * TP + e;
         if (p >= sh.S) continue;
-        float bm = sh_max[0][e], bs = sh_sum[0][e];
+        float bm = sh_max[0][e], bsum = sh_sum[0][e];
         int bi = sh_idx[0][e];
 #pragma unroll
         for (int j = 1; j < kWarpsPerBlock; ++j) {
             const float om = sh_max[j][e];
             const int oi = sh_idx[j][e];
-            bs += sh_sum[j][e];
+            bsum += sh_sum[j][e];
             if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }  // torch.max: first maximal channel
         }
         const size_t o = (size_t)b * sh.S + p;
         ctx.pmax[o] = bm;
-        ctx.pavg[o] = bs / (float)C;
+        ctx.pavg[o] = bsum / (float)C;
         ctx.idx[o] = bi;
     }
 }

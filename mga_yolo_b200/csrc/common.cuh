@@ -17,6 +17,17 @@ constexpr int kWarp = 32;
 constexpr int kBlock = 256;          // threads per CTA for the streaming kernels
 constexpr int kWarpsPerBlock = kBlock / kWarp;
 constexpr int kSMs = 148;            // B200
+// tuning knobs of the tile kernels (sam_reduce, bwd_reduce1/2, bwd_dx): resident CTAs per SM the register
+// allocation must allow, and channels per load batch (x-only kernels / x+g kernels)
+#ifndef MGA_TILE_MINB
+#define MGA_TILE_MINB 4
+#endif
+#ifndef MGA_KB1
+#define MGA_KB1 4
+#endif
+#ifndef MGA_KB2
+#define MGA_KB2 2
+#endif
 constexpr int kMaxK = 7;             // largest spatial-attention kernel that is built
 constexpr int kConvTW = 32, kConvTH = 8;  // output tile of the plane-convolution kernels
 

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "cbam_bwd.cuh"
+#include "cbam_conv.cuh"
 #include "cbam_fused.cuh"
 #include "cbam_fwd.cuh"
 #include "common.cuh"
@@ -106,7 +107,17 @@ static size_t carve_ctx(const Shape& s, void* base, Ctx* c) {
 }
 
 static int tiles_of(const Shape& s, int vec) { return (s.S / vec + 31) / 32; }
-static int conv_ctas(const Shape& s) { return ((s.W + kConvTW - 1) / kConvTW) * ((s.H + kConvTH - 1) / kConvTH) * s.B; }
+static int conv_ctas(const Shape& s) {
+    const int generic = ((s.W + kConvTW - 1) / kConvTW) * ((s.H + kConvTH - 1) / kConvTH) * s.B;
+    if (s.W % 4) return generic;
+    const ConvGeom cg = conv_geom(s.W);
+    return std::max(generic, ((s.H + cg.RB - 1) / cg.RB) * s.B);
+}
+
+template <typename K>
+static void allow_big_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
 
 static size_t carve_fwd(const Shape& s, void* base, FwdScratch* f) {
     Carver k{static_cast<char*>(base)};
@@ -139,6 +150,9 @@ static size_t carve_bwd(const Shape& s, void* base, BwdScratch* b) {
     b->alphapart = k.take<float>(s.B);
     return k.off;
 }
+
+// 64-unit tiles (two units per lane) when that still leaves >= ~10 CTAs per SM; otherwise 32-unit tiles
+static bool wide_tiles(const Shape& s, int U) { return (long long)s.B * ((U + 63) / 64) >= 10LL * kSMs; }
 
 // vector width usable for this call: plane size divisible and every pointer 16-byte aligned
 static int pick_vec(const Shape& s, int dtype, std::initializer_list<const void*> ptrs) {
@@ -251,15 +265,29 @@ static int forward_split(const Shape& sh, const T* x, const void* mask, int mask
     }
     const int planes = sh.B * sh.C;
     MGA_LAUNCH("cam_pool", st,
-        if (U >= 128) cam_pool_kernel<T, VEC, 32><<<(planes + 7) / 8, kBlock, 0, st>>>(x, sh, ctx, fs);
-        else if (U >= 48) cam_pool_kernel<T, VEC, 16><<<(planes + 15) / 16, kBlock, 0, st>>>(x, sh, ctx, fs);
-        else cam_pool_kernel<T, VEC, 8><<<(planes + 31) / 32, kBlock, 0, st>>>(x, sh, ctx, fs));
+        if (U > 6 * 128) cam_pool_kernel<T, VEC, 256><<<planes, kBlock, 0, st>>>(x, sh, ctx, fs);
+        else if (U > 6 * 64) cam_pool_kernel<T, VEC, 128><<<(planes + 1) / 2, kBlock, 0, st>>>(x, sh, ctx, fs);
+        else if (U > 6 * 32) cam_pool_kernel<T, VEC, 64><<<(planes + 3) / 4, kBlock, 0, st>>>(x, sh, ctx, fs);
+        else cam_pool_kernel<T, VEC, 32><<<(planes + 7) / 8, kBlock, 0, st>>>(x, sh, ctx, fs));
     const size_t mlp_smem = (2 * (size_t)sh.C + 2 * sh.hidden) * sizeof(float);
     MGA_LAUNCH("cam_mlp", st, cam_mlp_kernel<<<sh.B, kBlock, mlp_smem, st>>>(sh, p, ctx, fs, nMaskTiles));
-    const dim3 gtile((U + 31) / 32, sh.B);
-    MGA_LAUNCH("sam_reduce", st, (sam_reduce_kernel<T, VEC><<<gtile, kBlock, 0, st>>>(x, sh, ctx)));
-    const dim3 gconv((sh.W + kConvTW - 1) / kConvTW, (sh.H + kConvTH - 1) / kConvTH, sh.B);
-    MGA_LAUNCH("sam_conv", st, sam_conv_kernel<<<gconv, kBlock, 0, st>>>(sh, p.wsam, ctx));
+    if (wide_tiles(sh, U)) {
+        const dim3 gtile((U + 63) / 64, sh.B);
+        MGA_LAUNCH("sam_reduce", st, (sam_reduce_kernel<T, VEC, 2><<<gtile, kBlock, 0, st>>>(x, sh, ctx)));
+    } else {
+        const dim3 gtile((U + 31) / 32, sh.B);
+        MGA_LAUNCH("sam_reduce", st, (sam_reduce_kernel<T, VEC, 1><<<gtile, kBlock, 0, st>>>(x, sh, ctx)));
+    }
+    if (sh.W % 4 == 0) {
+        const ConvGeom cg = conv_geom(sh.W);
+        const size_t smem = ((size_t)3 * cg.rowsT * cg.TWp + (size_t)3 * cg.nStrips * 4 + 3 * kMaxK * kMaxK) * sizeof(float);
+        allow_big_smem(sam_conv4_kernel, smem);
+        const dim3 gconv((sh.H + cg.RB - 1) / cg.RB, sh.B);
+        MGA_LAUNCH("sam_conv", st, sam_conv4_kernel<<<gconv, kBlock, smem, st>>>(sh, p.wsam, ctx, cg));
+    } else {
+        const dim3 gconv((sh.W + kConvTW - 1) / kConvTW, (sh.H + kConvTH - 1) / kConvTH, sh.B);
+        MGA_LAUNCH("sam_conv", st, sam_conv_kernel<<<gconv, kBlock, 0, st>>>(sh, p.wsam, ctx));
+    }
     const size_t total = (size_t)planes * U;
     const int grid = (int)std::min<size_t>((total + kBlock - 1) / kBlock, (size_t)kSMs * 32);
     MGA_LAUNCH("rescale", st, (rescale_kernel<T, VEC><<<grid, kBlock, 0, st>>>(x, out, sh, ctx)));
@@ -271,7 +299,7 @@ static int forward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, con
                      Ctx ctx, FwdScratch fs, cudaStream_t st) {
     const int vec = pick_vec(sh, d->dtype, {x, out});
     FusedGeom gm;
-    if (vec > 1 && !(d->flags & MGA_FORCE_SPLIT) && fused_geometry(sh, (int)sizeof(T), false, &gm))
+    if (vec > 1 && (d->flags & MGA_USE_FUSED) && !(d->flags & MGA_FORCE_SPLIT) && fused_geometry(sh, (int)sizeof(T), false, &gm))
         return forward_fused<T>(sh, gm, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, st);
     if (vec == 1) return forward_split<T, 1>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
     return forward_split<T, VecOf<T>::V>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
@@ -282,14 +310,30 @@ template <typename T, int VEC, typename TM>
 static int backward_split(const Shape& sh, const T* x, const TM* mask, const T* g, const mga_cbam_params& p, Ctx ctx, T* dx, TM* dmask,
                           const mga_cbam_grads& gp, BwdScratch bs, cudaStream_t st) {
     const int U = sh.S / VEC;
-    const int nT = (U + 31) / 32;
-    const dim3 gtile(nT, sh.B);
-    MGA_LAUNCH("bwd_reduce1", st, (bwd_reduce1_kernel<T, VEC><<<gtile, kBlock, 0, st>>>(x, g, sh, ctx, bs, nT)));
-    const dim3 gconv((sh.W + kBT_W - 1) / kBT_W, (sh.H + kBT_H - 1) / kBT_H, sh.B);
-    const int nconv = gconv.x * gconv.y * gconv.z;
-    MGA_LAUNCH("bwd_conv", st, bwd_conv_kernel<<<gconv, kBlock, 0, st>>>(sh, p.wsam, ctx, bs));
-    if (!sh.samcam_add()) MGA_LAUNCH("bwd_reduce2", st, (bwd_reduce2_kernel<T, VEC><<<gtile, kBlock, 0, st>>>(x, sh, ctx, bs, nT)));
-    const size_t mlp_smem = ((size_t)sh.C + 2 * sh.hidden) * sizeof(float);
+    const bool wide = wide_tiles(sh, U);
+    const int nT = wide ? (U + 63) / 64 : (U + 31) / 32;  // tiles of the two reduce kernels (and of their per-tile partials)
+    const dim3 gred(nT, sh.B);
+    const dim3 gtile((U + 31) / 32, sh.B);
+    if (wide) MGA_LAUNCH("bwd_reduce1", st, (bwd_reduce1_kernel<T, VEC, 2><<<gred, kBlock, 0, st>>>(x, g, sh, ctx, bs, nT)));
+    else MGA_LAUNCH("bwd_reduce1", st, (bwd_reduce1_kernel<T, VEC, 1><<<gred, kBlock, 0, st>>>(x, g, sh, ctx, bs, nT)));
+    int nconv;
+    if (sh.W % 4 == 0) {
+        const ConvGeom cg = conv_geom(sh.W);
+        const size_t smem = ((size_t)4 * cg.rowsT * cg.TWp + 3 * kMaxK * kMaxK + 21 * 12 * kMaxK) * sizeof(float);
+        allow_big_smem(bwd_conv4_kernel, smem);
+        const dim3 gconv((sh.H + cg.RB - 1) / cg.RB, sh.B);
+        nconv = gconv.x * gconv.y;
+        MGA_LAUNCH("bwd_conv", st, bwd_conv4_kernel<<<gconv, kBlock, smem, st>>>(sh, p.wsam, ctx, bs, cg));
+    } else {
+        const dim3 gconv((sh.W + kBT_W - 1) / kBT_W, (sh.H + kBT_H - 1) / kBT_H, sh.B);
+        nconv = gconv.x * gconv.y * gconv.z;
+        MGA_LAUNCH("bwd_conv", st, bwd_conv_kernel<<<gconv, kBlock, 0, st>>>(sh, p.wsam, ctx, bs));
+    }
+    if (!sh.samcam_add()) {
+        if (wide) MGA_LAUNCH("bwd_reduce2", st, (bwd_reduce2_kernel<T, VEC, 2><<<gred, kBlock, 0, st>>>(x, sh, ctx, bs, nT)));
+        else MGA_LAUNCH("bwd_reduce2", st, (bwd_reduce2_kernel<T, VEC, 1><<<gred, kBlock, 0, st>>>(x, sh, ctx, bs, nT)));
+    }
+    const size_t mlp_smem = ((size_t)sh.C + 2 * sh.hidden + 3 * kBlock) * sizeof(float);
     MGA_LAUNCH("bwd_mlp", st, bwd_mlp_kernel<<<sh.B, kBlock, mlp_smem, st>>>(sh, p, ctx, bs, nT));
     MGA_LAUNCH("bwd_dx", st, (bwd_dx_kernel<T, VEC, TM><<<gtile, kBlock, 0, st>>>(x, g, mask, dx, dmask, sh, ctx, bs)));
     const int nw = 2 * sh.C * sh.hidden + sh.C + sh.hidden;

@@ -122,8 +122,10 @@ class MaskGuidedCBAM(nn.Module):
             f |= _lib.SAMCAM_ADD
         if self.mga_pyramid_fusion == "multiply":
             f |= _lib.PYRAMID_MULTIPLY
-        if os.getenv("MGA_FORCE_SPLIT", ""):  # debugging / tests: one kernel per phase instead of the cluster-resident kernels
+        if os.getenv("MGA_FORCE_SPLIT", ""):  # one kernel per phase (the default launch path)
             f |= _lib.FORCE_SPLIT
+        elif os.getenv("MGA_USE_FUSED", ""):  # experimental cluster-resident fused forward kernel
+            f |= _lib.USE_FUSED
         return f
 
     def forward(self, x: Union[torch.Tensor, Sequence[torch.Tensor]]) -> torch.Tensor:
