@@ -45,8 +45,8 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce1_kernel(cons
             for (int k = 0; k < UPT; ++k) {
                 const int u = ubase + k * 32;
                 if (u < U && c < C) {
-                    ldv<T, VEC>(x + base + (size_t)c * sh.S + (size_t)u * VEC, xv[kc][k]);
-                    ldv<T, VEC>(g + base + (size_t)c * sh.S + (size_t)u * VEC, gv[kc][k]);
+                    ldv<T, VEC, kLdKeepL2>(x + base + (size_t)c * sh.S + (size_t)u * VEC, xv[kc][k]);
+                    ldv<T, VEC, kLdKeepL2>(g + base + (size_t)c * sh.S + (size_t)u * VEC, gv[kc][k]);
                 } else {
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) { xv[kc][k][i] = 0.0f; gv[kc][k][i] = 0.0f; }
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kBlock) bwd_conv_kernel(Shape sh, const float*
     __shared__ float dpre[TH][TW + 1];
     __shared__ float cat[3][TH][TW + 1];
     __shared__ float wk[3 * kMaxK * kMaxK];
-    __shared__ float red[32];
+    __shared__ double red[32];
     const int k = sh.k, pad = k / 2, H = sh.H, W = sh.W, S = sh.S;
     const int b = blockIdx.z, x0 = blockIdx.x * kBT_W, y0 = blockIdx.y * kBT_H;
     const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kBlock) bwd_conv_kernel(Shape sh, const float*
 
     for (int i = threadIdx.x; i < 3 * k * k; i += kBlock) wk[i] = wsam[i];
     const int tw = kBT_W + k - 1, th = kBT_H + k - 1;
-    float at_acc = 0.0f;
+    double at_acc = 0.0;
     for (int i = threadIdx.x; i < tw * th; i += kBlock) {
         const int r = i / tw, c = i % tw;
         const int yy = y0 + r - pad, xx = x0 + c - pad;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kBlock) bwd_conv_kernel(Shape sh, const float*
             const float a = ap[yy * W + xx], t = Tp[yy * W + xx];
             dp = k1 * t * a * (1.0f - a);
             const bool own = r >= pad && r < pad + kBT_H && c >= pad && c < pad + kBT_W;
-            if (own) at_acc = fmaf(a, t, at_acc);
+            if (own) at_acc += (double)a * (double)t;
         }
         dpre[r][c] = dp;
 #pragma unroll
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(kBlock) bwd_conv_kernel(Shape sh, const float*
             for (int xx = 0; xx < kBT_W; ++xx) acc = fmaf(cat[pl][yy + i][xx + j], dpre[yy + pad][xx + pad], acc);
         part[threadIdx.x] = acc;
     }
-    const float at = block_sum(at_acc, red);
-    if (threadIdx.x == 0) part[3 * kMaxK * kMaxK] = at;
+    const double at = block_sum_d(at_acc, red);
+    if (threadIdx.x == 0) bs.atpart[cta] = at;
 }
 
 // ------------------------------------------------------------------ B3 (multiply mode)
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce2_kernel(cons
 #pragma unroll
             for (int k = 0; k < UPT; ++k) {
                 const int u = ubase + k * 32;
-                if (u < U && c < C) ldv<T, VEC>(x + base + (size_t)c * sh.S + (size_t)u * VEC, xv[kc][k]);
+                if (u < U && c < C) ldv<T, VEC, kLdKeepL2>(x + base + (size_t)c * sh.S + (size_t)u * VEC, xv[kc][k]);
                 else {
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) xv[kc][k][i] = 0.0f;
@@ -239,9 +239,10 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce2_kernel(cons
 }
 
 // ------------------------------------------------------------------ B4 (one CTA per sample)
-__global__ void __launch_bounds__(kBlock) bwd_mlp_kernel(Shape sh, mga_cbam_params prm, Ctx ctx, BwdScratch bs, int nT) {
+__global__ void __launch_bounds__(kBlock) bwd_mlp_kernel(Shape sh, mga_cbam_params prm, Ctx ctx, BwdScratch bs, int nT, int nT2) {
     extern __shared__ float smem[];
     __shared__ float red[32];
+    __shared__ double redd[32];
     const int C = sh.C, Hd = sh.hidden, b = blockIdx.x;
     float* s_dz = smem;          // C
     float* s_dha = s_dz + C;     // Hd
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kBlock) bwd_mlp_kernel(Shape sh, mga_cbam_para
     const bool multiply = !sh.samcam_add();
     const bool has_mask = sh.has_mask();
     const float k1 = ctx.consts[1];
-    float gx_tot = 0.0f, se_tot = 0.0f;
+    double gx_tot = 0.0, se_tot = 0.0;
     {
         // sum the per-tile partials: thread = (channel, tile part) so that every thread has independent loads in flight
         float* s_e = s_dhm + Hd;       // [parts][C]
@@ -261,11 +262,14 @@ __global__ void __launch_bounds__(kBlock) bwd_mlp_kernel(Shape sh, mga_cbam_para
             float e = 0.0f, q = 0.0f, gxs = 0.0f;
             if (c < C && part < parts) {
 #pragma unroll 4
-                for (int t = part; t < nT; t += parts) {
+                for (int t = part; t < nT; t += parts) {  // partials of bwd_reduce1 (nT tiles)
                     const size_t o = ((size_t)b * nT + t) * C + c;
                     e += __ldg(bs.epart + o);
                     gxs += __ldg(bs.gxpart + o);
-                    if (multiply) q += __ldg(bs.qpart + o);
+                }
+                if (multiply) {
+#pragma unroll 4
+                    for (int t = part; t < nT2; t += parts) q += __ldg(bs.qpart + ((size_t)b * nT2 + t) * C + c);  // bwd_reduce2 (nT2 tiles)
                 }
             }
             if (part < parts && c < C) { s_e[part * (C < kBlock ? C : kBlock) + (c - c0)] = e; s_g[part * (C < kBlock ? C : kBlock) + (c - c0)] = gxs; s_q[part * (C < kBlock ? C : kBlock) + (c - c0)] = q; }
@@ -280,16 +284,16 @@ __global__ void __launch_bounds__(kBlock) bwd_mlp_kernel(Shape sh, mga_cbam_para
                 const float dz = ds * s * (1.0f - s);
                 s_dz[cc] = dz;
                 bs.dz[b * C + cc] = dz;
-                gx_tot += gs;
-                if (!multiply) se_tot = fmaf(s, es, se_tot);  // add mode: sum_c s_c sum_p g x
+                gx_tot += (double)gs;
+                if (!multiply) se_tot += (double)s * (double)es;  // add mode: sum_c s_c sum_p g x
             }
             __syncthreads();
         }
     }
     // per-sample piece of d alpha: sum g x gate - [pyramid add] sum g x, minus the part B2 owns (sum_p a_p T_p)
-    const float gsum = block_sum(gx_tot, red);
-    const float ssum = block_sum(se_tot, red);
-    if (threadIdx.x == 0) bs.alphapart[b] = ssum - (sh.pyramid_multiply() ? 0.0f : gsum);
+    const double gsum = block_sum_d(gx_tot, redd);
+    const double ssum = block_sum_d(se_tot, redd);
+    if (threadIdx.x == 0) bs.alphapart[b] = ssum - (sh.pyramid_multiply() ? 0.0 : gsum);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -371,8 +375,8 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* 
             for (int k = 0; k < KB; ++k) {
                 const int c = c0 + k * kWarpsPerBlock;
                 if (c < C) {
-                    ldv<T, VEC, true>(x + base + (size_t)c * sh.S, xv[k]);
-                    ldv<T, VEC, true>(g + base + (size_t)c * sh.S, gv[k]);
+                    ldv<T, VEC, kLdLastUse>(x + base + (size_t)c * sh.S, xv[k]);
+                    ldv<T, VEC, kLdLastUse>(g + base + (size_t)c * sh.S, gv[k]);
                 }
             }
 #pragma unroll
@@ -428,59 +432,60 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* 
 // blocks after that: one block per spatial-conv tap (and one for d beta), summing the per-CTA partials.
 __global__ void __launch_bounds__(kBlock) bwd_wgrad_kernel(Shape sh, Ctx ctx, BwdScratch bs, mga_cbam_grads gp, int nConvCta, int nMlpBlocks,
                                                            int nAlphaPart) {
-    __shared__ float red[32];
+    __shared__ double red[32];
     const int C = sh.C, Hd = sh.hidden, B = sh.B;
     constexpr int kStride = 3 * kMaxK * kMaxK + 1;
     if ((int)blockIdx.x >= nMlpBlocks) {
         const int t = blockIdx.x - nMlpBlocks;  // tap index, or 3*k*k for d beta
         const int n_sam = 3 * sh.k * sh.k;
-        const int col = (t < n_sam) ? t : (kStride - 1);
-        float acc = 0.0f;
-        for (int r = threadIdx.x; r < nConvCta; r += kBlock) acc += bs.convpart[(size_t)r * kStride + col];
-        if (t == n_sam)
+        double acc = 0.0;
+        if (t < n_sam) {
+            for (int r = threadIdx.x; r < nConvCta; r += kBlock) acc += (double)bs.convpart[(size_t)r * kStride + t];
+        } else {
+            for (int r = threadIdx.x; r < nConvCta; r += kBlock) acc += bs.atpart[r];
             for (int r = threadIdx.x; r < nAlphaPart; r += kBlock) acc += bs.alphapart[r];
-        const float tot = block_sum(acc, red);
+        }
+        const double tot = block_sum_d(acc, red);
         if (threadIdx.x == 0) {
-            if (t < n_sam) gp.wsam[t] = tot;
-            else gp.beta[0] = ctx.consts[3] * tot;  // d beta = sigmoid(beta) * d alpha
+            if (t < n_sam) gp.wsam[t] = (float)tot;
+            else gp.beta[0] = (float)((double)ctx.consts[3] * tot);  // d beta = sigmoid(beta) * d alpha
         }
         return;
     }
+    // one WARP per MLP-gradient element: lanes stride over the batch (one memory round trip), then a shuffle sum
     const int n_w1 = Hd * C, n_b1 = Hd, n_w2 = C * Hd, n_b2 = C;
     const int total = n_w1 + n_b1 + n_w2 + n_b2;
-    int i = blockIdx.x * kBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (i >= total) return;
+    float acc = 0.0f;
     if (i < n_w1) {  // dW1[j][c] = sum_b dha[b][j] avg[b][c] + dhm[b][j] mx[b][c]
         const int j = i / C, c = i % C;
-        float acc = 0.0f;
-#pragma unroll 8
-        for (int b = 0; b < B; ++b)
+        for (int b = lane; b < B; b += 32)
             acc = fmaf(__ldg(bs.dha + b * Hd + j), __ldg(ctx.avg + b * C + c), fmaf(__ldg(bs.dhm + b * Hd + j), __ldg(ctx.mx + b * C + c), acc));
-        gp.w1[i] = acc;
+        acc = warp_sum(acc);
+        if (lane == 0) gp.w1[i] = acc;
         return;
     }
     i -= n_w1;
     if (i < n_b1) {
-        float acc = 0.0f;
-#pragma unroll 8
-        for (int b = 0; b < B; ++b) acc += __ldg(bs.dha + b * Hd + i) + __ldg(bs.dhm + b * Hd + i);
-        gp.b1[i] = acc;
+        for (int b = lane; b < B; b += 32) acc += __ldg(bs.dha + b * Hd + i) + __ldg(bs.dhm + b * Hd + i);
+        acc = warp_sum(acc);
+        if (lane == 0) gp.b1[i] = acc;
         return;
     }
     i -= n_b1;
     if (i < n_w2) {  // dW2[c][j] = sum_b dz[b][c] (ha + hm)[b][j]
         const int c = i / Hd, j = i % Hd;
-        float acc = 0.0f;
-#pragma unroll 8
-        for (int b = 0; b < B; ++b) acc = fmaf(__ldg(bs.dz + b * C + c), __ldg(ctx.ha + b * Hd + j) + __ldg(ctx.hm + b * Hd + j), acc);
-        gp.w2[i] = acc;
+        for (int b = lane; b < B; b += 32) acc = fmaf(__ldg(bs.dz + b * C + c), __ldg(ctx.ha + b * Hd + j) + __ldg(ctx.hm + b * Hd + j), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) gp.w2[i] = acc;
         return;
     }
     i -= n_w2;
-    float acc = 0.0f;
-#pragma unroll 8
-    for (int b = 0; b < B; ++b) acc += __ldg(bs.dz + b * C + i);
-    gp.b2[i] = 2.0f * acc;
+    for (int b = lane; b < B; b += 32) acc += __ldg(bs.dz + b * C + i);
+    acc = warp_sum(acc);
+    if (lane == 0) gp.b2[i] = 2.0f * acc;
 }
 
 }  // namespace mga

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kBlock, 4) sam_conv4_kernel(Shape sh, const fl
 // ------------------------------------------------------------------ backward: grid (ceil(H/RB), B)
 __global__ void __launch_bounds__(kBlock, 4) bwd_conv4_kernel(Shape sh, const float* __restrict__ wsam, Ctx ctx, BwdScratch bs, ConvGeom cg) {
     extern __shared__ __align__(16) float csm[];
-    __shared__ float red[32];
+    __shared__ double red[32];
     const int H = sh.H, W = sh.W, S = sh.S, b = blockIdx.y, y0 = blockIdx.x * cg.RB;
     const int cta = blockIdx.y * gridDim.x + blockIdx.x;
     const int planeT = cg.rowsT * cg.TWp;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kBlock, 4) bwd_conv4_kernel(Shape sh, const fl
     const float* ap = ctx.a + (size_t)b * S;
     const float* Tp = bs.T + (size_t)b * S;
     // dpre = k1 * T * a * (1 - a), and the CTA's share of sum_p a_p T_p (own rows only)
-    float at_acc = 0.0f;
+    double at_acc = 0.0;
     {
         const int cpr = cg.TWp / 4, total = cg.rowsT * cpr;
         for (int i0 = threadIdx.x; i0 < total; i0 += 2 * kBlock) {
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kBlock, 4) bwd_conv4_kernel(Shape sh, const fl
                     d.y = k1 * tv[q].y * av[q].y * (1.0f - av[q].y);
                     d.z = k1 * tv[q].z * av[q].z * (1.0f - av[q].z);
                     d.w = k1 * tv[q].w * av[q].w * (1.0f - av[q].w);
-                    if (own[q]) at_acc += (av[q].x * tv[q].x + av[q].y * tv[q].y) + (av[q].z * tv[q].z + av[q].w * tv[q].w);
+                    if (own[q]) at_acc += ((double)av[q].x * tv[q].x + (double)av[q].y * tv[q].y) + ((double)av[q].z * tv[q].z + (double)av[q].w * tv[q].w);
                 }
                 reinterpret_cast<float4*>(dpre)[i] = d;
             }
@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(kBlock, 4) bwd_conv4_kernel(Shape sh, const fl
             }
         }
     }
-    const float at = block_sum(at_acc, red);
-    if (threadIdx.x == 0) part[kStride - 1] = at;
+    const double at = block_sum_d(at_acc, red);
+    if (threadIdx.x == 0) bs.atpart[cta] = at;
 }
 
 }  // namespace mga

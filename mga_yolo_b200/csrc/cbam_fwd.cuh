@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kBlock) cam_pool_kernel(const T* __restrict__ 
         for (int q = 0; q < 4; ++q) {
             const int u = u0 + q * TPP;
             if (u < U) {
-                ldv<T, VEC, true>(xp + (size_t)u * VEC, v[q]);
+                ldv<T, VEC, kLdKeepL2>(xp + (size_t)u * VEC, v[q]);
                 if (has_mask) ldf<VEC>(mp + (size_t)u * VEC, mv[q]);
             }
         }
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) sam_reduce_kernel(const
 #pragma unroll
             for (int k = 0; k < UPT; ++k) {
                 const int u = ubase + k * 32;
-                if (c < C && u < U) ldv<T, VEC>(xp + (size_t)c * sh.S + (size_t)u * VEC, v[kc][k]);
+                if (c < C && u < U) ldv<T, VEC, kLdKeepL2>(xp + (size_t)c * sh.S + (size_t)u * VEC, v[kc][k]);
             }
         }
 #pragma unroll
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kBlock) rescale_kernel(const T* __restrict__ x
         const int pl = (int)(i / U), u = (int)(i % U);
         const int b = pl / sh.C;
         float v[VEC], av[VEC];
-        ldv<T, VEC, true>(x + i * VEC, v);
+        ldv<T, VEC, kLdLastUse>(x + i * VEC, v);
         ldf<VEC>(ctx.a + (size_t)b * sh.S + (size_t)u * VEC, av);
         const float s = __ldg(ctx.s + pl);
 #pragma unroll

@@ -44,42 +44,61 @@ template <> __device__ __forceinline__ __half from_f<__half>(float v) { return _
 
 template <typename T> struct VecOf { static constexpr int V = 16 / sizeof(T); };  // elements per 128-bit access
 
+// L2 eviction-priority policies for 128-bit accesses (the plain .L2::evict_* qualifiers need 256-bit accesses on sm_100).
+// keep  : data that a later kernel of the same forward/backward re-reads (x after pooling, x/g after the first reduce)
+// last  : final read of that data -> first candidate for eviction
+#ifndef MGA_L2_HINTS
+#define MGA_L2_HINTS 0  // measured on B200 (r1): no gain at batch 64 (x does not stay L2-resident between passes); kept for chunked launches
+#endif
+enum LdMode { kLdDefault = 0, kLdStream = 1, kLdKeepL2 = 2, kLdLastUse = 3 };
+__device__ __forceinline__ unsigned long long l2_policy_keep() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
 // 128-bit (or scalar) global load of VEC consecutive elements into fp32 registers.
-// kStream = true uses the no-L1-allocate path for data that is touched once.
-template <typename T, int VEC, bool kStream = false>
+// MODE: true / kLdStream = no L1 allocation (data touched once by this kernel); kLdKeepL2 / kLdLastUse add an L2 policy.
+template <typename T, int VEC, int MODE = 0>
 __device__ __forceinline__ void ldv(const T* __restrict__ p, float (&v)[VEC]) {
+    constexpr int kMode = (MGA_L2_HINTS || MODE < 2) ? MODE : 1;
     if constexpr (VEC == 1) {
         v[0] = to_f<T>(p[0]);
-    } else if constexpr (sizeof(T) == 4) {
-        static_assert(VEC == 4, "fp32 vector is 4 wide");
-        float4 t;
-        if constexpr (kStream) {
-            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                         : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(p));
-        } else {
-            t = __ldg(reinterpret_cast<const float4*>(p));
-        }
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     } else {
-        static_assert(VEC == 8, "16-bit vector is 8 wide");
         uint4 t;
-        if constexpr (kStream) {
-            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+        if constexpr (kMode == kLdStream) {
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+        } else if constexpr (kMode == kLdKeepL2) {
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                         : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p), "l"(l2_policy_keep()));
+        } else if constexpr (kMode == kLdLastUse) {
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                         : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p), "l"(l2_policy_last()));
         } else {
             t = __ldg(reinterpret_cast<const uint4*>(p));
         }
-        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+        if constexpr (sizeof(T) == 4) {
+            static_assert(VEC == 4, "fp32 vector is 4 wide");
+            v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+        } else {
+            static_assert(VEC == 8, "16-bit vector is 8 wide");
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if constexpr (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) {
-                v[2 * i] = __uint_as_float(w[i] << 16);
-                v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-            } else {
-                const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
-                const float2 f = __half22float2(h);
-                v[2 * i] = f.x;
-                v[2 * i + 1] = f.y;
+            for (int i = 0; i < 4; ++i) {
+                if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                    v[2 * i] = __uint_as_float(w[i] << 16);
+                    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+                } else {
+                    const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+                    const float2 f = __half22float2(h);
+                    v[2 * i] = f.x;
+                    v[2 * i + 1] = f.y;
+                }
             }
         }
     }
@@ -167,6 +186,22 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// block-wide fp64 sum (used only for the few scalars that feed d beta)
+__device__ __forceinline__ double block_sum_d(double v, double* sh /* >= 32 doubles */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum_d(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double r = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0.0;
+    return warp_sum_d(r);
+}
+
 // block-wide sum for kBlock threads; result valid in every thread
 __device__ __forceinline__ float block_sum(float v, float* sh /* >= 32 floats */) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -233,7 +268,8 @@ struct BwdScratch {
     float* dha;      // (B,hidden)
     float* dhm;      // (B,hidden)
     float* convpart; // (nConvCta, 3*k*k + 1)  dWsam partials + sum a*T
-    float* alphapart;// (B) per-sample pieces of d alpha that come from per-channel sums
+    double* alphapart;// (B) per-sample pieces of d alpha that come from per-channel sums (fp64: d beta sums all N elements)
+    double* atpart;   // (nConvCta) per-CTA sum_p a_p T_p
 };
 
 // records a message for mga_last_error() and returns `code` (defined in mga_cbam.cu)

@@ -147,7 +147,8 @@ static size_t carve_bwd(const Shape& s, void* base, BwdScratch* b) {
     b->dha = k.take<float>(BH);
     b->dhm = k.take<float>(BH);
     b->convpart = k.take<float>((size_t)conv_ctas(s) * (3 * kMaxK * kMaxK + 1));
-    b->alphapart = k.take<float>(s.B);
+    b->alphapart = k.take<double>(s.B);
+    b->atpart = k.take<double>((size_t)conv_ctas(s));
     return k.off;
 }
 
@@ -312,8 +313,9 @@ static int backward_split(const Shape& sh, const T* x, const TM* mask, const T* 
     const int U = sh.S / VEC;
     const bool wide = wide_tiles(sh, U);
     const int nT = wide ? (U + 63) / 64 : (U + 31) / 32;  // tiles of the two reduce kernels (and of their per-tile partials)
+    const int nT2 = (U + 31) / 32;
     const dim3 gred(nT, sh.B);
-    const dim3 gtile((U + 31) / 32, sh.B);
+    const dim3 gtile(nT2, sh.B);
     if (wide) MGA_LAUNCH("bwd_reduce1", st, (bwd_reduce1_kernel<T, VEC, 2><<<gred, kBlock, 0, st>>>(x, g, sh, ctx, bs, nT)));
     else MGA_LAUNCH("bwd_reduce1", st, (bwd_reduce1_kernel<T, VEC, 1><<<gred, kBlock, 0, st>>>(x, g, sh, ctx, bs, nT)));
     int nconv;
@@ -330,14 +332,14 @@ static int backward_split(const Shape& sh, const T* x, const TM* mask, const T* 
         MGA_LAUNCH("bwd_conv", st, bwd_conv_kernel<<<gconv, kBlock, 0, st>>>(sh, p.wsam, ctx, bs));
     }
     if (!sh.samcam_add()) {
-        if (wide) MGA_LAUNCH("bwd_reduce2", st, (bwd_reduce2_kernel<T, VEC, 2><<<gred, kBlock, 0, st>>>(x, sh, ctx, bs, nT)));
-        else MGA_LAUNCH("bwd_reduce2", st, (bwd_reduce2_kernel<T, VEC, 1><<<gred, kBlock, 0, st>>>(x, sh, ctx, bs, nT)));
+        // measured: the x-only reduce is faster with 32-unit tiles (its partials use the first tiles2 slots of the nT pitch)
+        MGA_LAUNCH("bwd_reduce2", st, (bwd_reduce2_kernel<T, VEC, 1><<<gtile, kBlock, 0, st>>>(x, sh, ctx, bs, nT2)));
     }
     const size_t mlp_smem = ((size_t)sh.C + 2 * sh.hidden + 3 * kBlock) * sizeof(float);
-    MGA_LAUNCH("bwd_mlp", st, bwd_mlp_kernel<<<sh.B, kBlock, mlp_smem, st>>>(sh, p, ctx, bs, nT));
+    MGA_LAUNCH("bwd_mlp", st, bwd_mlp_kernel<<<sh.B, kBlock, mlp_smem, st>>>(sh, p, ctx, bs, nT, nT2));
     MGA_LAUNCH("bwd_dx", st, (bwd_dx_kernel<T, VEC, TM><<<gtile, kBlock, 0, st>>>(x, g, mask, dx, dmask, sh, ctx, bs)));
     const int nw = 2 * sh.C * sh.hidden + sh.C + sh.hidden;
-    const int nMlpBlocks = (nw + kBlock - 1) / kBlock;
+    const int nMlpBlocks = (nw + kWarpsPerBlock - 1) / kWarpsPerBlock;  // one warp per element
     MGA_LAUNCH("bwd_wgrad", st, bwd_wgrad_kernel<<<nMlpBlocks + 3 * sh.k * sh.k + 1, kBlock, 0, st>>>(sh, ctx, bs, gp, nconv, nMlpBlocks, sh.B));
     return check_launch("mga_cbam_backward");
 }

@@ -1,0 +1,220 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, the nn.Module mirrors the reference's constructor/state_dict contract, the hook manager
+wires and unwires correctly, install() patches the graph builder, and CPU tensors fail loudly."""
+import copy
+import ctypes
+import pickle
+import re
+import sys
+import types
+from pathlib import Path
+
+import pytest
+import torch
+import torch.nn as nn
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_loads_and_exports_header_symbols():
+    from mga_yolo_b200 import _lib
+    from mga_yolo_b200.build import build
+
+    build()
+    lib = _lib.load()
+    header = (ROOT / "include" / "mga_cbam.h").read_text()
+    declared = set(re.findall(r"\b(mga_[a-z_0-9]+)\s*\(", header)) - {"mga_cbam_desc", "mga_cbam_params", "mga_cbam_grads"}
+    assert {"mga_cbam_forward", "mga_cbam_backward", "mga_mask_downsample", "mga_cbam_workspace"} <= declared
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/mga_cbam.h but not exported"
+    assert lib.mga_abi_version() == _lib.ABI_VERSION
+    # argument validation happens before any CUDA call, so it can be exercised without a GPU
+    d = _lib.Desc(0, 64, 8, 8, 4, 7, _lib.F32, _lib.F32, 0, 1e-4, 1e-6)
+    cb, sb = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    assert lib.mga_cbam_workspace(ctypes.byref(d), ctypes.byref(cb), ctypes.byref(sb)) == 1  # MGA_ERR_ARG
+    assert b"bad shape" in lib.mga_last_error()
+    d = _lib.Desc(2, 64, 8, 8, 4, 9, _lib.F32, _lib.F32, 0, 1e-4, 1e-6)
+    assert lib.mga_cbam_workspace(ctypes.byref(d), ctypes.byref(cb), ctypes.byref(sb)) == 2  # MGA_ERR_UNSUPPORTED (k > 7)
+    d = _lib.Desc(2, 64, 8, 8, 4, 7, _lib.F32, _lib.F32, 0, 1e-4, 1e-6)
+    assert lib.mga_cbam_workspace(ctypes.byref(d), ctypes.byref(cb), ctypes.byref(sb)) == 0 and cb.value > 0 and sb.value > 0
+
+
+def test_module_contract_matches_reference():
+    from mga_yolo_b200 import MaskCBAM, MaskGuidedCBAM
+
+    m = MaskGuidedCBAM(64)
+    sd = m.state_dict()
+    assert list(sd.keys()) == ["beta", "cam_mlp.0.weight", "cam_mlp.0.bias", "cam_mlp.2.weight", "cam_mlp.2.bias", "sam_conv.weight"]
+    assert sd["beta"].shape == () and sd["beta"].dtype == torch.float32
+    assert sd["cam_mlp.0.weight"].shape == (4, 64) and sd["cam_mlp.2.weight"].shape == (64, 4)
+    assert sd["sam_conv.weight"].shape == (1, 3, 7, 7)
+    assert abs(float(m.alpha) - 0.6931472) < 1e-6  # softplus(0)
+    assert MaskGuidedCBAM(8, r=16).cam_mlp[0].weight.shape == (1, 8)  # hidden = max(1, C // r)
+    assert MaskGuidedCBAM(32, spatial_k=4).k == 5  # even kernels are bumped to odd (masked_cbam.py:47)
+    assert MaskGuidedCBAM(64, reduction_ratio=8).r == 8
+    with pytest.raises(ValueError):
+        MaskGuidedCBAM(64, r=16, reduction_ratio=8)
+    with pytest.raises(ValueError):
+        MaskGuidedCBAM(64, sam_cam_fusion="concat")
+    with pytest.raises(ValueError):
+        MaskGuidedCBAM(64, mga_pyramid_fusion="nope")
+    assert issubclass(MaskCBAM, MaskGuidedCBAM) and MaskCBAM(16, 4).r == 4
+    # same construction order as the reference -> same parameters under the same seed as torch's own layers
+    torch.manual_seed(3)
+    a = MaskGuidedCBAM(32)
+    torch.manual_seed(3)
+    lin1 = nn.Linear(32, 2)
+    assert torch.equal(a.cam_mlp[0].weight, lin1.weight)
+    # beta is a plain Parameter named "beta" (Ultralytics puts it in the weight-decay group by name)
+    assert dict(m.named_parameters())["beta"].requires_grad
+
+
+def test_cpu_tensors_fail_loudly():
+    from mga_yolo_b200 import MaskGuidedCBAM, MaskUtils
+
+    m = MaskGuidedCBAM(16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 16, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m([torch.randn(1, 16, 8, 8), torch.randn(1, 1, 8, 8)])
+    with pytest.raises(AssertionError):
+        m([torch.randn(1, 16, 8, 8)])
+    with pytest.raises(RuntimeError):
+        MaskUtils.downsample_mask(torch.zeros(16, 16, dtype=torch.uint8), 8)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.mga.cbam_fwd(torch.randn(1, 16, 8, 8), None, *[p.detach() for p in (m.cam_mlp[0].weight, m.cam_mlp[0].bias,
+                               m.cam_mlp[2].weight, m.cam_mlp[2].bias, m.sam_conv.weight, m.beta)], 2, 1e-4, 1e-6)
+
+
+def test_gate_env_switch(monkeypatch):
+    from mga_yolo_b200 import MaskGate, MaskGuidedCBAM
+
+    monkeypatch.delenv("MGA_PROB_MODE", raising=False)
+    assert not hasattr(MaskGuidedCBAM(16), "gater")
+    monkeypatch.setenv("MGA_PROB_MODE", "False")  # any non-empty string switches it on (masked_cbam.py:67)
+    g = MaskGuidedCBAM(16).gater
+    assert g.mode == "gumbel" and not g.is_deterministic()
+    g.eval()
+    assert g.is_deterministic()
+    monkeypatch.setenv("MGA_PROB_APPROACH", "bogus")
+    with pytest.raises(ValueError):
+        MaskGuidedCBAM(16)
+    # sampling branches are plain torch ops: check ranges / straight-through value on CPU
+    p = torch.rand(2, 1, 8, 8)
+    for mode in ("gumbel", "hard_st", "bernoulli_detach"):
+        out = MaskGate(mode=mode).train().sample(p)
+        assert out.shape == p.shape and float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+    hard = MaskGate(mode="hard_st").train().sample(p)
+    assert set(hard.unique().tolist()) <= {0.0, 1.0}
+
+
+class _ToyDetect(nn.Module):
+    def __init__(self, chs):
+        super().__init__()
+        self.f = [1, 2, 3]
+        self.cv2 = nn.ModuleList(nn.Sequential(nn.Conv2d(c, 8, 1)) for c in chs)
+
+    def forward(self, feats):
+        return [cv(f) for cv, f in zip(self.cv2, feats)]
+
+
+class _ToyModel(nn.Module):
+    """layers 1,2,3 play P3/P4/P5; layer 4 is the head fed with [1,2,3] (Ultralytics-style .model Sequential)."""
+
+    def __init__(self):
+        super().__init__()
+        self.model = nn.Sequential(nn.Conv2d(3, 8, 1), nn.Conv2d(8, 16, 1), nn.Conv2d(16, 24, 3, 2, 1), nn.Conv2d(24, 32, 3, 2, 1),
+                                   _ToyDetect([16, 24, 32]))
+
+    def forward(self, x):
+        y = [self.model[0](x)]
+        for i in (1, 2, 3):
+            y.append(self.model[i](y[-1]))
+        return self.model[4](y[1:])
+
+
+def test_hook_manager_wiring_ownership_and_pickling():
+    from mga_yolo_b200 import MaskGuidedCBAM, MGAHookManager
+
+    net = _ToyModel()
+    n_before = sum(p.numel() for p in net.parameters())
+    mgr = MGAHookManager(net, target_layers=("1", "2", "3"), reduction_ratio=8)
+    assert [mgr.blocks[k].C for k in ("1", "2", "3")] == [16, 24, 32]  # inferred from the head's first convs
+    assert isinstance(net.mga_cbam["2"], MaskGuidedCBAM)
+    assert sum(p.numel() for p in net.parameters()) > n_before  # blocks are parameters of the model (optimizer / DDP / EMA)
+    assert any(k.startswith("mga_cbam.1.cam_mlp.0.weight") for k in net.state_dict())
+    assert not mgr.registered
+    mgr.register()
+    assert mgr.registered and all(len(net.model[i]._forward_hooks) == 1 for i in (1, 2, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):  # the hook really routes through the CUDA op
+        net(torch.randn(1, 3, 16, 16))
+    clone = copy.deepcopy(net)  # what ModelEMA does
+    hook = next(iter(clone.model[1]._forward_hooks.values()))
+    assert hook.block is clone.mga_cbam["1"] and hook.block is not net.mga_cbam["1"]
+    blob = pickle.dumps(net)  # what stock Ultralytics checkpoints do
+    again = pickle.loads(blob)
+    assert next(iter(again.model[2]._forward_hooks.values())).block is again.mga_cbam["2"]
+    mgr.remove()
+    assert not mgr.registered and all(len(net.model[i]._forward_hooks) == 0 for i in (1, 2, 3))
+    out = net(torch.randn(1, 3, 16, 16))  # un-hooked model is the plain model again
+    assert len(out) == 3
+    # re-attaching to a model that already owns its blocks re-uses them (checkpoint reload path)
+    mgr2 = MGAHookManager(net, target_layers=("1", "2", "3"))
+    assert mgr2.blocks is net.mga_cbam
+    # detect-input semantics: one pre-hook on the head
+    mgr3 = MGAHookManager(net, target_layers=("1", "2", "3"), semantics="detect_input").register()
+    assert len(net.model[4]._forward_pre_hooks) == 1
+    mgr3.remove()
+    with pytest.raises(IndexError):
+        MGAHookManager(_ToyModel(), target_layers=("99",))
+    with pytest.raises(ValueError):
+        MGAHookManager(_ToyModel(), target_layers=("1",), semantics="bogus")
+
+
+def test_hook_manager_mask_plumbing():
+    from mga_yolo_b200 import MGAHookManager
+
+    mgr = MGAHookManager(_ToyModel(), target_layers=("1", "2", "3"))
+    mgr.set_masks([torch.zeros(1, 1, 16, 16), None, torch.ones(1, 1, 4, 4)])
+    assert mgr.slot.per_level["2"] is None and mgr.slot.per_level["3"].shape == (1, 1, 4, 4)
+    mgr.set_masks({"1": torch.zeros(1, 1, 16, 16)})
+    assert list(mgr.slot.per_level) == ["1"]
+    mgr.set_masks(torch.ones(2, 1, 16, 16))
+    assert mgr.slot.full.dtype == torch.uint8 and mgr.slot.full.shape == (2, 16, 16)
+    mgr.set_masks(None)
+    assert mgr.slot.full is None and mgr.slot.mask_for("1", torch.zeros(1, 16, 16, 16)) is None
+    with pytest.raises(ValueError):
+        mgr.set_masks([torch.zeros(1)])
+    assert set(mgr.alphas()) == {"1", "2", "3"}
+
+
+def test_install_patches_graph_builder(monkeypatch):
+    from mga_yolo_b200 import MaskCBAM, install, uninstall
+
+    class Old:  # stands for the reference class
+        pass
+
+    tasks = types.ModuleType("ultralytics.nn.tasks")
+    tasks.MaskCBAM = Old
+    ref = types.ModuleType("mga_yolo.nn.modules.masked_cbam")
+    ref.MaskCBAM = Old
+    monkeypatch.setitem(sys.modules, "ultralytics.nn.tasks", tasks)
+    monkeypatch.setitem(sys.modules, "mga_yolo.nn.modules.masked_cbam", ref)
+    done = install(strict=True)
+    assert "ultralytics.nn.tasks" in done and tasks.MaskCBAM is MaskCBAM and ref.MaskCBAM is MaskCBAM
+    assert tasks.__dict__["MaskCBAM"] is MaskCBAM  # parse_model resolves names through globals()
+    uninstall()
+    assert tasks.MaskCBAM is Old and ref.MaskCBAM is Old
+    monkeypatch.delitem(sys.modules, "ultralytics.nn.tasks")
+    with pytest.raises(RuntimeError):
+        install(strict=True)
+    uninstall()
+
+
+def test_shard_range_partitions_batch():
+    from mga_yolo_b200 import shard_range
+
+    for n, w in ((64, 8), (10, 4), (3, 8), (256, 2)):
+        parts = [list(shard_range(n, r, w)) for r in range(w)]
+        assert sum(parts, []) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
