@@ -414,9 +414,13 @@ def gpu_arm(args, rank, world, local_rank):
         if best is None or k["ms"] > best["ms"]:
             best = k
     roofline = None
+    traffic = None
+    tpath = ROOT / "profiles" / "traffic.json"
+    if best and tpath.exists():  # dram bytes per launch from the committed ncu --set full capture of the same kernel/shape
+        traffic = json.loads(tpath.read_text()).get(f"{best['kernel']}[{best['level']}]") if args.workload == "cfg2" else None
     if best:
         roofline = {"bound": "hbm", "kernel": f"{best['kernel']}[{best['level']}]", "achieved": round(best["gbps"], 1), "peak": peak,
-                    "unit": "GB/s", "frac": round(best["gbps"] / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": round(best["gbps"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "launch_ms": round(best["ms"], 5), "alg_bytes_per_launch": best["alg_bytes"],
                     "step_frac": round(alg_bytes / (main["ms"] * 1e-3) / 1e9 / peak, 4),
                     "step_frac_of_8TBps_nominal": round(alg_bytes / (main["ms"] * 1e-3) / 1e9 / 8000.0, 4)}
