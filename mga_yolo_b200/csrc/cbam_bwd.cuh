@@ -12,15 +12,16 @@
 namespace mga {
 
 // ------------------------------------------------------------------ B1
-// CTA = (sample b, tile of 32*UPT units); warp w owns channels w, w+8, ...; a lane owns UPT units.
-template <typename T, int VEC, int UPT>
+// over (x,g): T_p (per pixel) and E_c, Gx_c (per channel, per-tile partials).  Thread mapping: TileMap (common.cuh).
+template <typename T, int VEC, int LPT, int UPT>
 __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce1_kernel(const T* __restrict__ x, const T* __restrict__ g, Shape sh, Ctx ctx,
                                                                             BwdScratch bs, int nT) {
-    constexpr int TP = 32 * VEC * UPT;
+    using TM_ = TileMap<LPT, UPT, VEC>;
+    constexpr int TP = TM_::TP;
     __shared__ float sh_t[kWarpsPerBlock][TP];
-    const int b = blockIdx.y, tile = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const TM_ tm;
+    const int b = blockIdx.y, tile = blockIdx.x;
     const int U = sh.S / VEC, C = sh.C;
-    const int ubase = tile * 32 * UPT + lane;
     const bool multiply = !sh.samcam_add();
     const float* sp = ctx.s + (size_t)b * C;
 
@@ -29,21 +30,21 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce1_kernel(cons
     for (int k = 0; k < UPT; ++k) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) { av[k][i] = 1.0f; tacc[k][i] = 0.0f; }
-        const int u = ubase + k * 32;
+        const int u = tm.unit(tile, k);
         if (u < U && multiply) ldf<VEC>(ctx.a + (size_t)b * sh.S + (size_t)u * VEC, av[k]);
     }
     const size_t base = ((size_t)b * C) * sh.S;
     // channels are taken KB at a time: all loads of a batch are issued before anything consumes them
     constexpr int KB0 = VEC == 8 ? MGA_KB2 / 2 : MGA_KB2;
     constexpr int KB = KB0 / UPT > 0 ? KB0 / UPT : 1;
-    for (int c0 = w; c0 < C; c0 += kWarpsPerBlock * KB) {
+    for (int c0 = tm.chan0(); c0 < C; c0 += TM_::kChanStep * KB) {
         float xv[KB][UPT][VEC], gv[KB][UPT][VEC], e[KB], gxs[KB];
 #pragma unroll
         for (int kc = 0; kc < KB; ++kc) {
-            const int c = c0 + kc * kWarpsPerBlock;
+            const int c = c0 + kc * TM_::kChanStep;
 #pragma unroll
             for (int k = 0; k < UPT; ++k) {
-                const int u = ubase + k * 32;
+                const int u = tm.unit(tile, k);
                 if (u < U && c < C) {
                     ldv<T, VEC, kLdKeepL2>(x + base + (size_t)c * sh.S + (size_t)u * VEC, xv[kc][k]);
                     ldv<T, VEC, kLdKeepL2>(g + base + (size_t)c * sh.S + (size_t)u * VEC, gv[kc][k]);
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce1_kernel(cons
         }
 #pragma unroll
         for (int kc = 0; kc < KB; ++kc) {
-            const int c = c0 + kc * kWarpsPerBlock;
+            const int c = c0 + kc * TM_::kChanStep;
             const float q = (multiply && c < C) ? __ldg(sp + c) : 1.0f;
             e[kc] = 0.0f; gxs[kc] = 0.0f;
 #pragma unroll
@@ -69,17 +70,14 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce1_kernel(cons
                 }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int kc = 0; kc < KB; ++kc) {
-                e[kc] += __shfl_xor_sync(0xffffffffu, e[kc], o);
-                gxs[kc] += __shfl_xor_sync(0xffffffffu, gxs[kc], o);
-            }
+        for (int kc = 0; kc < KB; ++kc) {
+            e[kc] = group_sum<LPT>(e[kc]);
+            gxs[kc] = group_sum<LPT>(gxs[kc]);
         }
-        if (lane == 0) {
+        if (tm.ul == 0) {
 #pragma unroll
             for (int kc = 0; kc < KB; ++kc) {
-                const int c = c0 + kc * kWarpsPerBlock;
+                const int c = c0 + kc * TM_::kChanStep;
                 if (c < C) {
                     const size_t o = ((size_t)b * nT + tile) * C + c;
                     bs.epart[o] = e[kc];
@@ -91,7 +89,10 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce1_kernel(cons
 #pragma unroll
     for (int k = 0; k < UPT; ++k)
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) sh_t[w][(k * 32 + lane) * VEC + i] = tacc[k][i];
+        for (int i = 0; i < VEC; ++i) {
+            const float t = cross_group_sum<LPT>(tacc[k][i]);
+            if (tm.sub == 0) sh_t[tm.w][tm.slot(k, i)] = t;
+        }
     __syncthreads();
     for (int e = threadIdx.x; e < TP; e += kBlock) {
         const int p = tile * TP + e;
@@ -173,11 +174,13 @@ __global__ void __launch_bounds__(kBlock) bwd_conv_kernel(Shape sh, const float*
 }
 
 // ------------------------------------------------------------------ B3 (multiply mode)
-template <typename T, int VEC, int UPT>
+// over x: Q_c = sum_p x (dcat1/C + [idx == c] dcat0), per-tile partials.  Thread mapping: TileMap.
+template <typename T, int VEC, int LPT, int UPT>
 __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce2_kernel(const T* __restrict__ x, Shape sh, Ctx ctx, BwdScratch bs, int nT) {
-    const int b = blockIdx.y, tile = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    using TM_ = TileMap<LPT, UPT, VEC>;
+    const TM_ tm;
+    const int b = blockIdx.y, tile = blockIdx.x;
     const int U = sh.S / VEC, C = sh.C;
-    const int ubase = tile * 32 * UPT + lane;
     const size_t plane = (size_t)sh.B * sh.S;
     float d0[UPT][VEC], d1[UPT][VEC];
     int ix[UPT][VEC];
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce2_kernel(cons
     for (int k = 0; k < UPT; ++k) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) { d0[k][i] = 0.0f; d1[k][i] = 0.0f; ix[k][i] = -1; }
-        const int u = ubase + k * 32;
+        const int u = tm.unit(tile, k);
         if (u < U) {
             const size_t o = (size_t)b * sh.S + (size_t)u * VEC;
             ldf<VEC>(bs.dcat + o, d0[k]);
@@ -199,14 +202,14 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce2_kernel(cons
     const size_t base = ((size_t)b * C) * sh.S;
     constexpr int KB0 = VEC == 8 ? MGA_KB1 / 2 : MGA_KB1;
     constexpr int KB = KB0 / UPT > 0 ? KB0 / UPT : 1;
-    for (int c0 = w; c0 < C; c0 += kWarpsPerBlock * KB) {
+    for (int c0 = tm.chan0(); c0 < C; c0 += TM_::kChanStep * KB) {
         float xv[KB][UPT][VEC], qv[KB];
 #pragma unroll
         for (int kc = 0; kc < KB; ++kc) {
-            const int c = c0 + kc * kWarpsPerBlock;
+            const int c = c0 + kc * TM_::kChanStep;
 #pragma unroll
             for (int k = 0; k < UPT; ++k) {
-                const int u = ubase + k * 32;
+                const int u = tm.unit(tile, k);
                 if (u < U && c < C) ldv<T, VEC, kLdKeepL2>(x + base + (size_t)c * sh.S + (size_t)u * VEC, xv[kc][k]);
                 else {
 #pragma unroll
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce2_kernel(cons
         }
 #pragma unroll
         for (int kc = 0; kc < KB; ++kc) {
-            const int c = c0 + kc * kWarpsPerBlock;
+            const int c = c0 + kc * TM_::kChanStep;
             qv[kc] = 0.0f;
 #pragma unroll
             for (int k = 0; k < UPT; ++k)
@@ -224,14 +227,11 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce2_kernel(cons
                 for (int i = 0; i < VEC; ++i) qv[kc] = fmaf(xv[kc][k][i], d1[k][i] + (ix[k][i] == c ? d0[k][i] : 0.0f), qv[kc]);
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int kc = 0; kc < KB; ++kc) qv[kc] += __shfl_xor_sync(0xffffffffu, qv[kc], o);
-        }
-        if (lane == 0) {
+        for (int kc = 0; kc < KB; ++kc) qv[kc] = group_sum<LPT>(qv[kc]);
+        if (tm.ul == 0) {
 #pragma unroll
             for (int kc = 0; kc < KB; ++kc) {
-                const int c = c0 + kc * kWarpsPerBlock;
+                const int c = c0 + kc * TM_::kChanStep;
                 if (c < C) bs.qpart[((size_t)b * nT + tile) * C + c] = qv[kc];
             }
         }
@@ -338,13 +338,18 @@ __global__ void __launch_bounds__(kBlock) bwd_mlp_kernel(Shape sh, mga_cbam_para
 }
 
 // ------------------------------------------------------------------ B5
-template <typename T, int VEC, typename TM>
-__global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ g, const TM* __restrict__ mask,
-                                                        T* __restrict__ dx, TM* __restrict__ dmask, Shape sh, Ctx ctx, BwdScratch bs) {
-    __shared__ float sh_r[kWarpsPerBlock][32 * VEC];
-    const int b = blockIdx.y, tile = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+// over (x,g): dx (streaming store) and R_p = sum_c cA_c x -> dmask.  Thread mapping: TileMap with UPT = 1.
+template <typename T, int VEC, int LPT>
+__global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ g, const void* __restrict__ mask,
+                                                                       int mdt, T* __restrict__ dx, void* __restrict__ dmask, Shape sh, Ctx ctx,
+                                                                       BwdScratch bs) {
+    using TM_ = TileMap<LPT, 1, VEC>;
+    constexpr int TP = TM_::TP;
+    __shared__ float sh_r[kWarpsPerBlock][TP];
+    const TM_ tm;
+    const int b = blockIdx.y, tile = blockIdx.x;
     const int U = sh.S / VEC, C = sh.C;
-    const int u = tile * 32 + lane;
+    const int u = tm.unit(tile, 0);
     const bool act = u < U;
     const bool add = sh.samcam_add();
     const bool has_mask = sh.has_mask();
@@ -369,11 +374,11 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* 
     const size_t base = ((size_t)b * C) * sh.S + (size_t)u * VEC;
     if (act) {
         constexpr int KB = VEC == 8 ? MGA_KB2 / 2 : MGA_KB2;  // channels per batch: 2*KB independent 128-bit loads in flight per thread
-        for (int c0 = w; c0 < C; c0 += kWarpsPerBlock * KB) {
+        for (int c0 = tm.chan0(); c0 < C; c0 += TM_::kChanStep * KB) {
             float xv[KB][VEC], gv[KB][VEC];
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
-                const int c = c0 + k * kWarpsPerBlock;
+                const int c = c0 + k * TM_::kChanStep;
                 if (c < C) {
                     ldv<T, VEC, kLdLastUse>(x + base + (size_t)c * sh.S, xv[k]);
                     ldv<T, VEC, kLdLastUse>(g + base + (size_t)c * sh.S, gv[k]);
@@ -381,7 +386,7 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* 
             }
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
-                const int c = c0 + k * kWarpsPerBlock;
+                const int c = c0 + k * TM_::kChanStep;
                 if (c >= C) continue;
                 const int bc = b * C + c;
                 float ov[VEC];
@@ -404,11 +409,14 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* 
     }
     if (!has_mask || dmask == nullptr) return;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) sh_r[w][lane * VEC + i] = racc[i];
+    for (int i = 0; i < VEC; ++i) {
+        const float r = cross_group_sum<LPT>(racc[i]);
+        if (tm.sub == 0) sh_r[tm.w][tm.slot(0, i)] = r;
+    }
     __syncthreads();
     const float kb = bs.kb[b];
-    for (int e = threadIdx.x; e < 32 * VEC; e += kBlock) {
-        const int p = tile * 32 * VEC + e;
+    for (int e = threadIdx.x; e < TP; e += kBlock) {
+        const int p = tile * TP + e;
         if (p >= sh.S) continue;
         float r = 0.0f;
 #pragma unroll
@@ -420,10 +428,14 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* 
             dm *= m * (1.0f - m);
         }
         if (sh.gate_clamp()) {
-            const float raw = to_f<TM>(mask[o]);
+            const float raw = mdt == MGA_F32 ? static_cast<const float*>(mask)[o]
+                            : mdt == MGA_BF16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(mask)[o])
+                                              : __half2float(static_cast<const __half*>(mask)[o]);
             if (!(raw >= 0.0f && raw <= 1.0f)) dm = 0.0f;
         }
-        dmask[o] = from_f<TM>(dm);
+        if (mdt == MGA_F32) static_cast<float*>(dmask)[o] = dm;
+        else if (mdt == MGA_BF16) static_cast<__nv_bfloat16*>(dmask)[o] = __float2bfloat16_rn(dm);
+        else static_cast<__half*>(dmask)[o] = __float2half_rn(dm);
     }
 }
 

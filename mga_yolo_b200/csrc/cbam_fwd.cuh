@@ -202,17 +202,17 @@ __global__ void __launch_bounds__(kBlock) cam_mlp_kernel(Shape sh, mga_cbam_para
 }
 
 // ------------------------------------------------------------------ F3
-// CTA = (sample b, tile of 32*UPT units); warp w owns channels w, w+8, ...; a lane owns UPT units (lane, lane+32, ..).
-// UPT = 2 halves the number of CTAs (and their fixed prologue/epilogue cost) when there are plenty of tiles.
-template <typename T, int VEC, int UPT>
+// per pixel: max / arg max / mean over channels of x*q.  Thread mapping: TileMap (common.cuh).
+template <typename T, int VEC, int LPT, int UPT>
 __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) sam_reduce_kernel(const T* __restrict__ x, Shape sh, Ctx ctx) {
-    constexpr int TP = 32 * VEC * UPT;  // pixels per tile
+    using TM_ = TileMap<LPT, UPT, VEC>;
+    constexpr int TP = TM_::TP;
     __shared__ float sh_max[kWarpsPerBlock][TP];
     __shared__ float sh_sum[kWarpsPerBlock][TP];
     __shared__ int sh_idx[kWarpsPerBlock][TP];
-    const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const TM_ tm;
+    const int b = blockIdx.y, tile = blockIdx.x;
     const int U = sh.S / VEC, C = sh.C;
-    const int ubase = blockIdx.x * 32 * UPT + lane;
     const bool use_q = !sh.samcam_add();
     const float* sp = ctx.s + (size_t)b * C;
 
@@ -221,28 +221,29 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) sam_reduce_kernel(const
 #pragma unroll
     for (int k = 0; k < UPT; ++k)
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) { vmax[k][i] = -INFINITY; vsum[k][i] = 0.0f; vidx[k][i] = 0; }
+        for (int i = 0; i < VEC; ++i) { vmax[k][i] = -INFINITY; vsum[k][i] = 0.0f; vidx[k][i] = 0x7fffffff; }
     const T* xp = x + ((size_t)b * C) * sh.S;
-    constexpr int KB = (VEC == 8 ? MGA_KB1 / 2 : MGA_KB1) / UPT > 0 ? (VEC == 8 ? MGA_KB1 / 2 : MGA_KB1) / UPT : 1;
-    for (int c0 = w; c0 < C; c0 += kWarpsPerBlock * KB) {
+    constexpr int KB0 = VEC == 8 ? MGA_KB1 / 2 : MGA_KB1;
+    constexpr int KB = KB0 / UPT > 0 ? KB0 / UPT : 1;
+    for (int c0 = tm.chan0(); c0 < C; c0 += TM_::kChanStep * KB) {
         float v[KB][UPT][VEC];
 #pragma unroll
         for (int kc = 0; kc < KB; ++kc) {
-            const int c = c0 + kc * kWarpsPerBlock;
+            const int c = c0 + kc * TM_::kChanStep;
 #pragma unroll
             for (int k = 0; k < UPT; ++k) {
-                const int u = ubase + k * 32;
+                const int u = tm.unit(tile, k);
                 if (c < C && u < U) ldv<T, VEC, kLdKeepL2>(xp + (size_t)c * sh.S + (size_t)u * VEC, v[kc][k]);
             }
         }
 #pragma unroll
         for (int kc = 0; kc < KB; ++kc) {
-            const int c = c0 + kc * kWarpsPerBlock;
+            const int c = c0 + kc * TM_::kChanStep;
             if (c >= C) continue;
             const float q = use_q ? __ldg(sp + c) : 1.0f;
 #pragma unroll
             for (int k = 0; k < UPT; ++k) {
-                if (ubase + k * 32 >= U) continue;
+                if (tm.unit(tile, k) >= U) continue;
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
                     const float y = v[kc][k][i] * q;
@@ -252,18 +253,30 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) sam_reduce_kernel(const
             }
         }
     }
+    // merge the 32/LPT channel groups of the warp (lanes with the same unit), then the 8 warps through shared memory
 #pragma unroll
     for (int k = 0; k < UPT; ++k)
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            const int e = (k * 32 + lane) * VEC + i;
-            sh_max[w][e] = vmax[k][i];
-            sh_sum[w][e] = vsum[k][i];
-            sh_idx[w][e] = vidx[k][i];
+            float bm = vmax[k][i], bsum = vsum[k][i];
+            int bi = vidx[k][i];
+#pragma unroll
+            for (int o = LPT; o < 32; o <<= 1) {
+                const float om = __shfl_xor_sync(0xffffffffu, bm, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+                if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }
+            }
+            if (tm.sub == 0) {
+                const int e = tm.slot(k, i);
+                sh_max[tm.w][e] = bm;
+                sh_sum[tm.w][e] = bsum;
+                sh_idx[tm.w][e] = bi;
+            }
         }
     __syncthreads();
     for (int e = threadIdx.x; e < TP; e += kBlock) {
-        const int p = blockIdx.x * TP + e;
+        const int p = tile * TP + e;
         if (p >= sh.S) continue;
         float bm = sh_max[0][e], bsum = sh_sum[0][e];
         int bi = sh_idx[0][e];

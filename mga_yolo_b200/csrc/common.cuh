@@ -214,6 +214,42 @@ __device__ __forceinline__ float block_sum(float v, float* sh /* >= 32 floats */
     return r;
 }
 
+// ---------------------------------------------------------------- tile kernels: thread -> (channel, unit) mapping
+// A CTA of 8 warps owns a tile of LPT*UPT units (16-byte groups of pixels) of one sample and ALL channels.
+// A warp load covers 32/LPT channels x LPT units (each channel's LPT units are contiguous: LPT*16 B >= 128 B), so small
+// feature maps (few units per sample) still produce enough CTAs: LPT = 32 for large planes, 16 / 8 for small ones.
+template <int LPT, int UPT, int VEC>
+struct TileMap {
+    static constexpr int CPW = 32 / LPT;                       // channels per warp load
+    static constexpr int kChanStep = kWarpsPerBlock * CPW;     // channel stride between two loads of the same thread
+    static constexpr int TU = LPT * UPT;                       // units per tile
+    static constexpr int TP = TU * VEC;                        // pixels per tile
+    int w, sub, ul;
+    __device__ __forceinline__ TileMap() {
+        const int lane = threadIdx.x & 31;
+        w = threadIdx.x >> 5;
+        sub = lane / LPT;
+        ul = lane % LPT;
+    }
+    __device__ __forceinline__ int chan0() const { return w * CPW + sub; }                // first channel of this thread
+    __device__ __forceinline__ int unit(int tile, int k) const { return tile * TU + k * LPT + ul; }
+    __device__ __forceinline__ int slot(int k, int i) const { return (k * LPT + ul) * VEC + i; }  // pixel slot inside the tile
+};
+// sum over the LPT lanes that share a channel (result in every lane of the group)
+template <int LPT>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LPT / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// sum over the 32/LPT channel groups of a warp (lanes with equal `ul`); result in every lane
+template <int LPT>
+__device__ __forceinline__ float cross_group_sum(float v) {
+#pragma unroll
+    for (int o = LPT; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // ---------------------------------------------------------------- shapes, context and scratch layouts
 struct Shape {
     int B, C, H, W, S, hidden, k;

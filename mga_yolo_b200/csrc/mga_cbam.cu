@@ -152,8 +152,26 @@ static size_t carve_bwd(const Shape& s, void* base, BwdScratch* b) {
     return k.off;
 }
 
-// 64-unit tiles (two units per lane) when that still leaves >= ~10 CTAs per SM; otherwise 32-unit tiles
-static bool wide_tiles(const Shape& s, int U) { return (long long)s.B * ((U + 63) / 64) >= 10LL * kSMs; }
+// Tile shape of the per-pixel / per-channel reduce kernels: LPT lanes per channel row (x UPT units per lane).  Large planes
+// take 64-unit tiles; small planes shrink the tile to 16 or 8 units so that the grid still has >= ~6 CTAs per SM.
+struct TileCfg { int lpt, upt; };
+// Chosen from the per-sample plane size only (never from B): the summation order inside a sample must not depend on how
+// the batch is sharded, so a sample gives bit-identical results alone, in a batch of 8 or in a batch of 64.
+static TileCfg pick_tiles(const Shape& s, int U, int vec) {
+    (void)s;
+    if (vec == 1) return {32, 1};
+    if (U >= 1024) return {32, 2};
+    if (U >= 256) return {16, 1};
+    return {8, 1};
+}
+// expands to the four tile instantiations; VEC == 1 only ever uses <32,1>
+#define MGA_TILE_DISPATCH(cfg, CALL)                                   \
+    do {                                                               \
+        if ((cfg).lpt == 32 && (cfg).upt == 2) { CALL(32, 2); }        \
+        else if ((cfg).lpt == 32) { CALL(32, 1); }                     \
+        else if ((cfg).lpt == 16) { if constexpr (VEC > 1) { CALL(16, 1); } } \
+        else { if constexpr (VEC > 1) { CALL(8, 1); } }                \
+    } while (0)
 
 // vector width usable for this call: plane size divisible and every pointer 16-byte aligned
 static int pick_vec(const Shape& s, int dtype, std::initializer_list<const void*> ptrs) {
@@ -272,12 +290,12 @@ static int forward_split(const Shape& sh, const T* x, const void* mask, int mask
         else cam_pool_kernel<T, VEC, 32><<<(planes + 7) / 8, kBlock, 0, st>>>(x, sh, ctx, fs));
     const size_t mlp_smem = (2 * (size_t)sh.C + 2 * sh.hidden) * sizeof(float);
     MGA_LAUNCH("cam_mlp", st, cam_mlp_kernel<<<sh.B, kBlock, mlp_smem, st>>>(sh, p, ctx, fs, nMaskTiles));
-    if (wide_tiles(sh, U)) {
-        const dim3 gtile((U + 63) / 64, sh.B);
-        MGA_LAUNCH("sam_reduce", st, (sam_reduce_kernel<T, VEC, 2><<<gtile, kBlock, 0, st>>>(x, sh, ctx)));
-    } else {
-        const dim3 gtile((U + 31) / 32, sh.B);
-        MGA_LAUNCH("sam_reduce", st, (sam_reduce_kernel<T, VEC, 1><<<gtile, kBlock, 0, st>>>(x, sh, ctx)));
+    {
+        const TileCfg tc = pick_tiles(sh, U, VEC);
+        const dim3 gtile((U + tc.lpt * tc.upt - 1) / (tc.lpt * tc.upt), sh.B);
+#define MGA_CALL(L, P) MGA_LAUNCH("sam_reduce", st, (sam_reduce_kernel<T, VEC, L, P><<<gtile, kBlock, 0, st>>>(x, sh, ctx)))
+        MGA_TILE_DISPATCH(tc, MGA_CALL);
+#undef MGA_CALL
     }
     if (sh.W % 4 == 0) {
         const ConvGeom cg = conv_geom(sh.W);
@@ -307,17 +325,19 @@ static int forward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, con
 }
 
 // ------------------------------------------------------------------ backward
-template <typename T, int VEC, typename TM>
-static int backward_split(const Shape& sh, const T* x, const TM* mask, const T* g, const mga_cbam_params& p, Ctx ctx, T* dx, TM* dmask,
-                          const mga_cbam_grads& gp, BwdScratch bs, cudaStream_t st) {
+template <typename T, int VEC>
+static int backward_split(const Shape& sh, const T* x, const void* mask, int mask_dtype, const T* g, const mga_cbam_params& p, Ctx ctx, T* dx,
+                          void* dmask, const mga_cbam_grads& gp, BwdScratch bs, cudaStream_t st) {
     const int U = sh.S / VEC;
-    const bool wide = wide_tiles(sh, U);
-    const int nT = wide ? (U + 63) / 64 : (U + 31) / 32;  // tiles of the two reduce kernels (and of their per-tile partials)
-    const int nT2 = (U + 31) / 32;
+    const TileCfg tc = pick_tiles(sh, U, VEC);
+    const TileCfg tc1 = {tc.lpt, 1};                       // x-only reduce and dx: one unit per lane (measured faster)
+    const int nT = (U + tc.lpt * tc.upt - 1) / (tc.lpt * tc.upt);  // tiles (= per-tile partial rows) of bwd_reduce1
+    const int nT2 = (U + tc.lpt - 1) / tc.lpt;             // tiles of bwd_reduce2 and bwd_dx
     const dim3 gred(nT, sh.B);
     const dim3 gtile(nT2, sh.B);
-    if (wide) MGA_LAUNCH("bwd_reduce1", st, (bwd_reduce1_kernel<T, VEC, 2><<<gred, kBlock, 0, st>>>(x, g, sh, ctx, bs, nT)));
-    else MGA_LAUNCH("bwd_reduce1", st, (bwd_reduce1_kernel<T, VEC, 1><<<gred, kBlock, 0, st>>>(x, g, sh, ctx, bs, nT)));
+#define MGA_CALL(L, P) MGA_LAUNCH("bwd_reduce1", st, (bwd_reduce1_kernel<T, VEC, L, P><<<gred, kBlock, 0, st>>>(x, g, sh, ctx, bs, nT)))
+    MGA_TILE_DISPATCH(tc, MGA_CALL);
+#undef MGA_CALL
     int nconv;
     if (sh.W % 4 == 0) {
         const ConvGeom cg = conv_geom(sh.W);
@@ -332,37 +352,30 @@ static int backward_split(const Shape& sh, const T* x, const TM* mask, const T* 
         MGA_LAUNCH("bwd_conv", st, bwd_conv_kernel<<<gconv, kBlock, 0, st>>>(sh, p.wsam, ctx, bs));
     }
     if (!sh.samcam_add()) {
-        // measured: the x-only reduce is faster with 32-unit tiles (its partials use the first tiles2 slots of the nT pitch)
-        MGA_LAUNCH("bwd_reduce2", st, (bwd_reduce2_kernel<T, VEC, 1><<<gtile, kBlock, 0, st>>>(x, sh, ctx, bs, nT2)));
+#define MGA_CALL(L, P) MGA_LAUNCH("bwd_reduce2", st, (bwd_reduce2_kernel<T, VEC, L, P><<<gtile, kBlock, 0, st>>>(x, sh, ctx, bs, nT2)))
+        MGA_TILE_DISPATCH(tc1, MGA_CALL);
+#undef MGA_CALL
     }
     const size_t mlp_smem = ((size_t)sh.C + 2 * sh.hidden + 3 * kBlock) * sizeof(float);
     MGA_LAUNCH("bwd_mlp", st, bwd_mlp_kernel<<<sh.B, kBlock, mlp_smem, st>>>(sh, p, ctx, bs, nT, nT2));
-    MGA_LAUNCH("bwd_dx", st, (bwd_dx_kernel<T, VEC, TM><<<gtile, kBlock, 0, st>>>(x, g, mask, dx, dmask, sh, ctx, bs)));
+#define MGA_CALL(L, P) MGA_LAUNCH("bwd_dx", st, (bwd_dx_kernel<T, VEC, L><<<gtile, kBlock, 0, st>>>(x, g, mask, mask_dtype, dx, dmask, sh, ctx, bs)))
+    MGA_TILE_DISPATCH(tc1, MGA_CALL);
+#undef MGA_CALL
     const int nw = 2 * sh.C * sh.hidden + sh.C + sh.hidden;
     const int nMlpBlocks = (nw + kWarpsPerBlock - 1) / kWarpsPerBlock;  // one warp per element
     MGA_LAUNCH("bwd_wgrad", st, bwd_wgrad_kernel<<<nMlpBlocks + 3 * sh.k * sh.k + 1, kBlock, 0, st>>>(sh, ctx, bs, gp, nconv, nMlpBlocks, sh.B));
     return check_launch("mga_cbam_backward");
 }
 
-template <typename T, typename TM>
-static int backward_tm(const Shape& sh, const mga_cbam_desc* d, const void* x, const void* mask, const void* g, const mga_cbam_params& p,
-                       Ctx ctx, void* dx, void* dmask, const mga_cbam_grads& gp, BwdScratch bs, cudaStream_t st) {
-    const int vec = pick_vec(sh, d->dtype, {x, g, dx});
-    if (vec == 1)
-        return backward_split<T, 1, TM>(sh, static_cast<const T*>(x), static_cast<const TM*>(mask), static_cast<const T*>(g), p, ctx,
-                                        static_cast<T*>(dx), static_cast<TM*>(dmask), gp, bs, st);
-    return backward_split<T, VecOf<T>::V, TM>(sh, static_cast<const T*>(x), static_cast<const TM*>(mask), static_cast<const T*>(g), p, ctx,
-                                              static_cast<T*>(dx), static_cast<TM*>(dmask), gp, bs, st);
-}
-
 template <typename T>
 static int backward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, const void* mask, const void* g, const mga_cbam_params& p,
                       Ctx ctx, void* dx, void* dmask, const mga_cbam_grads& gp, BwdScratch bs, cudaStream_t st) {
-    switch (d->mask_dtype) {
-        case MGA_F32: return backward_tm<T, float>(sh, d, x, mask, g, p, ctx, dx, dmask, gp, bs, st);
-        case MGA_BF16: return backward_tm<T, __nv_bfloat16>(sh, d, x, mask, g, p, ctx, dx, dmask, gp, bs, st);
-        default: return backward_tm<T, __half>(sh, d, x, mask, g, p, ctx, dx, dmask, gp, bs, st);
-    }
+    const int vec = pick_vec(sh, d->dtype, {x, g, dx});
+    if (vec == 1)
+        return backward_split<T, 1>(sh, static_cast<const T*>(x), mask, d->mask_dtype, static_cast<const T*>(g), p, ctx, static_cast<T*>(dx),
+                                    dmask, gp, bs, st);
+    return backward_split<T, VecOf<T>::V>(sh, static_cast<const T*>(x), mask, d->mask_dtype, static_cast<const T*>(g), p, ctx,
+                                          static_cast<T*>(dx), dmask, gp, bs, st);
 }
 
 }  // namespace mga
