@@ -351,25 +351,34 @@ def gpu_arm(args, rank, world, local_rank):
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             ms = float(tmax.item())
 
-        # instrumented pass: per-kernel CUDA events (same buffers, direct launches)
-        per_kernel = {}
+        # instrumented pass: per-kernel CUDA events (same buffers, direct launches, one stream); every record is tagged
+        # with the level whose call produced it
         lib.mga_profile_enable(1)
         reps = 5
+        tags = []
         for i in range(reps):
-            run_step(sets[i & 1][0], sptr)
+            plans = sets[i & 1][0]
+            for phase, order in (("fwd", list(enumerate(plans))), ("bwd", list(enumerate(plans))[::-1])):
+                for li, pl in order:
+                    n0 = lib.mga_profile_count()
+                    getattr(pl, phase)(sptr)
+                    tags += [(i, li, phase)] * (lib.mga_profile_count() - n0)
         torch.cuda.synchronize(dev)
         name, val = C.c_char_p(), C.c_float()
-        seq = []
-        for i in range(lib.mga_profile_count()):
-            _lib.check(lib.mga_profile_read(i, C.byref(name), C.byref(val)), "profile_read")
-            seq.append((name.value.decode(), val.value))
+        per_kernel = {}
+        order_keys = []
+        for idx in range(lib.mga_profile_count()):
+            _lib.check(lib.mga_profile_read(idx, C.byref(name), C.byref(val)), "profile_read")
+            rep, li, phase = tags[idx]
+            if rep == 0:
+                continue  # skip the first repetition
+            key = (phase, li, name.value.decode())
+            if key not in per_kernel:
+                order_keys.append(key)
+            per_kernel.setdefault(key, []).append(val.value)
         lib.mga_profile_enable(0)
-        per_step = len(seq) // reps
-        for r in range(1, reps):  # skip the first repetition
-            for j in range(per_step):
-                nm, v = seq[r * per_step + j]
-                per_kernel.setdefault((j, nm), []).append(v)
-        klist = [{"i": j, "kernel": nm, "ms": sum(v) / len(v)} for (j, nm), v in sorted(per_kernel.items())]
+        klist = [{"kernel": nm, "li": li, "phase": phase, "ms": sum(per_kernel[(phase, li, nm)]) / len(per_kernel[(phase, li, nm)])}
+                 for (phase, li, nm) in order_keys]
         return {"ms": ms, "launches_per_step": int(launches_per_step), "graph": graphs is not None, "kernels": klist,
                 "streams": 1 + len(sides),
                 "wall": (t_wall0, t_wall1), "sets": sets}
@@ -394,19 +403,13 @@ def gpu_arm(args, rank, world, local_rank):
         peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (of fallback)"
-    # map each launch to its level: forward order P3,P4,P5 then backward P5,P4,P3
     klist = main["kernels"]
-    fwd_n = sum(1 for k in klist if not k["kernel"].startswith("bwd") and not k["kernel"].startswith("fused_bwd"))
-    per_level_f = fwd_n // len(levels)
-    per_level_b = (len(klist) - fwd_n) // len(levels)
     best = None
     for k in klist:
-        j = k["i"]
-        li = j // per_level_f if j < fwd_n else len(levels) - 1 - (j - fwd_n) // per_level_b
-        Cc, H, W = levels[li]
+        Cc, H, W = levels[k["li"]]
         N, BS = B * Cc * H * W, B * H * W
         fn = KERNEL_BYTES.get(k["kernel"])
-        k["level"] = f"P{3 + li}"
+        k["level"] = f"P{3 + k['li']}"
         if fn is None:
             continue
         k["alg_bytes"] = fn(N, BS, esize)

@@ -45,8 +45,8 @@ enum {
     MGA_GATE_CLAMP = 1 << 2,       /* eval-mode ProbMaskGater: clamp mask to [0,1] first (probmaskgater.py:77) */
     MGA_SAMCAM_ADD = 1 << 4,       /* sam_cam_fusion = add (build-side mode, parity unpinned); default multiply = reference */
     MGA_PYRAMID_MULTIPLY = 1 << 6, /* mga_pyramid_fusion = multiply (build-side mode); default add = reference alpha-skip */
-    MGA_FORCE_SPLIT = 1 << 8,      /* never take the cluster-resident fused kernels (default behaviour in this round) */
-    MGA_USE_FUSED = 1 << 9         /* opt in to the experimental cluster-resident fused forward kernel */
+    MGA_FORCE_SPLIT = 1 << 8,      /* never take the cluster-resident fused forward kernel */
+    MGA_USE_FUSED = 1 << 9         /* take it whenever the sample fits a cluster (default: only when it fits <= 2 CTAs) */
 };
 
 typedef struct mga_cbam_desc {

@@ -6,6 +6,8 @@
 //   forward : a = sigmoid(conv7x7([pmax, pavg, m]))                       masked_cbam.py:146-147
 //   backward: dpre = k1*T*a*(1-a); dcat_k = conv7x7_T(dpre, W_k); dW_k = corr(cat_k, dpre); sum a*T
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace mga {
@@ -17,6 +19,8 @@ struct ConvGeom {
     int TWp;     // tile row pitch in floats = W + 8 (4 zero columns each side keeps 16-byte alignment)
     int rowsT;   // RB + 6
     int nStrips; // RB * W / 4
+    int planeT;  // floats per staged plane, rounded up to 128 bytes (TMA destination alignment)
+    int use_tma; // 1: the [pmax, pavg, m] tiles (+halo, zero padded) arrive by one 3-D TMA box load per plane
 };
 inline ConvGeom conv_geom(int W) {
     ConvGeom g;
@@ -24,7 +28,30 @@ inline ConvGeom conv_geom(int W) {
     g.TWp = W + 8;
     g.rowsT = g.RB + kMaxK - 1;
     g.nStrips = g.RB * (W / 4);
+    g.planeT = (g.rowsT * g.TWp + 31) & ~31;
+    g.use_tma = (g.TWp <= 256 && g.rowsT <= 256) ? 1 : 0;
     return g;
+}
+struct PlaneMaps {  // tensor maps of the three (B,H,W) fp32 planes, box = (W + 8, RB + 6, 1)
+    CUtensorMap m[3];
+};
+
+// the three planes of rows [y0-3, y0-3+rowsT) x columns [-4, W+4): one elected thread issues one box load per plane; out-of-image
+// rows / columns are zero-filled by the TMA unit -- exactly the conv's zero padding.  Every thread then waits on the mbarrier.
+__device__ __forceinline__ void stage_three_tma(float* tile, const ConvGeom& cg, const PlaneMaps& maps, bool has_mask, int b, int y0, uint64_t* bar) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    if (!has_mask)
+        for (int i = threadIdx.x; i < cg.planeT; i += kBlock) tile[2 * cg.planeT + i] = 0.0f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int np = has_mask ? 3 : 2;
+        mbar_expect_tx(bar, (uint32_t)(np * cg.rowsT * cg.TWp * 4));
+        for (int pl = 0; pl < np; ++pl) tma_load_3d(tile + pl * cg.planeT, &maps.m[pl], -4, y0 - kMaxK / 2, b, bar);
+    }
+    mbar_wait(bar, 0);
 }
 
 // Stage image rows [y_lo, y_lo+rows) of one (H,W) plane into shared memory as float4 chunks; chunk 0 and the
@@ -123,17 +150,20 @@ __device__ __forceinline__ void stage_three(float* tile, int planeT, const float
 }
 
 // ------------------------------------------------------------------ forward: grid (ceil(H/RB), B)
-__global__ void __launch_bounds__(kBlock, 4) sam_conv4_kernel(Shape sh, const float* __restrict__ wsam, Ctx ctx, ConvGeom cg) {
-    extern __shared__ __align__(16) float csm[];
+__global__ void __launch_bounds__(kBlock, 4) sam_conv4_kernel(Shape sh, const float* __restrict__ wsam, Ctx ctx, ConvGeom cg,
+                                                              const __grid_constant__ PlaneMaps maps) {
+    extern __shared__ __align__(128) float csm[];
+    __shared__ __align__(8) uint64_t bar;
     const int H = sh.H, W = sh.W, S = sh.S, b = blockIdx.y, y0 = blockIdx.x * cg.RB;
-    const int planeT = cg.rowsT * cg.TWp;
+    const int planeT = cg.planeT;
     float* tile = csm;                      // [3][rowsT][TWp]
     float* part = csm + 3 * planeT;         // [3][nStrips][4]
     float* wsm = part + 3 * cg.nStrips * 4; // [3][49]
     const int grp = threadIdx.x / kConvGroup, gl = threadIdx.x % kConvGroup;
     const float* const planes[3] = {ctx.pmax + (size_t)b * S, ctx.pavg + (size_t)b * S, sh.has_mask() ? ctx.m + (size_t)b * S : nullptr};
     load_weights7(wsam, sh.k, false, wsm);
-    stage_three(tile, planeT, planes, y0 - kMaxK / 2, cg.rowsT, H, W, cg.TWp);
+    if (cg.use_tma) stage_three_tma(tile, cg, maps, sh.has_mask(), b, y0, &bar);
+    else stage_three(tile, planeT, planes, y0 - kMaxK / 2, cg.rowsT, H, W, cg.TWp);
     __syncthreads();
     const float* w = wsm + (grp < 3 ? grp : 0) * kMaxK * kMaxK;
     const int spr = W / 4;
@@ -155,12 +185,14 @@ __global__ void __launch_bounds__(kBlock, 4) sam_conv4_kernel(Shape sh, const fl
 }
 
 // ------------------------------------------------------------------ backward: grid (ceil(H/RB), B)
-__global__ void __launch_bounds__(kBlock, 4) bwd_conv4_kernel(Shape sh, const float* __restrict__ wsam, Ctx ctx, BwdScratch bs, ConvGeom cg) {
-    extern __shared__ __align__(16) float csm[];
+__global__ void __launch_bounds__(kBlock, 4) bwd_conv4_kernel(Shape sh, const float* __restrict__ wsam, Ctx ctx, BwdScratch bs, ConvGeom cg,
+                                                              const __grid_constant__ PlaneMaps maps) {
+    extern __shared__ __align__(128) float csm[];
     __shared__ double red[32];
+    __shared__ __align__(8) uint64_t bar;
     const int H = sh.H, W = sh.W, S = sh.S, b = blockIdx.y, y0 = blockIdx.x * cg.RB;
     const int cta = blockIdx.y * gridDim.x + blockIdx.x;
-    const int planeT = cg.rowsT * cg.TWp;
+    const int planeT = cg.planeT;
     float* dpre = csm;              // [rowsT][TWp]
     float* cat = csm + planeT;      // [3][rowsT][TWp]
     float* wsm = cat + 3 * planeT;  // [3][49] flipped kernels
@@ -210,7 +242,8 @@ __global__ void __launch_bounds__(kBlock, 4) bwd_conv4_kernel(Shape sh, const fl
         }
     }
     const float* const planes[3] = {ctx.pmax + (size_t)b * S, ctx.pavg + (size_t)b * S, sh.has_mask() ? ctx.m + (size_t)b * S : nullptr};
-    stage_three(cat, planeT, planes, y0 - kMaxK / 2, cg.rowsT, H, W, cg.TWp);
+    if (cg.use_tma) stage_three_tma(cat, cg, maps, sh.has_mask(), b, y0, &bar);
+    else stage_three(cat, planeT, planes, y0 - kMaxK / 2, cg.rowsT, H, W, cg.TWp);
     __syncthreads();
     const float* w = wsm + (grp < 3 ? grp : 0) * kMaxK * kMaxK;
 

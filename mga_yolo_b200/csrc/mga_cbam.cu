@@ -114,6 +114,37 @@ static int conv_ctas(const Shape& s) {
     return std::max(generic, ((s.H + cg.RB - 1) / cg.RB) * s.B);
 }
 
+// ------------------------------------------------------------------ TMA tensor maps of the (B,H,W) fp32 planes
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// box (W + 8, RB + 6, 1) over a (B,H,W) fp32 plane; zero fill outside the image.  false -> stage with plain loads instead.
+static bool make_plane_maps(PlaneMaps* out, const float* const (&planes)[3], const Shape& sh, const ConvGeom& cg) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc || !cg.use_tma) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)sh.W, (cuuint64_t)sh.H, (cuuint64_t)sh.B};
+    const cuuint64_t strides[2] = {(cuuint64_t)sh.W * 4, (cuuint64_t)sh.S * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)cg.TWp, (cuuint32_t)cg.rowsT, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    for (int pl = 0; pl < 3; ++pl) {
+        if (planes[pl] == nullptr) { std::memset(&out->m[pl], 0, sizeof(CUtensorMap)); continue; }
+        if (reinterpret_cast<uintptr_t>(planes[pl]) & 15) return false;
+        const CUresult r = enc(&out->m[pl], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(planes[pl]), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+    }
+    return true;
+}
+
 template <typename K>
 static void allow_big_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -298,11 +329,14 @@ static int forward_split(const Shape& sh, const T* x, const void* mask, int mask
 #undef MGA_CALL
     }
     if (sh.W % 4 == 0) {
-        const ConvGeom cg = conv_geom(sh.W);
-        const size_t smem = ((size_t)3 * cg.rowsT * cg.TWp + (size_t)3 * cg.nStrips * 4 + 3 * kMaxK * kMaxK) * sizeof(float);
+        ConvGeom cg = conv_geom(sh.W);
+        PlaneMaps maps;
+        const float* const planes[3] = {ctx.pmax, ctx.pavg, sh.has_mask() ? ctx.m : nullptr};
+        if (!make_plane_maps(&maps, planes, sh, cg)) cg.use_tma = 0;
+        const size_t smem = ((size_t)3 * cg.planeT + (size_t)3 * cg.nStrips * 4 + 3 * kMaxK * kMaxK) * sizeof(float);
         allow_big_smem(sam_conv4_kernel, smem);
         const dim3 gconv((sh.H + cg.RB - 1) / cg.RB, sh.B);
-        MGA_LAUNCH("sam_conv", st, sam_conv4_kernel<<<gconv, kBlock, smem, st>>>(sh, p.wsam, ctx, cg));
+        MGA_LAUNCH("sam_conv", st, sam_conv4_kernel<<<gconv, kBlock, smem, st>>>(sh, p.wsam, ctx, cg, maps));
     } else {
         const dim3 gconv((sh.W + kConvTW - 1) / kConvTW, (sh.H + kConvTH - 1) / kConvTH, sh.B);
         MGA_LAUNCH("sam_conv", st, sam_conv_kernel<<<gconv, kBlock, 0, st>>>(sh, p.wsam, ctx));
@@ -317,6 +351,9 @@ template <typename T>
 static int forward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, const void* mask, const mga_cbam_params& p, void* out,
                      Ctx ctx, FwdScratch fs, cudaStream_t st) {
     const int vec = pick_vec(sh, d->dtype, {x, out});
+    // Cluster-resident fused forward: only when asked for (MGA_USE_FUSED).  Measured r1: alone it beats the split forward on
+    // small samples (29 us vs 44 us at B64 x C256 x 20x20) but its 227 KB CTAs evict the other levels' kernels from 128 SMs,
+    // so the three-level step got slower (0.404 vs 0.395 ms) -- not the default.  Never a function of B.
     FusedGeom gm;
     if (vec > 1 && (d->flags & MGA_USE_FUSED) && !(d->flags & MGA_FORCE_SPLIT) && fused_geometry(sh, (int)sizeof(T), false, &gm))
         return forward_fused<T>(sh, gm, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, st);
@@ -340,12 +377,15 @@ static int backward_split(const Shape& sh, const T* x, const void* mask, int mas
 #undef MGA_CALL
     int nconv;
     if (sh.W % 4 == 0) {
-        const ConvGeom cg = conv_geom(sh.W);
-        const size_t smem = ((size_t)4 * cg.rowsT * cg.TWp + 3 * kMaxK * kMaxK + 21 * 12 * kMaxK) * sizeof(float);
+        ConvGeom cg = conv_geom(sh.W);
+        PlaneMaps maps;
+        const float* const planes[3] = {ctx.pmax, ctx.pavg, sh.has_mask() ? ctx.m : nullptr};
+        if (!make_plane_maps(&maps, planes, sh, cg)) cg.use_tma = 0;
+        const size_t smem = ((size_t)4 * cg.planeT + 3 * kMaxK * kMaxK + 21 * 12 * kMaxK) * sizeof(float);
         allow_big_smem(bwd_conv4_kernel, smem);
         const dim3 gconv((sh.H + cg.RB - 1) / cg.RB, sh.B);
         nconv = gconv.x * gconv.y;
-        MGA_LAUNCH("bwd_conv", st, bwd_conv4_kernel<<<gconv, kBlock, smem, st>>>(sh, p.wsam, ctx, bs, cg));
+        MGA_LAUNCH("bwd_conv", st, bwd_conv4_kernel<<<gconv, kBlock, smem, st>>>(sh, p.wsam, ctx, bs, cg, maps));
     } else {
         const dim3 gconv((sh.W + kBT_W - 1) / kBT_W, (sh.H + kBT_H - 1) / kBT_H, sh.B);
         nconv = gconv.x * gconv.y * gconv.z;
