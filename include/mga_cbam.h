@@ -46,7 +46,8 @@ enum {
     MGA_SAMCAM_ADD = 1 << 4,       /* sam_cam_fusion = add (build-side mode, parity unpinned); default multiply = reference */
     MGA_PYRAMID_MULTIPLY = 1 << 6, /* mga_pyramid_fusion = multiply (build-side mode); default add = reference alpha-skip */
     MGA_FORCE_SPLIT = 1 << 8,      /* never take the cluster-resident fused forward kernel */
-    MGA_USE_FUSED = 1 << 9         /* take it whenever the sample fits a cluster (default: only when it fits <= 2 CTAs) */
+    MGA_USE_FUSED = 1 << 9,        /* opt in to the cluster-resident fused forward kernel (experimental) */
+    MGA_GATES_ONLY = 1 << 10       /* internal: compute / differentiate the two gates s(B,C), a(B,HW) only (concat fusion modes) */
 };
 
 typedef struct mga_cbam_desc {
@@ -103,6 +104,16 @@ int mga_cbam_forward(const mga_cbam_desc* d, const void* x, const void* mask, co
 int mga_cbam_backward(const mga_cbam_desc* d, const void* x, const void* mask, const void* grad_out,
                       const mga_cbam_params* p, const void* ctx, void* grad_x, void* grad_mask,
                       const mga_cbam_grads* gp, void* scratch, void* stream);
+
+/* Gates only (building block of the `concat` fusion modes, whose 1x1 convolutions are library GEMMs on the host side):
+ * forward fills ctx with s = channel gate (B,C) and a = spatial gate computed from x (B,HW) -- read them with
+ * mga_cbam_ctx_view; backward takes dL/ds (B,C) and dL/da (B,HW), both fp32, and returns grad_x, grad_mask and the
+ * gradients of w1,b1,w2,b2,wsam (gp->beta is written with an unspecified value). */
+int mga_cbam_gates_forward(const mga_cbam_desc* d, const void* x, const void* mask, const mga_cbam_params* p, void* ctx, void* scratch,
+                           void* stream);
+int mga_cbam_gates_backward(const mga_cbam_desc* d, const void* x, const void* mask, const float* grad_s, const float* grad_a,
+                            const mga_cbam_params* p, const void* ctx, void* grad_x, void* grad_mask, const mga_cbam_grads* gp,
+                            void* scratch, void* stream);
 
 /* read-back of small saved quantities for tests / logging: which = 0 s(B,C), 1 a(B,HW) */
 int mga_cbam_ctx_view(const mga_cbam_desc* d, const void* ctx, int which, const float** ptr, size_t* count);

@@ -16,12 +16,12 @@ ABI_VERSION = 1
 # enums of include/mga_cbam.h
 F32, BF16, F16, U8 = 0, 1, 2, 3
 HAS_MASK, SIGMOID_MASK, GATE_CLAMP = 1 << 0, 1 << 1, 1 << 2
-SAMCAM_ADD, PYRAMID_MULTIPLY, FORCE_SPLIT, USE_FUSED = 1 << 4, 1 << 6, 1 << 8, 1 << 9
+SAMCAM_ADD, PYRAMID_MULTIPLY, FORCE_SPLIT, USE_FUSED, GATES_ONLY = 1 << 4, 1 << 6, 1 << 8, 1 << 9, 1 << 10
 DS_NEAREST, DS_AREA, DS_MAXPOOL, DS_AVGPOOL, DS_AREA_RAW = 0, 1, 2, 3, 4
 
 EXPORTS = (
     "mga_abi_version", "mga_last_error", "mga_cbam_workspace", "mga_cbam_forward", "mga_cbam_backward",
-    "mga_cbam_ctx_view", "mga_mask_downsample", "mga_launch_count", "mga_profile_enable", "mga_profile_count",
+    "mga_cbam_ctx_view", "mga_mask_downsample", "mga_cbam_gates_forward", "mga_cbam_gates_backward", "mga_launch_count", "mga_profile_enable", "mga_profile_count",
     "mga_profile_read",
 )
 
@@ -68,6 +68,11 @@ def load() -> C.CDLL:
                                      C.c_void_p, C.c_void_p]
     lib.mga_cbam_backward.argtypes = [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.POINTER(Grads), C.c_void_p, C.c_void_p]
+    lib.mga_cbam_gates_forward.argtypes = [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mga_cbam_gates_backward.argtypes = [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.POINTER(Grads), C.c_void_p, C.c_void_p]
+    lib.mga_cbam_gates_forward.restype = C.c_int
+    lib.mga_cbam_gates_backward.restype = C.c_int
     lib.mga_cbam_ctx_view.argtypes = [C.POINTER(Desc), C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.mga_mask_downsample.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p]

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kBlock) bwd_conv_kernel(Shape sh, const float*
     const int k = sh.k, pad = k / 2, H = sh.H, W = sh.W, S = sh.S;
     const int b = blockIdx.z, x0 = blockIdx.x * kBT_W, y0 = blockIdx.y * kBT_H;
     const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    const float k1 = ctx.consts[1];
+    const float k1 = sh.gates_only() ? 1.0f : ctx.consts[1];
     const bool has_mask = sh.has_mask();
     const float* planes[3] = {ctx.pmax + (size_t)b * S, ctx.pavg + (size_t)b * S, ctx.m + (size_t)b * S};
     const float* Tp = bs.T + (size_t)b * S;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kBlock) bwd_mlp_kernel(Shape sh, mga_cbam_para
     float* s_dhm = s_dha + Hd;   // Hd
     const bool multiply = !sh.samcam_add();
     const bool has_mask = sh.has_mask();
-    const float k1 = ctx.consts[1];
+    const float k1 = sh.gates_only() ? 1.0f : ctx.consts[1];  // gates mode: epart (one tile) already holds dL/ds
     double gx_tot = 0.0, se_tot = 0.0;
     {
         // sum the per-tile partials: thread = (channel, tile part) so that every thread has independent loads in flight
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* 
     const bool act = u < U;
     const bool add = sh.samcam_add();
     const bool has_mask = sh.has_mask();
-    const float k0 = ctx.consts[0], k1 = ctx.consts[1];
+    const float k0 = sh.gates_only() ? 0.0f : ctx.consts[0], k1 = sh.gates_only() ? 0.0f : ctx.consts[1];  // gates mode: no direct g term
     const size_t plane = (size_t)sh.B * sh.S;
 
     float av[VEC], d0[VEC], d1[VEC], mv[VEC], racc[VEC];

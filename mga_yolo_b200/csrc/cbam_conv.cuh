@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kBlock, 4) bwd_conv4_kernel(Shape sh, const fl
     float* dwp = wsm + 3 * kMaxK * kMaxK;  // [21][12][7] dW partials of the (plane,row) thread teams
     const int grp = threadIdx.x / kConvGroup, gl = threadIdx.x % kConvGroup;
     load_weights7(wsam, sh.k, true, wsm);
-    const float k1 = ctx.consts[1];
+    const float k1 = sh.gates_only() ? 1.0f : ctx.consts[1];  // gates mode: bs.T already holds dL/da
     const float* ap = ctx.a + (size_t)b * S;
     const float* Tp = bs.T + (size_t)b * S;
     // dpre = k1 * T * a * (1 - a), and the CTA's share of sum_p a_p T_p (own rows only)

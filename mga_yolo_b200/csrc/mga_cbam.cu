@@ -341,9 +341,11 @@ static int forward_split(const Shape& sh, const T* x, const void* mask, int mask
         const dim3 gconv((sh.W + kConvTW - 1) / kConvTW, (sh.H + kConvTH - 1) / kConvTH, sh.B);
         MGA_LAUNCH("sam_conv", st, sam_conv_kernel<<<gconv, kBlock, 0, st>>>(sh, p.wsam, ctx));
     }
-    const size_t total = (size_t)planes * U;
-    const int grid = (int)std::min<size_t>((total + kBlock - 1) / kBlock, (size_t)kSMs * 32);
-    MGA_LAUNCH("rescale", st, (rescale_kernel<T, VEC><<<grid, kBlock, 0, st>>>(x, out, sh, ctx)));
+    if (!sh.gates_only()) {
+        const size_t total = (size_t)planes * U;
+        const int grid = (int)std::min<size_t>((total + kBlock - 1) / kBlock, (size_t)kSMs * 32);
+        MGA_LAUNCH("rescale", st, (rescale_kernel<T, VEC><<<grid, kBlock, 0, st>>>(x, out, sh, ctx)));
+    }
     return check_launch("mga_cbam_forward");
 }
 
@@ -355,7 +357,7 @@ static int forward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, con
     // small samples (29 us vs 44 us at B64 x C256 x 20x20) but its 227 KB CTAs evict the other levels' kernels from 128 SMs,
     // so the three-level step got slower (0.404 vs 0.395 ms) -- not the default.  Never a function of B.
     FusedGeom gm;
-    if (vec > 1 && (d->flags & MGA_USE_FUSED) && !(d->flags & MGA_FORCE_SPLIT) && fused_geometry(sh, (int)sizeof(T), false, &gm))
+    if (vec > 1 && (d->flags & MGA_USE_FUSED) && !(d->flags & (MGA_FORCE_SPLIT | MGA_GATES_ONLY)) && fused_geometry(sh, (int)sizeof(T), false, &gm))
         return forward_fused<T>(sh, gm, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, st);
     if (vec == 1) return forward_split<T, 1>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
     return forward_split<T, VecOf<T>::V>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
@@ -366,15 +368,18 @@ template <typename T, int VEC>
 static int backward_split(const Shape& sh, const T* x, const void* mask, int mask_dtype, const T* g, const mga_cbam_params& p, Ctx ctx, T* dx,
                           void* dmask, const mga_cbam_grads& gp, BwdScratch bs, cudaStream_t st) {
     const int U = sh.S / VEC;
+    const bool gates = sh.gates_only();  // dL/da is already in bs.T and dL/ds in bs.epart (one "tile"): no first reduce
     const TileCfg tc = pick_tiles(sh, U, VEC);
     const TileCfg tc1 = {tc.lpt, 1};                       // x-only reduce and dx: one unit per lane (measured faster)
-    const int nT = (U + tc.lpt * tc.upt - 1) / (tc.lpt * tc.upt);  // tiles (= per-tile partial rows) of bwd_reduce1
+    const int nT = gates ? 1 : (U + tc.lpt * tc.upt - 1) / (tc.lpt * tc.upt);  // tiles (= per-tile partial rows) of bwd_reduce1
     const int nT2 = (U + tc.lpt - 1) / tc.lpt;             // tiles of bwd_reduce2 and bwd_dx
     const dim3 gred(nT, sh.B);
     const dim3 gtile(nT2, sh.B);
+    if (!gates) {
 #define MGA_CALL(L, P) MGA_LAUNCH("bwd_reduce1", st, (bwd_reduce1_kernel<T, VEC, L, P><<<gred, kBlock, 0, st>>>(x, g, sh, ctx, bs, nT)))
-    MGA_TILE_DISPATCH(tc, MGA_CALL);
+        MGA_TILE_DISPATCH(tc, MGA_CALL);
 #undef MGA_CALL
+    }
     int nconv;
     if (sh.W % 4 == 0) {
         ConvGeom cg = conv_geom(sh.W);
@@ -497,6 +502,40 @@ int mga_cbam_backward(const mga_cbam_desc* d, const void* x, const void* mask, c
         case MGA_F32: return backward_t<float>(sh, d, x, mask, grad_out, *p, ctx, grad_x, grad_mask, *gp, bs, st);
         case MGA_BF16: return backward_t<__nv_bfloat16>(sh, d, x, mask, grad_out, *p, ctx, grad_x, grad_mask, *gp, bs, st);
         default: return backward_t<__half>(sh, d, x, mask, grad_out, *p, ctx, grad_x, grad_mask, *gp, bs, st);
+    }
+}
+
+int mga_cbam_gates_forward(const mga_cbam_desc* d, const void* x, const void* mask, const mga_cbam_params* p, void* ctx_buf, void* scratch,
+                           void* stream) {
+    if (!d) return fail(MGA_ERR_ARG, "null descriptor");
+    mga_cbam_desc g = *d;
+    g.flags |= MGA_GATES_ONLY | MGA_SAMCAM_ADD | MGA_FORCE_SPLIT;  // the spatial gate is computed from x itself (a')
+    return mga_cbam_forward(&g, x, mask, p, ctx_buf /* `out` is never written in gates mode */, ctx_buf, scratch, stream);
+}
+
+int mga_cbam_gates_backward(const mga_cbam_desc* d, const void* x, const void* mask, const float* grad_s, const float* grad_a,
+                            const mga_cbam_params* p, const void* ctx_buf, void* grad_x, void* grad_mask, const mga_cbam_grads* gp,
+                            void* scratch, void* stream) {
+    if (!d) return fail(MGA_ERR_ARG, "null descriptor");
+    if (!grad_s || !grad_a) return fail(MGA_ERR_ARG, "null gate gradient");
+    mga_cbam_desc g = *d;
+    g.flags |= MGA_GATES_ONLY | MGA_SAMCAM_ADD | MGA_FORCE_SPLIT;
+    Shape sh;
+    if (int rc = validate(&g, &sh)) return rc;
+    if (!x || !p || !ctx_buf || !grad_x || !gp || !scratch) return fail(MGA_ERR_ARG, "null pointer argument");
+    if (sh.has_mask() && !mask) return fail(MGA_ERR_ARG, "MGA_HAS_MASK set but mask is null");
+    Ctx ctx;
+    BwdScratch bs;
+    carve_ctx(sh, const_cast<void*>(ctx_buf), &ctx);
+    carve_bwd(sh, scratch, &bs);
+    bs.T = const_cast<float*>(grad_a);      // (B,S): plays sum_c g x q_c with k1 = 1
+    bs.epart = const_cast<float*>(grad_s);  // (B,1,C): the single "tile" of channel-gate gradients
+    bs.gxpart = const_cast<float*>(grad_s); // read but unused (feeds d beta only)
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (g.dtype) {  // grad_out := x (multiplied by k0 = k1 = 0 inside bwd_dx)
+        case MGA_F32: return backward_t<float>(sh, &g, x, mask, x, *p, ctx, grad_x, grad_mask, *gp, bs, st);
+        case MGA_BF16: return backward_t<__nv_bfloat16>(sh, &g, x, mask, x, *p, ctx, grad_x, grad_mask, *gp, bs, st);
+        default: return backward_t<__half>(sh, &g, x, mask, x, *p, ctx, grad_x, grad_mask, *gp, bs, st);
     }
 }
 

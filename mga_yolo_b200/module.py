@@ -28,8 +28,12 @@ _GATE_MODES = ("deterministic", "gumbel", "hard_st", "bernoulli_detach")
 # mga_pyramid_fusion: how the refined feature re-enters the pyramid
 #   add      -> x + alpha*(R - x)                         (== reference, masked_cbam.py:169-171)
 #   multiply -> alpha*R                                   (build-side definition, parity unpinned)
-SAM_CAM_FUSIONS = ("multiply", "add")
-PYRAMID_FUSIONS = ("add", "multiply")
+#   concat   -> Conv1x1([x*s ; x*a']) 2C->C with an extra learnable layer `fuse_sam_cam`      (build-side, parity unpinned)
+# mga_pyramid_fusion = concat -> Conv1x1([x ; R]) 2C->C with an extra learnable layer `fuse_pyramid`   (build-side, parity unpinned)
+# The concat modes run as: CUDA gates op (s, a') + elementwise torch ops + a cuDNN/cuBLAS 1x1 convolution (a plain library GEMM).
+SAM_CAM_FUSIONS = ("multiply", "add", "concat")
+PYRAMID_FUSIONS = ("add", "multiply", "concat")
+_BETA_ALPHA_ONE = 0.5413248546129181  # softplus(.) == 1: lets the fused op return the bare refined feature R = x*s*a
 
 
 class MaskGate(nn.Module):
@@ -84,9 +88,9 @@ class MaskGuidedCBAM(nn.Module):
         r = reduction_ratio if r is None and reduction_ratio is not None else (16 if r is None else r)
         assert r > 0 and channels > 0
         if sam_cam_fusion not in SAM_CAM_FUSIONS:
-            raise ValueError(f"sam_cam_fusion must be one of {SAM_CAM_FUSIONS} (concat: not built yet), got {sam_cam_fusion!r}")
+            raise ValueError(f"sam_cam_fusion must be one of {SAM_CAM_FUSIONS}, got {sam_cam_fusion!r}")
         if mga_pyramid_fusion not in PYRAMID_FUSIONS:
-            raise ValueError(f"mga_pyramid_fusion must be one of {PYRAMID_FUSIONS} (concat: not built yet), got {mga_pyramid_fusion!r}")
+            raise ValueError(f"mga_pyramid_fusion must be one of {PYRAMID_FUSIONS}, got {mga_pyramid_fusion!r}")
         self.C = channels
         self.r = r
         self.k = spatial_k if spatial_k % 2 == 1 else spatial_k + 1
@@ -102,6 +106,11 @@ class MaskGuidedCBAM(nn.Module):
         self.cam_mlp = nn.Sequential(nn.Linear(channels, hidden, bias=True), nn.ReLU(inplace=True), nn.Linear(hidden, channels, bias=True))
         self.sam_conv = nn.Conv2d(3, 1, kernel_size=self.k, padding=self.k // 2, bias=False)
         self.beta = nn.Parameter(torch.zeros((), dtype=torch.float32))
+        # extra layers exist only in the concat modes, so the default state_dict stays the reference's
+        if sam_cam_fusion == "concat":
+            self.fuse_sam_cam = nn.Conv2d(2 * channels, channels, kernel_size=1, bias=True)
+        if mga_pyramid_fusion == "concat":
+            self.fuse_pyramid = nn.Conv2d(2 * channels, channels, kernel_size=1, bias=True)
 
         # any non-empty MGA_PROB_MODE string switches the gate on, like os.getenv(..., False) does (masked_cbam.py:67)
         if os.getenv("MGA_PROB_MODE", False):
@@ -118,7 +127,7 @@ class MaskGuidedCBAM(nn.Module):
         f = 0
         if self.use_sigmoid_mask:
             f |= _lib.SIGMOID_MASK
-        if self.sam_cam_fusion == "add":
+        if self.sam_cam_fusion in ("add", "concat"):  # the spatial gate is computed from x itself (parallel CBAM)
             f |= _lib.SAMCAM_ADD
         if self.mga_pyramid_fusion == "multiply":
             f |= _lib.PYRAMID_MULTIPLY
@@ -149,10 +158,36 @@ class MaskGuidedCBAM(nn.Module):
             elif mask.dtype == torch.float64:
                 mask = mask.float()
         lin1, lin2 = self.cam_mlp[0], self.cam_mlp[2]
+        if "concat" in (self.sam_cam_fusion, self.mga_pyramid_fusion):
+            return self._forward_concat(feat, mask, flags)
         return ops.mask_guided_cbam(
             feat, mask, lin1.weight, lin1.bias, lin2.weight, lin2.bias, self.sam_conv.weight, self.beta,
             flags=flags, tiny_mask_thr=self.tiny_thr, eps=self.eps,
         )
+
+    def _forward_concat(self, feat: torch.Tensor, mask: Optional[torch.Tensor], flags: int) -> torch.Tensor:
+        """concat fusion modes: gates from the CUDA op, the 2C->C 1x1 convolutions from the library (cuDNN / cuBLAS)."""
+        lin1, lin2 = self.cam_mlp[0], self.cam_mlp[2]
+        dt = feat.dtype
+        if self.sam_cam_fusion == "multiply":  # R = x*s*a with a from x*s: the fused op with alpha == 1 and no identity skip
+            one = torch.full((), _BETA_ALPHA_ONE, dtype=torch.float32, device=feat.device)
+            R = ops.mask_guided_cbam(feat, mask, lin1.weight, lin1.bias, lin2.weight, lin2.bias, self.sam_conv.weight, one,
+                                     flags=(flags | _lib.PYRAMID_MULTIPLY), tiny_mask_thr=self.tiny_thr, eps=self.eps)
+        else:
+            s, a = ops.cbam_gates(feat, mask, lin1.weight, lin1.bias, lin2.weight, lin2.bias, self.sam_conv.weight,
+                                  flags=flags & ~_lib.PYRAMID_MULTIPLY, tiny_mask_thr=self.tiny_thr, eps=self.eps)
+            xs = feat * s.to(dt)[:, :, None, None]
+            xa = feat * a.to(dt)
+            if self.sam_cam_fusion == "concat":
+                R = F.conv2d(torch.cat([xs, xa], dim=1), self.fuse_sam_cam.weight.to(dt), self.fuse_sam_cam.bias.to(dt))
+            else:
+                R = xs + xa
+        if self.mga_pyramid_fusion == "concat":
+            return F.conv2d(torch.cat([feat, R], dim=1), self.fuse_pyramid.weight.to(dt), self.fuse_pyramid.bias.to(dt))
+        alpha = self.alpha.to(dt)
+        if self.mga_pyramid_fusion == "multiply":
+            return alpha * R
+        return feat + alpha * (R - feat)
 
     def extra_repr(self) -> str:  # pragma: no cover
         return (f"channels={self.C}, r={self.r}, spatial_k={self.k}, use_sigmoid_mask={self.use_sigmoid_mask}, "

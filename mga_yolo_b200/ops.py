@@ -29,6 +29,14 @@ _LIBDEF.define(
     "cbam_bwd(Tensor grad_out, Tensor x, Tensor? mask, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor wsam, Tensor beta, "
     "Tensor ctx, int flags, float tiny_thr, float eps, bool need_mask_grad) -> (Tensor, Tensor?, Tensor)"
 )
+_LIBDEF.define(
+    "cbam_gates_fwd(Tensor x, Tensor? mask, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor wsam, int flags, float tiny_thr, "
+    "float eps) -> (Tensor, Tensor, Tensor)"
+)
+_LIBDEF.define(
+    "cbam_gates_bwd(Tensor grad_s, Tensor grad_a, Tensor x, Tensor? mask, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor wsam, "
+    "Tensor ctx, int flags, float tiny_thr, float eps, bool need_mask_grad) -> (Tensor, Tensor?, Tensor)"
+)
 _LIBDEF.define("mask_downsample(Tensor src, int stride, int method, float thresh, bool close3x3, bool out_float) -> Tensor")
 
 
@@ -138,7 +146,59 @@ def _mask_downsample_cuda(src, stride, method, thresh, close3x3, out_float):
     return out[0] if squeeze else out
 
 
+def _cbam_gates_fwd_cuda(x, mask, w1, b1, w2, b2, wsam, flags, tiny_thr, eps):
+    lib = _lib.load()
+    x = x.contiguous()
+    mask = None if mask is None else mask.contiguous()
+    d, ctx_bytes, scratch_bytes = _prep(x, mask, w1, wsam, flags, tiny_thr, eps)
+    with torch.cuda.device(x.device):
+        beta = torch.zeros((), dtype=torch.float32, device=x.device)  # unused by the gates
+        keep, prm = _params(w1, b1, w2, b2, wsam, beta)
+        ctx = torch.empty(ctx_bytes, dtype=torch.uint8, device=x.device)
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=x.device)
+        rc = lib.mga_cbam_gates_forward(C.byref(d), x.data_ptr(), None if mask is None else mask.data_ptr(), C.byref(prm),
+                                        ctx.data_ptr(), scratch.data_ptr(), _stream(x))
+    _lib.check(rc, "mga_cbam_gates_forward")
+    B, Cc, H, W = x.shape
+    views = []
+    for which, shape in ((0, (B, Cc)), (1, (B, 1, H, W))):
+        ptr, cnt = C.c_void_p(0), C.c_size_t(0)
+        _lib.check(lib.mga_cbam_ctx_view(C.byref(d), ctx.data_ptr(), which, C.byref(ptr), C.byref(cnt)), "mga_cbam_ctx_view")
+        off = ptr.value - ctx.data_ptr()
+        views.append(ctx[off:off + 4 * cnt.value].view(torch.float32).view(shape).clone())
+    return views[0], views[1], ctx
+
+
+def _cbam_gates_bwd_cuda(grad_s, grad_a, x, mask, w1, b1, w2, b2, wsam, ctx, flags, tiny_thr, eps, need_mask_grad):
+    lib = _lib.load()
+    x = x.contiguous()
+    mask = None if mask is None else mask.contiguous()
+    grad_s = grad_s.float().contiguous()
+    grad_a = grad_a.float().contiguous()
+    d, _, scratch_bytes = _prep(x, mask, w1, wsam, flags, tiny_thr, eps)
+    hidden, Cc, k = w1.shape[0], x.shape[1], wsam.shape[-1]
+    n = [hidden * Cc, hidden, Cc * hidden, Cc, 3 * k * k, 1]
+    with torch.cuda.device(x.device):
+        beta = torch.zeros((), dtype=torch.float32, device=x.device)
+        keep, prm = _params(w1, b1, w2, b2, wsam, beta)
+        dx = torch.empty_like(x)
+        dmask = torch.empty_like(mask) if (mask is not None and need_mask_grad) else None
+        flat = torch.empty(sum(n), dtype=torch.float32, device=x.device)
+        offs = [0]
+        for v in n:
+            offs.append(offs[-1] + v)
+        gp = _lib.Grads(*(flat.data_ptr() + 4 * o for o in offs[:-1]))
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=x.device)
+        rc = lib.mga_cbam_gates_backward(C.byref(d), x.data_ptr(), None if mask is None else mask.data_ptr(), grad_s.data_ptr(),
+                                         grad_a.data_ptr(), C.byref(prm), ctx.data_ptr(), dx.data_ptr(),
+                                         None if dmask is None else dmask.data_ptr(), C.byref(gp), scratch.data_ptr(), _stream(x))
+    _lib.check(rc, "mga_cbam_gates_backward")
+    return dx, dmask, flat
+
+
 _LIBIMPL = torch.library.Library("mga", "IMPL")
+_LIBIMPL.impl("cbam_gates_fwd", _cbam_gates_fwd_cuda, "CUDA")
+_LIBIMPL.impl("cbam_gates_bwd", _cbam_gates_bwd_cuda, "CUDA")
 _LIBIMPL.impl("cbam_fwd", _cbam_fwd_cuda, "CUDA")
 _LIBIMPL.impl("cbam_bwd", _cbam_bwd_cuda, "CUDA")
 _LIBIMPL.impl("mask_downsample", _mask_downsample_cuda, "CUDA")
@@ -169,6 +229,41 @@ class _CbamFn(torch.autograd.Function):
             grads.append(flat[o:o + n].view(shp))
             o += n
         return (dx, dmask, *grads, None, None, None)
+
+
+class _CbamGatesFn(torch.autograd.Function):
+    """(s, a) = the channel gate (B,C) and the spatial gate computed from x (B,1,H,W), both fp32."""
+
+    @staticmethod
+    def forward(ctx, x, mask, w1, b1, w2, b2, wsam, flags, tiny_thr, eps):
+        if not x.is_cuda:
+            raise RuntimeError("mga_yolo_b200: the mask-guided CBAM path runs on CUDA tensors only (no CPU fallback)")
+        s, a, saved = torch.ops.mga.cbam_gates_fwd(x, mask, w1, b1, w2, b2, wsam, flags, tiny_thr, eps)
+        ctx.save_for_backward(x, mask, w1, b1, w2, b2, wsam, saved)
+        ctx.cfg = (flags, tiny_thr, eps)
+        ctx.param_shapes = tuple(t.shape for t in (w1, b1, w2, b2, wsam))
+        return s, a
+
+    @staticmethod
+    def backward(ctx, grad_s, grad_a):
+        x, mask, w1, b1, w2, b2, wsam, saved = ctx.saved_tensors
+        flags, tiny_thr, eps = ctx.cfg
+        need_mask = mask is not None and ctx.needs_input_grad[1]
+        dx, dmask, flat = torch.ops.mga.cbam_gates_bwd(grad_s, grad_a, x, mask, w1, b1, w2, b2, wsam, saved, flags, tiny_thr, eps, need_mask)
+        grads, o = [], 0
+        for shp in ctx.param_shapes:
+            n = 1
+            for v in shp:
+                n *= v
+            grads.append(flat[o:o + n].view(shp))
+            o += n
+        return (dx, dmask, *grads, None, None, None)
+
+
+def cbam_gates(x, mask, w1, b1, w2, b2, wsam, *, flags: int, tiny_mask_thr: float = 1e-4, eps: float = 1e-6):
+    """Differentiable gates of the block: s = sigmoid(MLP(masked avg) + MLP(masked max)) (B,C) and a' = sigmoid(conv7x7([max_c x,
+    mean_c x, m])) (B,1,H,W).  Used by the `concat` fusion modes, whose 1x1 convolutions are ordinary library GEMMs."""
+    return _CbamGatesFn.apply(x, mask, w1, b1, w2, b2, wsam, int(flags), float(tiny_mask_thr), float(eps))
 
 
 def mask_guided_cbam(x: torch.Tensor, mask: Optional[torch.Tensor], w1, b1, w2, b2, wsam, beta, *, flags: int,

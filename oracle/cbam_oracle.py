@@ -253,6 +253,30 @@ def cbam_backward(g: torch.Tensor, p: CbamParams, sv: CbamSaved) -> Dict[str, to
     }
 
 
+def cbam_forward_general(x, mask, p: CbamParams, *, sam_cam_fusion="multiply", mga_pyramid_fusion="add", fuse_sam_cam=None,
+                         fuse_pyramid=None, **kw):
+    """All nine fusion combinations, built from the same primitives (build-side definitions,
+    reference parity unpinned except multiply/add).  Differentiable with torch autograd (used in fp64 as the checker).
+    fuse_* = (weight (C,2C,1,1), bias (C)) of the extra 1x1 convolution of a `concat` mode."""
+    B, C, H, W = x.shape
+    inner = "multiply" if sam_cam_fusion == "multiply" else "add"  # where the spatial gate is computed from: x*s or x
+    _, sv = cbam_forward(x, mask, p, sam_cam_fusion=inner, mga_pyramid_fusion="add", **kw)
+    s = sv.tensors["s"][:, :, None, None]
+    a = sv.tensors["a"].reshape(B, 1, H, W)
+    if sam_cam_fusion == "multiply":
+        R = x * s * a
+    elif sam_cam_fusion == "add":
+        R = x * s + x * a
+    else:
+        R = F.conv2d(torch.cat([x * s, x * a], dim=1), fuse_sam_cam[0], fuse_sam_cam[1])
+    alpha = F.softplus(p.beta)
+    if mga_pyramid_fusion == "add":
+        return x + alpha * (R - x)
+    if mga_pyramid_fusion == "multiply":
+        return alpha * R
+    return F.conv2d(torch.cat([x, R], dim=1), fuse_pyramid[0], fuse_pyramid[1])
+
+
 def cbam_forward_autograd(x, mask, p: CbamParams, **kw):
     """Same forward, but built so torch autograd can differentiate it -- used as the CPU
     baseline in bench.py (it costs what the reference's eager path costs: one ATen call

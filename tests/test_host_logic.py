@@ -54,8 +54,10 @@ def test_module_contract_matches_reference():
     assert MaskGuidedCBAM(64, reduction_ratio=8).r == 8
     with pytest.raises(ValueError):
         MaskGuidedCBAM(64, r=16, reduction_ratio=8)
+    cc = MaskGuidedCBAM(64, sam_cam_fusion="concat", mga_pyramid_fusion="concat")  # extra 2C->C 1x1 layers only in concat modes
+    assert cc.fuse_sam_cam.weight.shape == (64, 128, 1, 1) and cc.fuse_pyramid.weight.shape == (64, 128, 1, 1)
     with pytest.raises(ValueError):
-        MaskGuidedCBAM(64, sam_cam_fusion="concat")
+        MaskGuidedCBAM(64, sam_cam_fusion="bogus")
     with pytest.raises(ValueError):
         MaskGuidedCBAM(64, mga_pyramid_fusion="nope")
     assert issubclass(MaskCBAM, MaskGuidedCBAM) and MaskCBAM(16, 4).r == 4
