@@ -71,6 +71,8 @@ KERNEL_BYTES = {
     "bwd_reduce2": lambda N, BS, e: N * e + 3 * BS * 4,   # read x, dcat0/1, idx
     "bwd_dx": lambda N, BS, e: 3 * N * e + 6 * BS * 4,    # read x, g, write dx (+ planes, dmask)
     "fused_fwd": lambda N, BS, e: 2 * N * e + 2 * BS * 4,
+    "flow_fwd": lambda N, BS, e: 2 * N * e + BS * 4,      # the whole forward: read x, mask; write out
+    "flow_bwd": lambda N, BS, e: 3 * N * e + 2 * BS * 4,  # the whole backward: read x, g, mask; write dx, dmask
     "fused_bwd": lambda N, BS, e: 3 * N * e + 3 * BS * 4,
 }
 
@@ -282,7 +284,7 @@ def gpu_arm(args, rank, world, local_rank):
 
     def flags_of(scf):
         f = _lib.SAMCAM_ADD if scf == "add" else 0
-        return f | (_lib.FORCE_SPLIT if args.force_split else 0) | (_lib.USE_FUSED if args.use_fused else 0)
+        return f | (_lib.FORCE_SPLIT if args.force_split else 0) | (_lib.USE_FUSED if args.use_fused else 0) | (_lib.USE_FLOW if args.use_flow else 0)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -573,6 +575,7 @@ def main():
     ap.add_argument("--no-variant", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--force-split", action="store_true", help="never use the cluster-resident fused kernels")
+    ap.add_argument("--use-flow", action="store_true", help="wavefront-ordered dataflow kernels (one launch per direction)")
     ap.add_argument("--use-fused", action="store_true", help="opt in to the experimental cluster-resident fused forward kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -47,6 +47,7 @@ enum {
     MGA_PYRAMID_MULTIPLY = 1 << 6, /* mga_pyramid_fusion = multiply (build-side mode); default add = reference alpha-skip */
     MGA_FORCE_SPLIT = 1 << 8,      /* never take the cluster-resident fused forward kernel */
     MGA_USE_FUSED = 1 << 9,        /* opt in to the cluster-resident fused forward kernel (experimental) */
+    MGA_USE_FLOW = 1 << 11,        /* one wavefront-ordered dataflow kernel per direction instead of one kernel per phase */
     MGA_GATES_ONLY = 1 << 10       /* internal: compute / differentiate the two gates s(B,C), a(B,HW) only (concat fusion modes) */
 };
 

@@ -134,7 +134,7 @@ __device__ __forceinline__ void stage_three(float* tile, int planeT, const float
                     const int o = yy * W + (c - 1) * 4;
 #pragma unroll
                     for (int pl = 0; pl < 3; ++pl)
-                        if (planes[pl] != nullptr) v[q][pl] = __ldg(reinterpret_cast<const float4*>(planes[pl] + o));
+                        if (planes[pl] != nullptr) v[q][pl] = __ldcg(reinterpret_cast<const float4*>(planes[pl] + o));
                 }
             }
         }
@@ -150,11 +150,10 @@ __device__ __forceinline__ void stage_three(float* tile, int planeT, const float
 }
 
 // ------------------------------------------------------------------ forward: grid (ceil(H/RB), B)
-__global__ void __launch_bounds__(kBlock, 4) sam_conv4_kernel(Shape sh, const float* __restrict__ wsam, Ctx ctx, ConvGeom cg,
-                                                              const __grid_constant__ PlaneMaps maps) {
-    extern __shared__ __align__(128) float csm[];
+__device__ __forceinline__ void sam_conv4_body(const Shape& sh, const float* __restrict__ wsam, const Ctx& ctx, const ConvGeom& cg,
+                                               const PlaneMaps* maps /* nullptr: stage with plain loads */, const Blk blk, float* csm) {
     __shared__ __align__(8) uint64_t bar;
-    const int H = sh.H, W = sh.W, S = sh.S, b = blockIdx.y, y0 = blockIdx.x * cg.RB;
+    const int H = sh.H, W = sh.W, S = sh.S, b = blk.y, y0 = blk.x * cg.RB;
     const int planeT = cg.planeT;
     float* tile = csm;                      // [3][rowsT][TWp]
     float* part = csm + 3 * planeT;         // [3][nStrips][4]
@@ -162,7 +161,7 @@ __global__ void __launch_bounds__(kBlock, 4) sam_conv4_kernel(Shape sh, const fl
     const int grp = threadIdx.x / kConvGroup, gl = threadIdx.x % kConvGroup;
     const float* const planes[3] = {ctx.pmax + (size_t)b * S, ctx.pavg + (size_t)b * S, sh.has_mask() ? ctx.m + (size_t)b * S : nullptr};
     load_weights7(wsam, sh.k, false, wsm);
-    if (cg.use_tma) stage_three_tma(tile, cg, maps, sh.has_mask(), b, y0, &bar);
+    if (cg.use_tma && maps != nullptr) stage_three_tma(tile, cg, *maps, sh.has_mask(), b, y0, &bar);
     else stage_three(tile, planeT, planes, y0 - kMaxK / 2, cg.rowsT, H, W, cg.TWp);
     __syncthreads();
     const float* w = wsm + (grp < 3 ? grp : 0) * kMaxK * kMaxK;
@@ -182,6 +181,11 @@ __global__ void __launch_bounds__(kBlock, 4) sam_conv4_kernel(Shape sh, const fl
         const float v = (part[e] + part[cg.nStrips * 4 + e]) + part[2 * cg.nStrips * 4 + e];
         ctx.a[(size_t)b * S + (y0 + ry) * W + xx] = sigmoidf_acc(v);
     }
+}
+__global__ void __launch_bounds__(kBlock, 4) sam_conv4_kernel(Shape sh, const float* __restrict__ wsam, Ctx ctx, ConvGeom cg,
+                                                              const __grid_constant__ PlaneMaps maps) {
+    extern __shared__ __align__(128) float csm_fwd[];
+    sam_conv4_body(sh, wsam, ctx, cg, &maps, this_block(), csm_fwd);
 }
 
 // ------------------------------------------------------------------ backward: grid (ceil(H/RB), B)

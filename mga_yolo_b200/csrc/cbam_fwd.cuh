@@ -16,14 +16,14 @@ namespace mga {
 // grid (tiles of kMaskTile pixels, B): writes m and one partial sum per tile; cam_mlp finalises use/den.
 constexpr int kMaskTile = 4 * kBlock;
 template <typename TM>
-__global__ void __launch_bounds__(kBlock) mask_prep_kernel(const TM* __restrict__ mask, Shape sh, Ctx ctx, FwdScratch fs) {
+__device__ __forceinline__ void mask_prep_body(const TM* __restrict__ mask, const Shape& sh, const Ctx& ctx, const FwdScratch& fs, const Blk blk) {
     __shared__ float red[32];
-    const int b = blockIdx.y;
+    const int b = blk.y;
     const int S = sh.S;
     const TM* mp = mask + (size_t)b * S;
     float* mo = ctx.m + (size_t)b * S;
     float acc = 0.0f;
-    const int p0 = blockIdx.x * kMaskTile;
+    const int p0 = blk.x * kMaskTile;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int p = p0 + i * kBlock + threadIdx.x;
@@ -36,20 +36,24 @@ __global__ void __launch_bounds__(kBlock) mask_prep_kernel(const TM* __restrict_
         }
     }
     const float tot = block_sum(acc, red);
-    if (threadIdx.x == 0) fs.mpart[(size_t)b * gridDim.x + blockIdx.x] = tot;
+    if (threadIdx.x == 0) fs.mpart[(size_t)b * blk.gx + blk.x] = tot;
+}
+template <typename TM>
+__global__ void __launch_bounds__(kBlock) mask_prep_kernel(const TM* __restrict__ mask, Shape sh, Ctx ctx, FwdScratch fs) {
+    mask_prep_body<TM>(mask, sh, ctx, fs, this_block());
 }
 
 // ------------------------------------------------------------------ F1
 // TPP threads cooperate on one (b,c) plane (TPP = 32..256, chosen so that a thread owns ~6 units):
 // every thread issues its loads four units at a time, so a whole plane is in flight at once.
 template <typename T, int VEC, int TPP>
-__global__ void __launch_bounds__(kBlock) cam_pool_kernel(const T* __restrict__ x, Shape sh, Ctx ctx, FwdScratch fs) {
+__device__ __forceinline__ void cam_pool_body(const T* __restrict__ x, const Shape& sh, const Ctx& ctx, const FwdScratch& fs, const Blk blk) {
     constexpr int kGroups = kBlock / TPP;
     constexpr int kWarpsPerPlane = TPP / 32;
     __shared__ float red[4][kWarpsPerBlock];
     const int grp = threadIdx.x / TPP, lt = threadIdx.x % TPP;
     const int planes = sh.B * sh.C;
-    int pl = blockIdx.x * kGroups + grp;
+    int pl = blk.x * kGroups + grp;
     const bool active = pl < planes;
     if (!active) pl = planes - 1;  // keep every lane alive for the shuffles
     const int b = pl / sh.C;
@@ -115,11 +119,15 @@ __global__ void __launch_bounds__(kBlock) cam_pool_kernel(const T* __restrict__ 
         fs.bidx[pl] = bidx;
     }
 }
+template <typename T, int VEC, int TPP>
+__global__ void __launch_bounds__(kBlock) cam_pool_kernel(const T* __restrict__ x, Shape sh, Ctx ctx, FwdScratch fs) {
+    cam_pool_body<T, VEC, TPP>(x, sh, ctx, fs, this_block());
+}
 
 // ------------------------------------------------------------------ F2 (one CTA per sample)
-__global__ void __launch_bounds__(kBlock) cam_mlp_kernel(Shape sh, mga_cbam_params prm, Ctx ctx, FwdScratch fs, int nMaskTiles) {
-    extern __shared__ float smem[];
-    const int C = sh.C, Hd = sh.hidden, b = blockIdx.x;
+__device__ __forceinline__ void cam_mlp_body(const Shape& sh, const mga_cbam_params& prm, const Ctx& ctx, const FwdScratch& fs, int nMaskTiles,
+                                             const Blk blk, float* smem /* 2C + 2h floats */) {
+    const int C = sh.C, Hd = sh.hidden, b = blk.x;
     float* s_avg = smem;            // C
     float* s_mx = s_avg + C;        // C
     float* s_ha = s_mx + C;         // Hd
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(kBlock) cam_mlp_kernel(Shape sh, mga_cbam_para
     if (has_mask) {
         float tot = 0.0f;
 #pragma unroll 8
-        for (int t = 0; t < nMaskTiles; ++t) tot += __ldg(fs.mpart + (size_t)b * nMaskTiles + t);  // same order in every thread
+        for (int t = 0; t < nMaskTiles; ++t) tot += ldc(fs.mpart + (size_t)b * nMaskTiles + t);  // same order in every thread
         use = (tot / (float)sh.S >= sh.tiny_thr) ? 1.0f : 0.0f;
         den = fmaxf(tot, sh.eps);
         if (threadIdx.x == 0) {
@@ -142,12 +150,12 @@ __global__ void __launch_bounds__(kBlock) cam_mlp_kernel(Shape sh, mga_cbam_para
 
     for (int c = threadIdx.x; c < C; c += kBlock) {
         const int i = b * C + c;
-        const float G = fs.sx[i] * invS;
-        const float A = has_mask ? fs.sxm[i] / den : G;
+        const float G = ldc(fs.sx + i) * invS;
+        const float A = has_mask ? ldc(fs.sxm + i) / den : G;
         const float avg = has_mask ? (A * use + G * (1.0f - use)) : G;
-        const int bi = fs.bidx[i];
+        const int bi = ldc(fs.bidx + i);
         const bool dead = bi < 0;  // no pixel with m > 0.5 (masked_cbam.py:118-121)
-        const float mx = dead ? G : fs.best[i];
+        const float mx = dead ? G : ldc(fs.best + i);
         s_avg[c] = avg;
         s_mx[c] = mx;
         ctx.avg[i] = avg;
@@ -200,18 +208,22 @@ __global__ void __launch_bounds__(kBlock) cam_mlp_kernel(Shape sh, mga_cbam_para
         ctx.s[b * C + c] = sigmoidf_acc(z);
     }
 }
+__global__ void __launch_bounds__(kBlock) cam_mlp_kernel(Shape sh, mga_cbam_params prm, Ctx ctx, FwdScratch fs, int nMaskTiles) {
+    extern __shared__ float dsm_mlp[];
+    cam_mlp_body(sh, prm, ctx, fs, nMaskTiles, this_block(), dsm_mlp);
+}
 
 // ------------------------------------------------------------------ F3
 // per pixel: max / arg max / mean over channels of x*q.  Thread mapping: TileMap (common.cuh).
 template <typename T, int VEC, int LPT, int UPT>
-__global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) sam_reduce_kernel(const T* __restrict__ x, Shape sh, Ctx ctx) {
+__device__ __forceinline__ void sam_reduce_body(const T* __restrict__ x, const Shape& sh, const Ctx& ctx, const Blk blk) {
     using TM_ = TileMap<LPT, UPT, VEC>;
     constexpr int TP = TM_::TP;
     __shared__ float sh_max[kWarpsPerBlock][TP];
     __shared__ float sh_sum[kWarpsPerBlock][TP];
     __shared__ int sh_idx[kWarpsPerBlock][TP];
     const TM_ tm;
-    const int b = blockIdx.y, tile = blockIdx.x;
+    const int b = blk.y, tile = blk.x;
     const int U = sh.S / VEC, C = sh.C;
     const bool use_q = !sh.samcam_add();
     const float* sp = ctx.s + (size_t)b * C;
@@ -240,7 +252,7 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) sam_reduce_kernel(const
         for (int kc = 0; kc < KB; ++kc) {
             const int c = c0 + kc * TM_::kChanStep;
             if (c >= C) continue;
-            const float q = use_q ? __ldg(sp + c) : 1.0f;
+            const float q = use_q ? ldc(sp + c) : 1.0f;
 #pragma unroll
             for (int k = 0; k < UPT; ++k) {
                 if (tm.unit(tile, k) >= U) continue;
@@ -292,6 +304,10 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) sam_reduce_kernel(const
         ctx.pavg[o] = bsum / (float)C;
         ctx.idx[o] = bi;
     }
+}
+template <typename T, int VEC, int LPT, int UPT>
+__global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) sam_reduce_kernel(const T* __restrict__ x, Shape sh, Ctx ctx) {
+    sam_reduce_body<T, VEC, LPT, UPT>(x, sh, ctx, this_block());
 }
 
 // ------------------------------------------------------------------ F4
@@ -345,6 +361,42 @@ __global__ void __launch_bounds__(kBlock) rescale_kernel(const T* __restrict__ x
             v[e] = v[e] * fmaf(k1, gate, k0);
         }
         stv<T, VEC, true>(out + i * VEC, v);
+    }
+}
+
+// per-sample form for the dataflow kernel: CTA `tile` of sample b rescales 8 units per thread (2048 units per CTA)
+constexpr int kRescaleUnits = 8 * kBlock;
+template <typename T, int VEC>
+__device__ __forceinline__ void rescale_tile_body(const T* __restrict__ x, T* __restrict__ out, const Shape& sh, const Ctx& ctx, float k0, float k1,
+                                                  int b, int tile) {
+    const int U = sh.S / VEC;
+    const int total = sh.C * U;  // units of one sample
+    const bool add = sh.samcam_add();
+    const size_t sbase = (size_t)b * sh.C * sh.S;
+#pragma unroll 2
+    for (int k = 0; k < 8; k += 4) {
+        float v[4][VEC], av[4][VEC], s[4];
+        int idx[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            idx[q] = tile * kRescaleUnits + (k + q) * kBlock + threadIdx.x;
+            if (idx[q] < total) {
+                const int c = idx[q] / U, u = idx[q] - c * U;
+                ldv<T, VEC, kLdLastUse>(x + sbase + (size_t)idx[q] * VEC, v[q]);
+                ldf<VEC>(ctx.a + (size_t)b * sh.S + (size_t)u * VEC, av[q]);
+                s[q] = ldc(ctx.s + b * sh.C + c);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (idx[q] >= total) continue;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const float gate = add ? (s[q] + av[q][e]) : (s[q] * av[q][e]);
+                v[q][e] *= fmaf(k1, gate, k0);
+            }
+            stv<T, VEC, true>(out + sbase + (size_t)idx[q] * VEC, v[q]);
+        }
     }
 }
 

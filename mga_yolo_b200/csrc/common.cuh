@@ -134,11 +134,11 @@ __device__ __forceinline__ void stv(T* __restrict__ p, const float (&v)[VEC]) {
 template <int VEC>
 __device__ __forceinline__ void ldf(const float* __restrict__ p, float (&v)[VEC]) {
     if constexpr (VEC == 1) {
-        v[0] = __ldg(p);
+        v[0] = __ldcg(p);
     } else {
 #pragma unroll
         for (int i = 0; i < VEC / 4; ++i) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(p) + i);
             v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
         }
     }
@@ -146,11 +146,11 @@ __device__ __forceinline__ void ldf(const float* __restrict__ p, float (&v)[VEC]
 template <int VEC>
 __device__ __forceinline__ void ldi(const int* __restrict__ p, int (&v)[VEC]) {
     if constexpr (VEC == 1) {
-        v[0] = __ldg(p);
+        v[0] = __ldcg(p);
     } else {
 #pragma unroll
         for (int i = 0; i < VEC / 4; ++i) {
-            const int4 t = __ldg(reinterpret_cast<const int4*>(p) + i);
+            const int4 t = __ldcg(reinterpret_cast<const int4*>(p) + i);
             v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
         }
     }
@@ -247,6 +247,18 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0,
                  ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
                  : "memory");
 }
+
+// ---------------------------------------------------------------- block coordinates as data
+// Every phase is written as a __device__ body that takes its block coordinates as an argument, so the same code runs
+// either as its own kernel (coordinates = blockIdx) or as one role of the wavefront-ordered dataflow kernels (cbam_flow.cuh).
+struct Blk {
+    int x, y, z, gx;  // blockIdx.x/y/z and gridDim.x of the equivalent stand-alone launch
+};
+__device__ __forceinline__ Blk this_block() { return Blk{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)gridDim.x}; }
+
+// loads of data that ANOTHER CTA of the same kernel may have produced (dataflow mode): L2-coherent, never the read-only path
+__device__ __forceinline__ float ldc(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ int ldc(const int* p) { return __ldcg(p); }
 
 // ---------------------------------------------------------------- tile kernels: thread -> (channel, unit) mapping
 // A CTA of 8 warps owns a tile of LPT*UPT units (16-byte groups of pixels) of one sample and ALL channels.

@@ -1,5 +1,6 @@
 // mga_cbam.cu -- C ABI (include/mga_cbam.h) and launch logic for the mask-guided CBAM path.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include <algorithm>
@@ -7,6 +8,7 @@
 
 #include "cbam_bwd.cuh"
 #include "cbam_conv.cuh"
+#include "cbam_flow.cuh"
 #include "cbam_fused.cuh"
 #include "cbam_fwd.cuh"
 #include "common.cuh"
@@ -186,19 +188,30 @@ static size_t carve_bwd(const Shape& s, void* base, BwdScratch* b) {
 // Tile shape of the per-pixel / per-channel reduce kernels: LPT lanes per channel row (x UPT units per lane).  Large planes
 // take 64-unit tiles; small planes shrink the tile to 16 or 8 units so that the grid still has >= ~6 CTAs per SM.
 struct TileCfg { int lpt, upt; };
-// Chosen from the per-sample plane size only (never from B): the summation order inside a sample must not depend on how
-// the batch is sharded, so a sample gives bit-identical results alone, in a batch of 8 or in a batch of 64.
+// Plane class: chosen from the per-sample plane size only (never from B): the summation order inside a sample must not
+// depend on how the batch is sharded, so a sample gives bit-identical results alone, in a batch of 8 or in a batch of 64.
+static int plane_class(int U) { return U >= 1024 ? 0 : (U >= 256 ? 1 : 2); }
 static TileCfg pick_tiles(const Shape& s, int U, int vec) {
     (void)s;
     if (vec == 1) return {32, 1};
-    if (U >= 1024) return {32, 2};
-    if (U >= 256) return {16, 1};
-    return {8, 1};
+    switch (plane_class(U)) {
+        case 0: return {32, vec == 8 ? 1 : 2};
+        case 1: return {16, 1};
+        default: return {8, 1};
+    }
+}
+static int pool_tpp(int U, int vec) {  // threads per (b,c) plane of the pooling phase
+    if (vec == 1) return U > 6 * 128 ? 256 : (U > 6 * 64 ? 128 : (U > 6 * 32 ? 64 : 32));
+    switch (plane_class(U)) {
+        case 0: return 256;
+        case 1: return 128;
+        default: return 32;
+    }
 }
 // expands to the four tile instantiations; VEC == 1 only ever uses <32,1>
 #define MGA_TILE_DISPATCH(cfg, CALL)                                   \
     do {                                                               \
-        if ((cfg).lpt == 32 && (cfg).upt == 2) { CALL(32, 2); }        \
+        if ((cfg).lpt == 32 && (cfg).upt == 2) { if constexpr (VEC != 8) { CALL(32, 2); } } \
         else if ((cfg).lpt == 32) { CALL(32, 1); }                     \
         else if ((cfg).lpt == 16) { if constexpr (VEC > 1) { CALL(16, 1); } } \
         else { if constexpr (VEC > 1) { CALL(8, 1); } }                \
@@ -300,6 +313,73 @@ static int forward_fused(const Shape& sh, const FusedGeom& gm, const T* x, const
     return launch_cluster("fused_fwd", fused_fwd_kernel<T>, gm, sh.B, st, x, mask, mask_dtype, out, sh, p, ctx, gm);
 }
 
+// ------------------------------------------------------------------ wavefront-ordered dataflow forward (one launch)
+// Steps between two dependent phases of the same sample.  A phase takes a few microseconds (it is latency bound), a step
+// (= one sample's worth of CTAs of every role) far less, so the lag is sized to ~5 us of streaming: when a role's CTAs
+// are dispatched their dependency has normally completed and nobody spins.  ~7.5 MB of feature map per lag keeps the
+// in-flight window (5-6 lags) well inside the 126 MB L2.  MGA_FLOW_LAG overrides (tuning).
+static int flow_lag(const Shape& s, int esize) {
+    if (const char* e = getenv("MGA_FLOW_LAG")) { const int v = atoi(e); if (v > 0) return v; }
+    const double sample_bytes = (double)s.C * s.S * esize;
+    const int lag = (int)(7.5e6 / sample_bytes + 0.999);
+    return std::min(std::max(lag, 2), 32);
+}
+
+static size_t flow_ctl_bytes(const Shape& s) { return align256(((size_t)kFlowMaxRoles * s.B + 16) * sizeof(unsigned)); }
+
+template <typename T>
+static bool flow_fwd_supported(const Shape& sh) {
+    constexpr int VEC = 16 / sizeof(T);
+    if (sh.S % VEC || sh.W % 4) return false;
+    const int U = sh.S / VEC;
+    const int tpp = pool_tpp(U, VEC);
+    return sh.C % (kBlock / tpp) == 0;  // a pooling CTA must not straddle two samples
+}
+
+template <typename T>
+static int forward_flow(const Shape& sh, const T* x, const void* mask, int mask_dtype, const mga_cbam_params& p, T* out, Ctx ctx, FwdScratch fs,
+                        void* ctl, cudaStream_t st) {
+    constexpr int VEC = 16 / sizeof(T);
+    const int U = sh.S / VEC;
+    const int cls = plane_class(U);
+    const TileCfg tc = pick_tiles(sh, U, VEC);
+    const int tpp = pool_tpp(U, VEC);
+    const int nMaskTiles = (sh.S + kMaskTile - 1) / kMaskTile;
+    ConvGeom cg = conv_geom(sh.W);
+    cg.use_tma = 0;  // planes are produced inside the same kernel: staged with L2-coherent loads
+    FlowSched sc{};
+    sc.nRoles = kFwdRoles;
+    sc.cnt[kFwdMask] = sh.has_mask() ? nMaskTiles : 0;
+    sc.cnt[kFwdPool] = sh.C / (kBlock / tpp);
+    sc.cnt[kFwdMlp] = 1;
+    sc.cnt[kFwdReduce] = (U + tc.lpt * tc.upt - 1) / (tc.lpt * tc.upt);
+    sc.cnt[kFwdConv] = (sh.H + cg.RB - 1) / cg.RB;
+    sc.cnt[kFwdRescale] = (sh.C * U + kRescaleUnits - 1) / kRescaleUnits;
+    sc.pre[0] = 0;
+    for (int r = 0; r < kFwdRoles; ++r) {
+        sc.lag[r] = flow_lag(sh, (int)sizeof(T)) * r;
+        sc.dep[r] = r - 1;
+        sc.pre[r + 1] = sc.pre[r] + sc.cnt[r];
+    }
+    sc.per_step = sc.pre[kFwdRoles];
+    sc.steps = sh.B + sc.lag[kFwdRoles - 1];
+    sc.done = static_cast<unsigned*>(ctl);
+    sc.err = reinterpret_cast<int*>(sc.done + (size_t)kFlowMaxRoles * sh.B);
+    cudaMemsetAsync(ctl, 0, flow_ctl_bytes(sh), st);
+    const size_t smem = std::max((size_t)(2 * sh.C + 2 * sh.hidden), (size_t)3 * cg.planeT + (size_t)3 * cg.nStrips * 4 + 3 * kMaxK * kMaxK) * sizeof(float);
+    const unsigned grid = (unsigned)sc.steps * (unsigned)sc.per_step;
+#define MGA_FLOW(CLS)                                                                                                                  \
+    do {                                                                                                                               \
+        allow_big_smem(flow_fwd_kernel<T, CLS>, smem);                                                                                 \
+        MGA_LAUNCH("flow_fwd", st, (flow_fwd_kernel<T, CLS><<<grid, kBlock, smem, st>>>(x, mask, mask_dtype, out, sh, p, ctx, fs, cg, sc, nMaskTiles))); \
+    } while (0)
+    if (cls == 0) MGA_FLOW(0);
+    else if (cls == 1) MGA_FLOW(1);
+    else MGA_FLOW(2);
+#undef MGA_FLOW
+    return check_launch("mga_cbam_forward(flow)");
+}
+
 // ------------------------------------------------------------------ forward
 template <typename T, int VEC>
 static int forward_split(const Shape& sh, const T* x, const void* mask, int mask_dtype, const mga_cbam_params& p, T* out, Ctx ctx,
@@ -315,9 +395,10 @@ static int forward_split(const Shape& sh, const T* x, const void* mask, int mask
     }
     const int planes = sh.B * sh.C;
     MGA_LAUNCH("cam_pool", st,
-        if (U > 6 * 128) cam_pool_kernel<T, VEC, 256><<<planes, kBlock, 0, st>>>(x, sh, ctx, fs);
-        else if (U > 6 * 64) cam_pool_kernel<T, VEC, 128><<<(planes + 1) / 2, kBlock, 0, st>>>(x, sh, ctx, fs);
-        else if (U > 6 * 32) cam_pool_kernel<T, VEC, 64><<<(planes + 3) / 4, kBlock, 0, st>>>(x, sh, ctx, fs);
+        const int tpp = pool_tpp(U, VEC);
+        if (tpp == 256) cam_pool_kernel<T, VEC, 256><<<planes, kBlock, 0, st>>>(x, sh, ctx, fs);
+        else if (tpp == 128) cam_pool_kernel<T, VEC, 128><<<(planes + 1) / 2, kBlock, 0, st>>>(x, sh, ctx, fs);
+        else if (tpp == 64) cam_pool_kernel<T, VEC, 64><<<(planes + 3) / 4, kBlock, 0, st>>>(x, sh, ctx, fs);
         else cam_pool_kernel<T, VEC, 32><<<(planes + 7) / 8, kBlock, 0, st>>>(x, sh, ctx, fs));
     const size_t mlp_smem = (2 * (size_t)sh.C + 2 * sh.hidden) * sizeof(float);
     MGA_LAUNCH("cam_mlp", st, cam_mlp_kernel<<<sh.B, kBlock, mlp_smem, st>>>(sh, p, ctx, fs, nMaskTiles));
@@ -351,7 +432,7 @@ static int forward_split(const Shape& sh, const T* x, const void* mask, int mask
 
 template <typename T>
 static int forward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, const void* mask, const mga_cbam_params& p, void* out,
-                     Ctx ctx, FwdScratch fs, cudaStream_t st) {
+                     Ctx ctx, FwdScratch fs, void* flow_ctl, cudaStream_t st) {
     const int vec = pick_vec(sh, d->dtype, {x, out});
     // Cluster-resident fused forward: only when asked for (MGA_USE_FUSED).  Measured r1: alone it beats the split forward on
     // small samples (29 us vs 44 us at B64 x C256 x 20x20) but its 227 KB CTAs evict the other levels' kernels from 128 SMs,
@@ -359,6 +440,8 @@ static int forward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, con
     FusedGeom gm;
     if (vec > 1 && (d->flags & MGA_USE_FUSED) && !(d->flags & (MGA_FORCE_SPLIT | MGA_GATES_ONLY)) && fused_geometry(sh, (int)sizeof(T), false, &gm))
         return forward_fused<T>(sh, gm, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, st);
+    if (vec > 1 && (d->flags & MGA_USE_FLOW) && !(d->flags & (MGA_FORCE_SPLIT | MGA_GATES_ONLY)) && flow_fwd_supported<T>(sh))
+        return forward_flow<T>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, flow_ctl, st);
     if (vec == 1) return forward_split<T, 1>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
     return forward_split<T, VecOf<T>::V>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
 }
@@ -463,7 +546,7 @@ int mga_cbam_workspace(const mga_cbam_desc* d, size_t* ctx_bytes, size_t* scratc
     FwdScratch f;
     BwdScratch b;
     if (ctx_bytes) *ctx_bytes = carve_ctx(sh, nullptr, &c);
-    if (scratch_bytes) *scratch_bytes = std::max(carve_fwd(sh, nullptr, &f), carve_bwd(sh, nullptr, &b));
+    if (scratch_bytes) *scratch_bytes = std::max(carve_fwd(sh, nullptr, &f), carve_bwd(sh, nullptr, &b)) + flow_ctl_bytes(sh);
     return MGA_OK;
 }
 
@@ -477,12 +560,14 @@ int mga_cbam_forward(const mga_cbam_desc* d, const void* x, const void* mask, co
     Ctx ctx;
     FwdScratch fs;
     carve_ctx(sh, ctx_buf, &ctx);
-    carve_fwd(sh, scratch, &fs);
+    const size_t fwd_bytes = carve_fwd(sh, scratch, &fs);
+    BwdScratch btmp;
+    void* flow_ctl = static_cast<char*>(scratch) + std::max(fwd_bytes, carve_bwd(sh, nullptr, &btmp));  // tail of the scratch buffer
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (d->dtype) {
-        case MGA_F32: return forward_t<float>(sh, d, x, mask, *p, out, ctx, fs, st);
-        case MGA_BF16: return forward_t<__nv_bfloat16>(sh, d, x, mask, *p, out, ctx, fs, st);
-        default: return forward_t<__half>(sh, d, x, mask, *p, out, ctx, fs, st);
+        case MGA_F32: return forward_t<float>(sh, d, x, mask, *p, out, ctx, fs, flow_ctl, st);
+        case MGA_BF16: return forward_t<__nv_bfloat16>(sh, d, x, mask, *p, out, ctx, fs, flow_ctl, st);
+        default: return forward_t<__half>(sh, d, x, mask, *p, out, ctx, fs, flow_ctl, st);
     }
 }
 

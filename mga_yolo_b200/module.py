@@ -135,6 +135,8 @@ class MaskGuidedCBAM(nn.Module):
             f |= _lib.FORCE_SPLIT
         elif os.getenv("MGA_USE_FUSED", ""):  # experimental cluster-resident fused forward kernel
             f |= _lib.USE_FUSED
+        elif os.getenv("MGA_USE_FLOW", ""):  # wavefront-ordered dataflow kernels
+            f |= _lib.USE_FLOW
         return f
 
     def forward(self, x: Union[torch.Tensor, Sequence[torch.Tensor]]) -> torch.Tensor:

@@ -13,6 +13,8 @@ reps = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4].isdigit() else 3
 flags = _lib.FORCE_SPLIT if "--split" in sys.argv else 0
 if "--add" in sys.argv:
     flags |= _lib.SAMCAM_ADD
+if "--flow" in sys.argv:
+    flags |= _lib.USE_FLOW
 levels, B, dtname, _ = WORKLOADS[wl]
 Cc, H, W = levels[li]
 dev = torch.device("cuda:0")
