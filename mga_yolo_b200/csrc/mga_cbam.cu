@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "cbam_bwd.cuh"
+#include "cbam_cluster.cuh"
 #include "cbam_conv.cuh"
 #include "cbam_flow.cuh"
 #include "cbam_fused.cuh"
@@ -110,7 +111,7 @@ static size_t carve_ctx(const Shape& s, void* base, Ctx* c) {
 
 static int tiles_of(const Shape& s, int vec) { return (s.S / vec + 31) / 32; }
 static int conv_ctas(const Shape& s) {
-    const int generic = ((s.W + kConvTW - 1) / kConvTW) * ((s.H + kConvTH - 1) / kConvTH) * s.B;
+    const int generic = std::max(((s.W + kConvTW - 1) / kConvTW) * ((s.H + kConvTH - 1) / kConvTH) * s.B, 16 * s.B);  // 16: cluster path
     if (s.W % 4) return generic;
     const ConvGeom cg = conv_geom(s.W);
     return std::max(generic, ((s.H + cg.RB - 1) / cg.RB) * s.B);
@@ -313,6 +314,93 @@ static int forward_fused(const Shape& sh, const FusedGeom& gm, const T* x, const
     return launch_cluster("fused_fwd", fused_fwd_kernel<T>, gm, sh.B, st, x, mask, mask_dtype, out, sh, p, ctx, gm);
 }
 
+
+// ------------------------------------------------------------------ cluster-per-sample path (cbam_cluster.cuh): geometry + launch
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+// Smallest cluster whose per-CTA share of the sample (x, plus g in backward) is <= ~224 KB: with 2 CTAs per SM that keeps
+// ~60 MB of feature map in flight on the whole GPU, well inside the 126 MB L2, so the later passes are L2 hits.
+// Chosen from the per-sample shape only (never from B).  false -> the one-kernel-per-phase path is used.
+static bool cl_geometry(const Shape& sh, int esize, bool bwd, ClGeom* out) {
+    static const int enabled = env_int("MGA_CL", 1);
+    static const int kb_f = env_int("MGA_CL_KB_F", 224), kb_b = env_int("MGA_CL_KB_B", 224);
+    static const int cs_f = env_int("MGA_CL_CS_F", 0), cs_b = env_int("MGA_CL_CS_B", 0);  // tuning overrides
+    if (!enabled || sh.gates_only()) return false;
+    const int vec = 16 / esize;
+    if (sh.S % vec || sh.W % 4 || sh.C < 1) return false;
+    const int K = vec == 4 ? 7 : 4;
+    int rowq = 1;
+    while ((rowq * sh.W) % vec) ++rowq;
+    const double bytes = (double)sh.C * sh.S * esize * (bwd ? 2.0 : 1.0);
+    const double target = 1024.0 * (bwd ? kb_b : kb_f);
+    const int forced = bwd ? cs_b : cs_f;
+    ClGeom best{};
+    bool have = false;
+    for (int CS = 1; CS <= 16; CS *= 2) {
+        int rowsPer = (sh.H + CS - 1) / CS;
+        rowsPer = (rowsPer + rowq - 1) / rowq * rowq;
+        if (CS > 1 && (CS - 1) * rowsPer >= sh.H) break;  // trailing ranks would own nothing
+        const int nP = rowsPer * sh.W, nU = nP / vec;
+        if (nU > 32 * K || nU > kCT) continue;
+        ClGeom g{};
+        g.CS = CS;
+        g.rowsPer = rowsPer;
+        g.nUmax = nU;
+        g.nPmax = nP;
+        g.G = std::max(1, std::min(kCT / nU, sh.C));
+        g.lsh = 0;
+        while ((K << g.lsh) < nU) ++g.lsh;
+        g.tileRows = rowsPer + kMaxK - 1;
+        g.TWp = sh.W + 8;
+        g.planeT = (g.tileRows * g.TWp + 31) & ~31;
+        g.smem_bytes = 4 * (bwd ? cl_bwd_off(sh.C, sh.hidden, g).total : cl_fwd_off(sh.C, sh.hidden, g).total);
+        if (g.smem_bytes > kSmemLimit) continue;
+        best = g;
+        have = true;
+        if (forced ? CS >= forced : bytes / CS <= target) break;
+    }
+    if (!have) return false;
+    if (!forced && bytes / best.CS > 2.0 * target) return false;  // sample too large to stay L2-resident: split path
+    *out = best;
+    return true;
+}
+
+template <typename Kern, typename... Args>
+static int launch_cl(const char* name, Kern kernel, const ClGeom& gm, int nClusters, cudaStream_t st, Args... args) {
+    static thread_local const void* configured[16] = {};
+    bool done = false;
+    for (const void* c : configured) done |= (c == (const void*)kernel);
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return fail(MGA_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+        for (auto& c : configured)
+            if (!c) { c = (const void*)kernel; break; }
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(nClusters * gm.CS));
+    cfg.blockDim = dim3(kCT);
+    cfg.dynamicSmemBytes = (size_t)gm.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)gm.CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    {
+        LaunchScope ls(name, st);
+        e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    }
+    if (e != cudaSuccess) return fail(MGA_ERR_CUDA, "%s: launch (cluster %d, %d B smem): %s", name, gm.CS, gm.smem_bytes, cudaGetErrorString(e));
+    return MGA_OK;
+}
+
 // ------------------------------------------------------------------ wavefront-ordered dataflow forward (one launch)
 // Steps between two dependent phases of the same sample.  A phase takes a few microseconds (it is latency bound), a step
 // (= one sample's worth of CTAs of every role) far less, so the lag is sized to ~5 us of streaming: when a role's CTAs
@@ -442,6 +530,9 @@ static int forward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, con
         return forward_fused<T>(sh, gm, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, st);
     if (vec > 1 && (d->flags & MGA_USE_FLOW) && !(d->flags & (MGA_FORCE_SPLIT | MGA_GATES_ONLY)) && flow_fwd_supported<T>(sh))
         return forward_flow<T>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, flow_ctl, st);
+    ClGeom cgm;
+    if (vec > 1 && !(d->flags & MGA_FORCE_SPLIT) && cl_geometry(sh, (int)sizeof(T), false, &cgm))
+        return launch_cl("cl_fwd", cl_fwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), mask, d->mask_dtype, static_cast<T*>(out), sh, p, ctx, cgm);
     if (vec == 1) return forward_split<T, 1>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
     return forward_split<T, VecOf<T>::V>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
 }
@@ -499,6 +590,16 @@ template <typename T>
 static int backward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, const void* mask, const void* g, const mga_cbam_params& p,
                       Ctx ctx, void* dx, void* dmask, const mga_cbam_grads& gp, BwdScratch bs, cudaStream_t st) {
     const int vec = pick_vec(sh, d->dtype, {x, g, dx});
+    ClGeom cgm;
+    if (vec > 1 && !(d->flags & MGA_FORCE_SPLIT) && cl_geometry(sh, (int)sizeof(T), true, &cgm)) {
+        if (int rc = launch_cl("cl_bwd", cl_bwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), static_cast<const T*>(g), mask, d->mask_dtype,
+                               static_cast<T*>(dx), dmask, sh, p, ctx, bs, cgm))
+            return rc;
+        const int nw = 2 * sh.C * sh.hidden + sh.C + sh.hidden;
+        const int nMlpBlocks = (nw + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        MGA_LAUNCH("bwd_wgrad", st, bwd_wgrad_kernel<<<nMlpBlocks + 3 * sh.k * sh.k + 1, kBlock, 0, st>>>(sh, ctx, bs, gp, sh.B * cgm.CS, nMlpBlocks, sh.B));
+        return check_launch("mga_cbam_backward(cluster)");
+    }
     if (vec == 1)
         return backward_split<T, 1>(sh, static_cast<const T*>(x), mask, d->mask_dtype, static_cast<const T*>(g), p, ctx, static_cast<T*>(dx),
                                     dmask, gp, bs, st);
