@@ -431,7 +431,7 @@ def gpu_arm(args, rank, world, local_rank):
                     "step_frac_of_8TBps_nominal": round(alg_bytes / (main["ms"] * 1e-3) / 1e9 / 8000.0, 4)}
 
     # ---- e2e: public module API, host buffers
-    e2e = e2e_module(args, dev, levels, B, dtype, world, alg_bytes)
+    e2e = None if args.no_e2e else e2e_module(args, dev, levels, B, dtype, world, alg_bytes)
 
     sampler.stop()
     clocks = sampler.summary(t0w, t1w)
@@ -574,6 +574,7 @@ def main():
     ap.add_argument("--one-stream", action="store_true", help="run the three levels back to back on one stream")
     ap.add_argument("--no-variant", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer end-to-end measurement")
     ap.add_argument("--force-split", action="store_true", help="never use the cluster-resident fused kernels")
     ap.add_argument("--use-flow", action="store_true", help="wavefront-ordered dataflow kernels (one launch per direction)")
     ap.add_argument("--use-fused", action="store_true", help="opt in to the experimental cluster-resident fused forward kernel")

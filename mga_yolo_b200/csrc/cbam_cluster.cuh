@@ -14,9 +14,13 @@
 //   * the 7x7 convolution needs 3 halo rows of the 3-plane map (forward) / of dpre (backward) from the neighbouring
 //     CTAs' tiles: read through DSMEM after a cluster barrier.
 //
-// Two thread -> data mappings (both runtime-shaped, so one instantiation per element type):
-//   T1 "channel rows": a group of LPT lanes owns one channel, lane = up to K units (16 B of pixels) of the CTA's pixel
-//      range -> per-CHANNEL sums are thread-private and need one shuffle reduction per channel (pool, bwd reduce 1/2);
+// Two thread -> data mappings (both runtime-shaped, so one instantiation per element type).  The kernels are
+// instruction-issue bound before they are bandwidth bound, so both are written for few instructions per element:
+// addresses are one mad.wide per access off a running row pointer, per-channel constants sit in shared memory in the
+// order the thread walks them (128-bit reads), reductions across threads go through shared memory, not shuffles.
+//   T1 "channel rows": LPT consecutive threads own one channel slot, thread = K units (16 B of pixels) of the CTA's
+//      pixel range -> per-CHANNEL sums are thread-private; the LPT partials of a channel are staged in shared memory and
+//      summed in a fixed order afterwards (pool, bwd reduce 1 / 2);
 //   T2 "pixel columns": thread = (unit, channel group), loops over the channels of its group -> per-PIXEL sums / max are
 //      thread-private (channel max/mean, rescale, dx); the G channel groups merge through shared memory.
 //
@@ -31,34 +35,45 @@
 namespace mga {
 namespace cgx = cooperative_groups;
 
-constexpr int kCT = 256;        // threads per CTA (== kBlock: the conv helpers stride by kBlock)
-constexpr int kCW = kCT / 32;
-static_assert(kCT == kBlock, "conv helpers assume kBlock threads");
+#ifndef MGA_CL_NT_F
+#define MGA_CL_NT_F 512  // threads per CTA of the forward kernel (64 registers per thread, 2 CTAs per SM = 32 warps per SM)
+#endif
+#ifndef MGA_CL_NT_B
+#define MGA_CL_NT_B 256  // ... of the backward kernel (128 registers per thread)
+#endif
+constexpr int kClNTF = MGA_CL_NT_F, kClNTB = MGA_CL_NT_B;
+constexpr int kClWmax = 16;  // most warps per CTA (sizes the warp-private bins of the backward kernel)
+constexpr int kClK = 5;   // T1: units per thread and channel
 
 #ifndef MGA_CL_HINTS
 #define MGA_CL_HINTS 1  // L2 eviction-priority hints: first touch of x/g = keep, last read = evict first
 #endif
-#ifndef MGA_CL_MINB
-#define MGA_CL_MINB 2   // resident CTAs per SM the register allocation must allow
+#ifndef MGA_CL_MINB_F
+#define MGA_CL_MINB_F 2  // resident CTAs per SM the register allocation of the forward kernel must allow
+#endif
+#ifndef MGA_CL_MINB_B
+#define MGA_CL_MINB_B 2  // ... of the backward kernel
 #endif
 
 struct ClGeom {
+    int NT;        // threads per CTA
     int CS;        // CTAs per cluster (= per sample)
     int rowsPer;   // image rows per CTA
     int nUmax;     // 16-byte units per CTA (rowsPer * W / VEC)
     int nPmax;     // pixels per CTA
-    int G;         // T2: channel groups = kCT / nUmax
-    int lsh;       // T1: log2(lanes per channel)
+    int G;         // T2: channel groups = NT / nUmax
+    int CG;        // T2: channels per group, rounded up to a multiple of 8 (group-major constant arrays)
+    int LPT;       // T1: threads per channel slot = ceil(nUmax / K)
+    int slots;     // T1: channel slots = NT / LPT
     int tileRows;  // rowsPer + 6
     int TWp;       // W + 8
     int planeT;    // floats per tile plane (multiple of 32)
     int smem_bytes;
+    int prefetch;  // 1: bulk L2 prefetch of the sample at kernel start, so the HBM stream overlaps the latency-bound prologue
 };
 
-template <int VEC> struct ClK { static constexpr int K = (VEC == 4) ? 7 : 4; };  // T1 units per lane
-
 // ---------------------------------------------------------------- shared-memory layouts (float offsets)
-struct ClFwdOff { int wk, red, avg, mx, ha, hm, sA, sB, q, mypart, part, msum, mloc, aloc, tile, mg, total; };
+struct ClFwdOff { int wk, red, avg, mx, ha, hm, sAB, q, part, msum, mloc, aloc, tile, mg, stage, total; };
 __host__ __device__ inline ClFwdOff cl_fwd_off(int C, int Hd, const ClGeom& g) {
     ClFwdOff o;
     int p = 0;
@@ -66,21 +81,25 @@ __host__ __device__ inline ClFwdOff cl_fwd_off(int C, int Hd, const ClGeom& g) {
     o.wk = take(3 * kMaxK * kMaxK);
     o.red = take(64);
     o.avg = take(C); o.mx = take(C); o.ha = take(Hd); o.hm = take(Hd);
-    o.sA = take(C); o.sB = take(C); o.q = take(C);
-    o.mypart = take(4 * C);
-    o.part = take(4 * C * g.CS);
+    o.sAB = take(2 * g.G * g.CG);   // group-major (A,B) pairs of the rescale
+    o.q = take(g.G * g.CG);         // group-major q
+    o.part = take(4 * C * g.CS);    // pool partials of every rank (pushed)
     o.msum = take(16);
-    o.mloc = take(g.nPmax);
+    o.mloc = take(g.LPT * kClK * 8);  // m of the own pixels, zero padded to the T1 footprint
+    // the T1 per-thread partials [4][C][LPT|1] of the pooling phase are dead before the planes exist: same storage
+    o.stage = p;
     o.aloc = take(g.nPmax);
     o.tile = take(3 * g.planeT);
     o.mg = take(3 * g.G * g.nPmax);  // T2 merge buffers [max | sum | idx][G][nPmax]; later the conv's per-plane partials [3][nPmax]
+    const int stage_end = o.stage + ((4 * C * (g.LPT | 1) + 3) & ~3);
+    if (p < stage_end) p = stage_end;
     o.total = p;
     return o;
 }
 
 struct ClBwdOff {
-    int wsm, red, s, q, chA, chB, amx, dz, eloc, qloc, binloc, dha, dhm, epart, qpart, binpart, gxpart;
-    int aloc, ae, mloc, idx, pmx, d0, d1s, d2, dpre, cat, tp, dwp, binw, total;
+    int wsm, red, s, chA, chG, amx, cM, dz, eloc, qloc, binloc, dha, dhm, q, epart, qpart, binpart, gxpart;
+    int aloc, ae, mloc, idx, pmx, d0, d1s, d2, dpre, cat, tp, dwp, binw, stage, total;
 };
 __host__ __device__ inline ClBwdOff cl_bwd_off(int C, int Hd, const ClGeom& g) {
     ClBwdOff o;
@@ -88,20 +107,26 @@ __host__ __device__ inline ClBwdOff cl_bwd_off(int C, int Hd, const ClGeom& g) {
     auto take = [&p](int n) { const int r = p; p += (n + 3) & ~3; return r; };
     o.wsm = take(3 * kMaxK * kMaxK);
     o.red = take(64);  // 32 doubles
-    o.s = take(C); o.q = take(C);
-    o.chA = take(4 * C); o.chB = take(2 * C); o.amx = take(C);
+    o.s = take(C);
+    o.chA = take(4 * g.G * g.CG);  // group-major (A, B, q, cA)
+    o.chG = take(g.G * g.CG);      // group-major cG
+    o.amx = take(C); o.cM = take(C);
     o.dz = take(C); o.eloc = take(C); o.qloc = take(C); o.binloc = take(C);
     o.dha = take(Hd); o.dhm = take(Hd);
+    o.q = take(C);
     o.epart = take(C * g.CS); o.qpart = take(C * g.CS); o.binpart = take(C * g.CS);
     o.gxpart = take(2 * 16);  // doubles
-    o.aloc = take(g.nPmax); o.ae = take(g.nPmax); o.mloc = take(g.nPmax); o.idx = take(g.nPmax); o.pmx = take(g.nPmax);
-    o.d0 = take(g.nPmax); o.d1s = take(g.nPmax); o.d2 = take(g.nPmax);
+    const int padP = g.LPT * kClK * 8;  // T1 footprint in pixels (>= nPmax), zero padded
+    o.aloc = take(g.nPmax); o.ae = take(padP); o.mloc = take(g.nPmax); o.idx = take(g.nPmax); o.pmx = take(g.nPmax);
+    o.d0 = take(g.nPmax); o.d1s = take(padP); o.d2 = take(g.nPmax);
     o.dpre = take(g.planeT);
     o.cat = take(3 * g.planeT);
-    const int tpn = (kCW > g.G ? kCW : g.G) * g.nPmax;
-    o.tp = take(tpn);          // T partials of the 8 warps, later the R partials of the G channel groups
-    o.dwp = take(21 * 12 * kMaxK);
-    o.binw = take(kCW * C);
+    int tpn = (g.slots > g.G ? g.slots : g.G) * g.nPmax;
+    if (tpn < 21 * 12 * kMaxK) tpn = 21 * 12 * kMaxK;
+    o.tp = take(tpn);          // T partials of the channel slots, then the dW team partials, then the R partials of the G channel groups
+    o.dwp = o.tp;
+    o.binw = take((g.NT / 32) * C);
+    o.stage = take(C * (g.LPT | 1));
     o.total = p;
     return o;
 }
@@ -134,6 +159,17 @@ __device__ __forceinline__ uint4 ldg128(const void* p, const ClPol& pol) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
 #endif
     return t;
+}
+// base + 32-bit byte offset in ONE instruction (IMAD.WIDE.U32)
+__device__ __forceinline__ const char* addw(const char* base, unsigned off) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(off), "l"(base));
+    return reinterpret_cast<const char*>(r);
+}
+__device__ __forceinline__ char* addw(char* base, unsigned off) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(off), "l"(base));
+    return reinterpret_cast<char*>(r);
 }
 template <typename T, int VEC>
 __device__ __forceinline__ void unpack(const uint4& t, float (&v)[VEC]) {
@@ -193,15 +229,49 @@ __device__ __forceinline__ void lds_i(const int* p, int (&v)[VEC]) {
     }
 }
 
-// block-wide fp64 sum over kCT threads (result in every thread)
-__device__ __forceinline__ double cl_block_sum_d(double v, double* sh /* >= 32 */) { return block_sum_d(v, sh); }
+// Asynchronous L2 prefetch of this CTA's 1/CS share of the sample's CONTIGUOUS bytes (the cluster needs the whole sample):
+// a few bulk-prefetch instructions issued by one thread, executed by the copy engine -- no registers, no scoreboard, no
+// back-pressure on the compute warps.  The HBM -> L2 stream then runs at full speed underneath the latency-bound prologue.
+__device__ __forceinline__ void cl_prefetch_share(const void* sample, size_t sample_bytes, int r, int CS) {
+    if (threadIdx.x != 0) return;
+    size_t share = (sample_bytes / (size_t)CS + 15) & ~(size_t)15;
+    size_t lo = (size_t)r * share;
+    if (lo >= sample_bytes) return;
+    size_t hi = lo + share < sample_bytes ? lo + share : (sample_bytes & ~(size_t)15);
+    const char* base = static_cast<const char*>(sample);
+    constexpr size_t kChunk = 32768;
+    for (size_t o = lo; o < hi; o += kChunk) {
+        const unsigned n = (unsigned)(hi - o < kChunk ? hi - o : kChunk);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + o), "r"(n) : "memory");
+    }
+}
+
+// position of channel c in the group-major constant arrays: thread group g walks g, g+G, g+2G ... -> consecutive floats
+__device__ __forceinline__ int cl_gm(int c, int G, int CG) { const int j = c / G; return (c - j * G) * CG + j; }
+
+// sum the LPT staged partials of every channel in a fixed order: dst[c] = sum_j stage[c*(LPT|1) + j]
+template <int NT>
+__device__ __forceinline__ void cl_stage_sum(const float* stage, float* dst, int C, int LPT) {
+    const int LPTp = LPT | 1;
+    const int tpc = C * 2 > NT ? 1 : (C * 4 > NT ? 2 : (C * 8 > NT ? 4 : 8));  // threads per channel (power of two)
+    const int sl = threadIdx.x & (tpc - 1);
+    for (int c0 = 0; c0 < C; c0 += NT / tpc) {
+        const int c = c0 + (int)threadIdx.x / tpc;
+        float acc = 0.0f;
+        if (c < C)
+            for (int j = sl; j < LPT; j += tpc) acc += stage[c * LPTp + j];
+        for (int of = tpc >> 1; of > 0; of >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, of);
+        if (c < C && sl == 0) dst[c] = acc;
+    }
+}
 
 // fetch the halo rows of `nplanes` tile planes from the CTAs that own them (DSMEM); own rows and padding stay untouched
+template <int NT>
 __device__ __forceinline__ void cl_fetch_halo(cgx::cluster_group& cluster, float* tile, int nplanes, const ClGeom& gm, int y0, int rows, int H,
                                               int W) {
     const int cpr = W / 4;  // float4 chunks per image row
     const int per = 6 * cpr;
-    for (int i = threadIdx.x; i < nplanes * per; i += kCT) {
+    for (int i = threadIdx.x; i < nplanes * per; i += NT) {
         const int pl = i / per, rem = i - pl * per;
         const int hr = rem / cpr, ch = rem - hr * cpr;       // halo row 0..5: 3 above, 3 below
         const int tr = hr < 3 ? hr : rows + hr;              // tile row (own rows are 3 .. 3+rows-1)
@@ -217,10 +287,12 @@ __device__ __forceinline__ void cl_fetch_halo(cgx::cluster_group& cluster, float
 
 // ================================================================== forward
 template <typename T>
-__global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __restrict__ x, const void* __restrict__ mask, int mdt,
+__global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* __restrict__ x, const void* __restrict__ mask, int mdt,
                                                                   T* __restrict__ out, Shape sh, mga_cbam_params prm, Ctx ctx, ClGeom gm) {
     constexpr int VEC = 16 / sizeof(T);
-    constexpr int K = ClK<VEC>::K;
+    constexpr int K = kClK;
+    constexpr int NT = kClNTF, NW = NT / 32;
+    constexpr int kGrp = NT / 3;  // conv: threads per input plane
     extern __shared__ __align__(128) float clsm[];
     float* const csm = clsm;
     cgx::cluster_group cluster = cgx::this_cluster();
@@ -233,6 +305,7 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
     const int rows = max(0, min(gm.rowsPer, H - y0));
     const int nP = rows * W, nU = nP / VEC, p0 = y0 * W;
     const int nPmax = gm.nPmax, nUmax = gm.nUmax, TWp = gm.TWp, planeT = gm.planeT;
+    const int G = gm.G, CG = gm.CG;
     const bool has_mask = sh.has_mask();
     const ClFwdOff o = cl_fwd_off(C, Hd, gm);
     float* wk = csm + o.wk;
@@ -241,37 +314,36 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
     float* s_mx = csm + o.mx;
     float* s_ha = csm + o.ha;
     float* s_hm = csm + o.hm;
-    float* sA = csm + o.sA;
-    float* sB = csm + o.sB;
+    float2* sAB = reinterpret_cast<float2*>(csm + o.sAB);
     float* s_q = csm + o.q;
-    float* mypart = csm + o.mypart;
     float* part = csm + o.part;
     float* msum_part = csm + o.msum;
     float* mloc = csm + o.mloc;
     float* aloc = csm + o.aloc;
     float* tile = csm + o.tile;  // [pmax | pavg | m][tileRows][TWp]
     float* mg = csm + o.mg;
+    float* stage = csm + o.stage;
     const ClPol pol = cl_policies();
-    const size_t bS = (size_t)b * S;
+    const unsigned rowB = (unsigned)S * (unsigned)sizeof(T);  // bytes per channel plane
 
+    const size_t bS = (size_t)b * S;
     // ---- phase 0: zero the tile (padding), conv weights, mask -> m (own pixels), sum(m)
     stamp(0);
     cluster.barrier_arrive();  // #0 (waited before the first push): every CTA of the cluster has started
-    for (int i = tid; i < 3 * planeT; i += kCT) tile[i] = 0.0f;
-    load_weights7(prm.wsam, sh.k, false, wk);
+    if (gm.prefetch) cl_prefetch_share(x + (size_t)b * C * S, (size_t)C * rowB, r, CS);
+    for (int i = nP + tid; i < gm.LPT * K * VEC; i += NT) mloc[i] = 0.0f;  // padding of the T1 footprint
+    cl_load_weights7<NT>(prm.wsam, sh.k, false, wk);
     __syncthreads();
     float mtot = 0.0f;
     {
         float macc = 0.0f;
-        for (int i = tid; i < nP; i += kCT) {
+        for (int i = tid; i < nP; i += NT) {
             float v = 1.0f;
             if (has_mask) {
                 v = load_mask_any(mask, mdt, bS + p0 + i);
                 if (sh.gate_clamp()) v = fminf(fmaxf(v, 0.0f), 1.0f);
                 if (sh.sigmoid_mask()) v = sigmoidf_acc(v);
                 ctx.m[bS + p0 + i] = v;
-                const int ry = i / W, cx = i - ry * W;
-                tile[2 * planeT + (3 + ry) * TWp + 4 + cx] = v;
                 macc += v;
             }
             mloc[i] = v;
@@ -282,57 +354,83 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
 
     // ---- phase 1 (T1): per channel over the CTA's pixels: sum x*m, sum x, masked max + arg max
     stamp(1);
-    const int lsh = gm.lsh, LPT = 1 << lsh, CPW = 32 >> lsh;
-    const int sub = lane >> lsh, ul = lane & (LPT - 1);
-    const T* xb = x + (size_t)b * C * S + p0;  // the CTA's pixel range of channel 0
-    for (int cb = w * CPW; cb < C; cb += kCW * CPW) {
-        const int c = cb + sub;
-        const bool cok = c < C;
-        uint4 raw[K];
+    const int LPT = gm.LPT, LPTp = LPT | 1, slots = gm.slots;
+    const int slot = tid / LPT, ul = tid - slot * LPT;
+    const char* xbytes = reinterpret_cast<const char*>(x + (size_t)b * C * S + p0);  // the CTA's pixel range of channel 0
+    if (slot < slots) {
+        unsigned offk[K];
+        int nk = 0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const int u = ul + (k << lsh);
-            if (cok && u < nU) raw[k] = ldg128<kPolKeep>(xb + (size_t)c * S + (size_t)u * VEC, pol);
+            const int u = ul + k * LPT;
+            offk[k] = (unsigned)u * 16u;
+            nk += (u < nU) ? 1 : 0;
         }
-        float sxm = 0.0f, sx = 0.0f, best = -INFINITY;
-        int bidx = -1;
+        // software pipelined: the loads of the next channel are in flight while this one is reduced
+        uint4 nxt[K];
+        if (slot < C) {
+            const char* row = xbytes + (size_t)slot * rowB;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int u = ul + (k << lsh);
-            if (cok && u < nU) {
-                float v[VEC], mv[VEC];
-                unpack<T, VEC>(raw[k], v);
-                lds_f<VEC>(mloc + u * VEC, mv);
+            for (int k = 0; k < K; ++k)
+                if (k < nk) nxt[k] = ldg128<kPolKeep>(addw(row, offk[k]), pol);
+        }
+        for (int c = slot; c < C; c += slots) {
+            uint4 raw[K];
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    sx += v[i];
-                    sxm = fmaf(v[i], mv[i], sxm);
-                    if (mv[i] > 0.5f && v[i] > best) { best = v[i]; bidx = p0 + u * VEC + i; }
+            for (int k = 0; k < K; ++k) raw[k] = nxt[k];
+            if (c + slots < C) {
+                const char* row = xbytes + (size_t)(c + slots) * rowB;
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (k < nk) nxt[k] = ldg128<kPolKeep>(addw(row, offk[k]), pol);
+            }
+            float sxm = 0.0f, sx = 0.0f, best = -INFINITY;
+            int bpos = -1;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (k < nk) {
+                    float v[VEC], mv[VEC];
+                    unpack<T, VEC>(raw[k], v);
+                    lds_f<VEC>(mloc + (ul + k * LPT) * VEC, mv);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        sx += v[i];
+                        sxm = fmaf(v[i], mv[i], sxm);
+                        if (mv[i] > 0.5f && v[i] > best) { best = v[i]; bpos = k * VEC + i; }  // scan order = pixel order within the thread
+                    }
                 }
             }
-        }
-        // larger value wins; on a tie the lower pixel index (first maximum in scan order)
-        for (int of = LPT >> 1; of > 0; of >>= 1) {
-            sx += __shfl_xor_sync(0xffffffffu, sx, of);
-            sxm += __shfl_xor_sync(0xffffffffu, sxm, of);
-            const float ob = __shfl_xor_sync(0xffffffffu, best, of);
-            const int oi = __shfl_xor_sync(0xffffffffu, bidx, of);
-            if ((oi >= 0) && (bidx < 0 || ob > best || (ob == best && oi < bidx))) { best = ob; bidx = oi; }
-        }
-        if (ul == 0 && cok) {
-            mypart[c] = sxm;
-            mypart[C + c] = sx;
-            mypart[2 * C + c] = best;
-            mypart[3 * C + c] = __int_as_float(bidx);
+            int bidx = -1;
+            if (bpos >= 0) { const int kk = bpos / VEC; bidx = p0 + (ul + kk * LPT) * VEC + (bpos - kk * VEC); }
+            float* st = stage + c * LPTp + ul;
+            st[0] = sxm;
+            st[C * LPTp] = sx;
+            st[2 * C * LPTp] = best;
+            st[3 * C * LPTp] = __int_as_float(bidx);
         }
     }
     __syncthreads();
+    // per channel: combine the LPT thread partials (fixed order; max ties -> lower pixel index), then push to every rank
     cluster.barrier_wait();  // #0
-    // push this CTA's partials into every CTA of the cluster: part[src rank][4][C]
     if (has_mask && tid < CS) cluster.map_shared_rank(msum_part, tid)[r] = mtot;
-    for (int i = tid; i < 4 * C * CS; i += kCT) {
-        const int rr = i / (4 * C), j = i - rr * 4 * C;
-        cluster.map_shared_rank(part, rr)[r * 4 * C + j] = mypart[j];
+    for (int c = tid; c < C; c += NT) {
+        const float* st = stage + c * LPTp;
+        float sxm = 0.0f, sx = 0.0f, best = -INFINITY;
+        int bidx = -1;
+        for (int j = 0; j < LPT; ++j) {
+            sxm += st[j];
+            sx += st[C * LPTp + j];
+            const float ob = st[2 * C * LPTp + j];
+            const int oi = __float_as_int(st[3 * C * LPTp + j]);
+            if ((oi >= 0) && (bidx < 0 || ob > best || (ob == best && oi < bidx))) { best = ob; bidx = oi; }
+        }
+        for (int rr = 0; rr < CS; ++rr) {
+            float* dst = cluster.map_shared_rank(part, rr) + r * 4 * C;
+            dst[c] = sxm;
+            dst[C + c] = sx;
+            dst[2 * C + c] = best;
+            dst[3 * C + c] = __int_as_float(bidx);
+        }
     }
     const float beta = __ldg(prm.beta);
     stamp(2);
@@ -340,6 +438,14 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
 
     // ---- phase 2: pooled descriptors, shared MLP, sigmoid (recomputed by every CTA)
     stamp(3);
+    // the staging area is dead: build the conv tile in it (zero padding; own rows of the m plane)
+    for (int i = tid; i < 3 * planeT; i += NT) tile[i] = 0.0f;
+    __syncthreads();
+    if (has_mask)
+        for (int i = tid; i < nP; i += NT) {
+            const int ry = i / W, cx = i - ry * W;
+            tile[2 * planeT + (3 + ry) * TWp + 4 + cx] = mloc[i];
+        }
     {
         float use = 0.0f, den = 1.0f;
         if (has_mask) {
@@ -350,7 +456,7 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
             if (r == 0 && tid == 0) { ctx.msum[b] = tot; ctx.use[b] = use; ctx.den[b] = den; }
         }
         const float invS = 1.0f / (float)S;
-        for (int c = tid; c < C; c += kCT) {
+        for (int c = tid; c < C; c += NT) {
             float sxm = 0.0f, sx = 0.0f, best = -INFINITY;
             int bidx = -1;
             for (int rr = 0; rr < CS; ++rr) {  // ranks own increasing pixel ranges: strict > keeps the first maximum
@@ -361,11 +467,11 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
                 const int oi = __float_as_int(pp[3 * C + c]);
                 if (oi >= 0 && (bidx < 0 || ob > best)) { best = ob; bidx = oi; }
             }
-            const float G = sx * invS;
-            const float A = has_mask ? sxm / den : G;
-            const float avg = has_mask ? (A * use + G * (1.0f - use)) : G;
+            const float Gm = sx * invS;
+            const float A = has_mask ? sxm / den : Gm;
+            const float avg = has_mask ? (A * use + Gm * (1.0f - use)) : Gm;
             const bool dead = bidx < 0;  // no pixel with m > 0.5 (masked_cbam.py:118-121)
-            const float mx = dead ? G : best;
+            const float mx = dead ? Gm : best;
             s_avg[c] = avg;
             s_mx[c] = mx;
             if (r == 0) {
@@ -378,7 +484,7 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
     const float k0 = sh.pyramid_multiply() ? 0.0f : 1.0f - alpha, k1 = alpha;
     if (b == 0 && r == 0 && tid == 0) { ctx.consts[0] = k0; ctx.consts[1] = k1; ctx.consts[2] = alpha; ctx.consts[3] = sigmoidf_acc(beta); }
     __syncthreads();
-    for (int j = w; j < Hd; j += kCW) {
+    for (int j = w; j < Hd; j += NW) {
         const float* wr = prm.w1 + (size_t)j * C;
         float pa = 0.0f, pm = 0.0f;
 #pragma unroll 4
@@ -400,7 +506,7 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
     __syncthreads();
     {
         const bool add = sh.samcam_add();
-        for (int c = tid; c < C; c += kCT) {
+        for (int c = tid; c < C; c += NT) {
             const float* wr = prm.w2 + (size_t)c * Hd;
             float za = 0.0f, zm = 0.0f;
 #pragma unroll 4
@@ -412,10 +518,10 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
             const float bb = __ldg(prm.b2 + c);
             const float s = sigmoidf_acc((za + bb) + (zm + bb));  // b2 enters twice (masked_cbam.py:128)
             if (r == 0) ctx.s[b * C + c] = s;
-            s_q[c] = add ? 1.0f : s;
-            // out = x * (sA * a + sB):  multiply: k0 + k1*s*a ;  add: k0 + k1*(s + a)
-            sA[c] = add ? k1 : k1 * s;
-            sB[c] = add ? fmaf(k1, s, k0) : k0;
+            const int gi = cl_gm(c, G, CG);
+            s_q[gi] = add ? 1.0f : s;
+            // out = x * (A * a + B):  multiply: k0 + k1*s*a ;  add: k0 + k1*(s + a)
+            sAB[gi] = add ? make_float2(k1, fmaf(k1, s, k0)) : make_float2(k1 * s, k0);
         }
     }
     __syncthreads();
@@ -423,38 +529,49 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
     // ---- phase 3 (T2): per pixel max / arg max / sum over channels of x*q
     stamp(4);
     const int g2 = tid / nUmax, ul2 = tid - g2 * nUmax;
-    const int G = gm.G;
     const bool act2 = g2 < G && ul2 < nU;
+    const int nj = act2 ? (C - g2 + G - 1) / G : 0;  // channels of this thread's group
     constexpr int KB = (VEC == 4) ? 8 : 4;
+    const unsigned gstep = (unsigned)G * rowB;       // bytes between two channels of a group
     {
         float vmax[VEC], vsum[VEC];
         int vidx[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) { vmax[i] = -INFINITY; vsum[i] = 0.0f; vidx[i] = 0x7fffffff; }
+        for (int i = 0; i < VEC; ++i) { vmax[i] = -INFINITY; vsum[i] = 0.0f; vidx[i] = -1; }
         if (act2) {
-            const T* xp = xb + (size_t)ul2 * VEC;
-            for (int c0 = g2; c0 < C; c0 += G * KB) {
+            const char* p = xbytes + (size_t)g2 * rowB + (size_t)ul2 * 16;
+            const float* qp = s_q + g2 * CG;
+            int j = 0;
+            for (; j + KB <= nj; j += KB) {
                 uint4 raw[KB];
 #pragma unroll
-                for (int kc = 0; kc < KB; ++kc) {
-                    const int c = c0 + kc * G;
-                    if (c < C) raw[kc] = ldg128<kPolKeep>(xp + (size_t)c * S, pol);
-                }
+                for (int kc = 0; kc < KB; ++kc) raw[kc] = ldg128<kPolKeep>(addw(p, kc * gstep), pol);
+                float qv[KB];
+                lds_f<KB>(qp + j, qv);
 #pragma unroll
                 for (int kc = 0; kc < KB; ++kc) {
-                    const int c = c0 + kc * G;
-                    if (c < C) {
-                        float v[VEC];
-                        unpack<T, VEC>(raw[kc], v);
-                        const float q = s_q[c];
+                    float v[VEC];
+                    unpack<T, VEC>(raw[kc], v);
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i) {
-                            const float y = v[i] * q;
-                            vsum[i] += y;
-                            if (y > vmax[i]) { vmax[i] = y; vidx[i] = c; }
-                        }
+                    for (int i = 0; i < VEC; ++i) {
+                        const float y = v[i] * qv[kc];
+                        vsum[i] += y;
+                        if (y > vmax[i]) { vmax[i] = y; vidx[i] = j + kc; }
                     }
                 }
+                p += (size_t)KB * gstep;
+            }
+            for (; j < nj; ++j) {
+                float v[VEC];
+                unpack<T, VEC>(ldg128<kPolKeep>(p, pol), v);
+                const float q = qp[j];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float y = v[i] * q;
+                    vsum[i] += y;
+                    if (y > vmax[i]) { vmax[i] = y; vidx[i] = j; }
+                }
+                p += gstep;
             }
         }
         if (g2 < G && ul2 < nUmax) {
@@ -463,14 +580,14 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
             for (int i = 0; i < VEC; ++i) {
                 d[i] = vmax[i];
                 d[(size_t)G * nPmax + i] = vsum[i];
-                d[(size_t)2 * G * nPmax + i] = __int_as_float(vidx[i]);
+                d[(size_t)2 * G * nPmax + i] = __int_as_float(vidx[i] < 0 ? 0x7fffffff : g2 + vidx[i] * G);  // channel index
             }
         }
     }
     __syncthreads();
     {
         const float invC = 1.0f / (float)C;
-        for (int p = tid; p < nP; p += kCT) {
+        for (int p = tid; p < nP; p += NT) {
             float bm = mg[p], bsum = mg[(size_t)G * nPmax + p];
             int bi = __float_as_int(mg[(size_t)2 * G * nPmax + p]);
             for (int j = 1; j < G; ++j) {
@@ -493,16 +610,16 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
 
     // ---- phase 4: halo rows through DSMEM, then a = sigmoid(conv7x7([pmax, pavg, m])) for the own rows
     stamp(6);
-    if (nP > 0) cl_fetch_halo(cluster, tile, has_mask ? 3 : 2, gm, y0, rows, H, W);
+    if (nP > 0) cl_fetch_halo<NT>(cluster, tile, has_mask ? 3 : 2, gm, y0, rows, H, W);
     cluster.barrier_arrive();  // #3 (waited at the end): this CTA reads no remote shared memory any more
     __syncthreads();
     {
         float* cpart = mg;  // [3][nPmax]
-        const int grp = tid / kConvGroup, gl = tid - grp * kConvGroup;
+        const int grp = tid / kGrp, gl = tid - grp * kGrp;
         const int spr = W / 4, nStrips = rows * spr;
         if (grp < 3) {
             const float* wv = wk + grp * kMaxK * kMaxK;
-            for (int s = gl; s < nStrips; s += kConvGroup) {
+            for (int s = gl; s < nStrips; s += kGrp) {
                 const int ry = s / spr, x0 = (s - ry * spr) * 4;
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 strip_conv7(tile + grp * planeT + ry * TWp + x0, TWp, wv, acc);
@@ -510,7 +627,7 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
             }
         }
         __syncthreads();
-        for (int p = tid; p < nP; p += kCT) {
+        for (int p = tid; p < nP; p += NT) {
             const float v = (cpart[p] + cpart[nPmax + p]) + cpart[2 * nPmax + p];
             const float a = sigmoidf_acc(v);
             aloc[p] = a;
@@ -519,32 +636,41 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
     }
     __syncthreads();
 
-    // ---- phase 5 (T2): out = x * (sA*a + sB)
+    // ---- phase 5 (T2): out = x * (A*a + B)
     stamp(7);
     if (act2) {
         float av[VEC];
         lds_f<VEC>(aloc + ul2 * VEC, av);
-        const T* xp = xb + (size_t)ul2 * VEC;
-        T* op = out + (size_t)b * C * S + p0 + (size_t)ul2 * VEC;
-        for (int c0 = g2; c0 < C; c0 += G * KB) {
+        const char* p = xbytes + (size_t)g2 * rowB + (size_t)ul2 * 16;
+        char* q = reinterpret_cast<char*>(out + (size_t)b * C * S + p0) + (size_t)g2 * rowB + (size_t)ul2 * 16;
+        const float2* ab = sAB + g2 * CG;
+        int j = 0;
+        for (; j + KB <= nj; j += KB) {
             uint4 raw[KB];
 #pragma unroll
-            for (int kc = 0; kc < KB; ++kc) {
-                const int c = c0 + kc * G;
-                if (c < C) raw[kc] = ldg128<kPolLast>(xp + (size_t)c * S, pol);
-            }
+            for (int kc = 0; kc < KB; ++kc) raw[kc] = ldg128<kPolLast>(addw(p, kc * gstep), pol);
+            float abv[2 * KB];
+            lds_f<2 * KB>(reinterpret_cast<const float*>(ab + j), abv);
 #pragma unroll
             for (int kc = 0; kc < KB; ++kc) {
-                const int c = c0 + kc * G;
-                if (c < C) {
-                    float v[VEC];
-                    unpack<T, VEC>(raw[kc], v);
-                    const float ga = sA[c], gb = sB[c];
+                float v[VEC];
+                unpack<T, VEC>(raw[kc], v);
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) v[i] *= fmaf(ga, av[i], gb);
-                    __stcs(reinterpret_cast<uint4*>(op + (size_t)c * S), pack<T, VEC>(v));
-                }
+                for (int i = 0; i < VEC; ++i) v[i] *= fmaf(abv[2 * kc], av[i], abv[2 * kc + 1]);
+                __stcs(reinterpret_cast<uint4*>(addw(q, kc * gstep)), pack<T, VEC>(v));
             }
+            p += (size_t)KB * gstep;
+            q += (size_t)KB * gstep;
+        }
+        for (; j < nj; ++j) {
+            float v[VEC];
+            unpack<T, VEC>(ldg128<kPolLast>(p, pol), v);
+            const float2 c2 = ab[j];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) v[i] *= fmaf(c2.x, av[i], c2.y);
+            __stcs(reinterpret_cast<uint4*>(q), pack<T, VEC>(v));
+            p += gstep;
+            q += gstep;
         }
     }
     stamp(8);
@@ -553,11 +679,13 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_fwd_kernel(const T* __res
 
 // ================================================================== backward
 template <typename T>
-__global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __restrict__ x, const T* __restrict__ g, const void* __restrict__ mask,
+__global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* __restrict__ x, const T* __restrict__ g, const void* __restrict__ mask,
                                                                   int mdt, T* __restrict__ dx, void* __restrict__ dmask, Shape sh,
                                                                   mga_cbam_params prm, Ctx ctx, BwdScratch bs, ClGeom gm) {
     constexpr int VEC = 16 / sizeof(T);
-    constexpr int K = ClK<VEC>::K;
+    constexpr int K = kClK;
+    constexpr int NT = kClNTB, NW = NT / 32;
+    constexpr int kGrp = NT / 3;  // conv: threads per input plane
     constexpr int kStride = 3 * kMaxK * kMaxK + 1;
     extern __shared__ __align__(128) float clsm[];
     float* const csm = clsm;
@@ -571,22 +699,24 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __res
     const int rows = max(0, min(gm.rowsPer, H - y0));
     const int nP = rows * W, nU = nP / VEC, p0 = y0 * W;
     const int nPmax = gm.nPmax, nUmax = gm.nUmax, TWp = gm.TWp, planeT = gm.planeT;
+    const int G = gm.G, CG = gm.CG;
     const bool has_mask = sh.has_mask();
     const bool multiply = !sh.samcam_add();
     const ClBwdOff o = cl_bwd_off(C, Hd, gm);
     float* wsm = csm + o.wsm;
     double* redd = reinterpret_cast<double*>(csm + o.red);
     float* s_s = csm + o.s;
-    float* s_q = csm + o.q;
     float4* chA = reinterpret_cast<float4*>(csm + o.chA);
-    float2* chB = reinterpret_cast<float2*>(csm + o.chB);
+    float* chG = csm + o.chG;
     int* amx = reinterpret_cast<int*>(csm + o.amx);
+    float* s_cM = csm + o.cM;
     float* s_dz = csm + o.dz;
     float* e_loc = csm + o.eloc;
     float* q_loc = csm + o.qloc;
     float* bin_loc = csm + o.binloc;
     float* s_dha = csm + o.dha;
     float* s_dhm = csm + o.dhm;
+    float* s_q = csm + o.q;
     float* epart = csm + o.epart;
     float* qpart = csm + o.qpart;
     float* binpart = csm + o.binpart;
@@ -604,41 +734,59 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __res
     float* tp = csm + o.tp;
     float* dwp = csm + o.dwp;
     float* binw = csm + o.binw;
+    float* stage = csm + o.stage;
     const ClPol pol = cl_policies();
-    const size_t bS = (size_t)b * S;
     const float k0 = ctx.consts[0], k1 = ctx.consts[1];
+    const unsigned rowB = (unsigned)S * (unsigned)sizeof(T);
 
+    const size_t bS = (size_t)b * S;
     // ---- phase 0: per-sample vectors and planes of the saved context
     stamp(0);
-    load_weights7(prm.wsam, sh.k, true, wsm);
-    for (int i = tid; i < planeT; i += kCT) dpre[i] = 0.0f;
-    for (int i = tid; i < kCW * C; i += kCT) binw[i] = 0.0f;
-    for (int c = tid; c < C; c += kCT) {
+    if (gm.prefetch) {
+        cl_prefetch_share(x + (size_t)b * C * S, (size_t)C * rowB, r, CS);
+        cl_prefetch_share(g + (size_t)b * C * S, (size_t)C * rowB, r, CS);
+    }
+    cl_load_weights7<NT>(prm.wsam, sh.k, true, wsm);
+    for (int i = tid; i < planeT; i += NT) dpre[i] = 0.0f;
+    for (int i = tid; i < NW * C; i += NT) binw[i] = 0.0f;
+    for (int c = tid; c < C; c += NT) {
         const float s = ctx.s[b * C + c];
         s_s[c] = s;
         s_q[c] = multiply ? s : 1.0f;
     }
-    for (int p = tid; p < nP; p += kCT) {
-        const float a = ctx.a[bS + p0 + p];
-        aloc[p] = a;
-        ae[p] = multiply ? a : 1.0f;
-        mloc[p] = has_mask ? ctx.m[bS + p0 + p] : 0.0f;
-        idxl[p] = ctx.idx[bS + p0 + p];
-        pmx[p] = ctx.pmax[bS + p0 + p];
+    for (int p = tid; p < gm.LPT * K * VEC; p += NT) {
+        const bool in = p < nP;
+        const float a = in ? ctx.a[bS + p0 + p] : 0.0f;
+        ae[p] = in ? (multiply ? a : 1.0f) : 0.0f;
+        d1s[p] = 0.0f;
+        if (in) {
+            aloc[p] = a;
+            mloc[p] = has_mask ? ctx.m[bS + p0 + p] : 0.0f;
+            idxl[p] = ctx.idx[bS + p0 + p];
+            pmx[p] = ctx.pmax[bS + p0 + p];
+        }
     }
     {
         const float* const planes[3] = {ctx.pmax + bS, ctx.pavg + bS, has_mask ? ctx.m + bS : nullptr};
-        stage_three(cat, planeT, planes, y0 - kMaxK / 2, gm.tileRows, H, W, TWp);
+        cl_stage_three<NT>(cat, planeT, planes, y0 - kMaxK / 2, gm.tileRows, H, W, TWp);
     }
     __syncthreads();
 
     // ---- phase 1 (T1) over (x,g): T_p = sum_c g x q_c (per pixel), E_c = sum_p g x (a | 1) (per channel), sum g x
     stamp(1);
-    const int lsh = gm.lsh, LPT = 1 << lsh, CPW = 32 >> lsh;
-    const int sub = lane >> lsh, ul = lane & (LPT - 1);
+    const int LPT = gm.LPT, LPTp = LPT | 1, slots = gm.slots;
+    const int slot = tid / LPT, ul = tid - slot * LPT;
     const size_t sbase = (size_t)b * C * S + p0;
-    const T* xb = x + sbase;
-    const T* gb = g + sbase;
+    const char* xbytes = reinterpret_cast<const char*>(x + sbase);
+    const char* gbytes = reinterpret_cast<const char*>(g + sbase);
+    unsigned offk[K];
+    int nk = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int u = ul + k * LPT;
+        offk[k] = (unsigned)u * 16u;
+        nk += (slot < slots && u < nU) ? 1 : 0;
+    }
     float gxs = 0.0f;
     {
         float tacc[K][VEC];
@@ -646,58 +794,54 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __res
         for (int k = 0; k < K; ++k)
 #pragma unroll
             for (int i = 0; i < VEC; ++i) tacc[k][i] = 0.0f;
-        for (int cb = w * CPW; cb < C; cb += kCW * CPW) {
-            const int c = cb + sub;
-            const bool cok = c < C;
-            uint4 xr[K], gr[K];
+        if (slot < slots) {
+            for (int c = slot; c < C; c += slots) {
+                const char* xrow = xbytes + (size_t)c * rowB;
+                const char* grow = gbytes + (size_t)c * rowB;
+                uint4 xr[K], gr[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int u = ul + (k << lsh);
-                if (cok && u < nU) {
-                    xr[k] = ldg128<kPolKeep>(xb + (size_t)c * S + (size_t)u * VEC, pol);
-                    gr[k] = ldg128<kPolKeep>(gb + (size_t)c * S + (size_t)u * VEC, pol);
-                }
-            }
-            const float q = cok ? s_q[c] : 0.0f;
-            float e = 0.0f;
+                for (int k = 0; k < K; ++k)
+                    if (k < nk) {
+                        xr[k] = ldg128<kPolKeep>(addw(xrow, offk[k]), pol);
+                        gr[k] = ldg128<kPolKeep>(addw(grow, offk[k]), pol);
+                    }
+                const float q = s_q[c];
+                float e = 0.0f;
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int u = ul + (k << lsh);
-                if (cok && u < nU) {
-                    float xv[VEC], gv[VEC], av[VEC];
-                    unpack<T, VEC>(xr[k], xv);
-                    unpack<T, VEC>(gr[k], gv);
-                    lds_f<VEC>(ae + u * VEC, av);
+                for (int k = 0; k < K; ++k) {
+                    if (k < nk) {
+                        float xv[VEC], gv[VEC], av[VEC];
+                        unpack<T, VEC>(xr[k], xv);
+                        unpack<T, VEC>(gr[k], gv);
+                        lds_f<VEC>(ae + (ul + k * LPT) * VEC, av);
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        const float gx = gv[i] * xv[i];
-                        tacc[k][i] = fmaf(gx, q, tacc[k][i]);
-                        e = fmaf(gx, av[i], e);
-                        gxs += gx;
+                        for (int i = 0; i < VEC; ++i) {
+                            const float gx = gv[i] * xv[i];
+                            tacc[k][i] = fmaf(gx, q, tacc[k][i]);
+                            e = fmaf(gx, av[i], e);
+                            gxs += gx;
+                        }
                     }
                 }
+                stage[c * LPTp + ul] = e;
             }
-            for (int of = LPT >> 1; of > 0; of >>= 1) e += __shfl_xor_sync(0xffffffffu, e, of);
-            if (ul == 0 && cok) e_loc[c] = e;
-        }
-        // merge the channel sub-groups of the warp, then the 8 warps through shared memory
+            // per-pixel partials of this channel slot
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int u = ul + (k << lsh);
+            for (int k = 0; k < K; ++k) {
+                if (k < nk) {
+                    float* d = tp + (size_t)slot * nPmax + (ul + k * LPT) * VEC;
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                float t = tacc[k][i];
-                for (int of = LPT; of < 32; of <<= 1) t += __shfl_xor_sync(0xffffffffu, t, of);
-                if (sub == 0 && u < nU) tp[(size_t)w * nPmax + u * VEC + i] = t;
+                    for (int i = 0; i < VEC; ++i) d[i] = tacc[k][i];
+                }
             }
         }
     }
     __syncthreads();
+    cl_stage_sum<NT>(stage, e_loc, C, LPT);
     double at_acc = 0.0;
-    for (int p = tid; p < nP; p += kCT) {
+    for (int p = tid; p < nP; p += NT) {
         float t = 0.0f;
-#pragma unroll
-        for (int j = 0; j < kCW; ++j) t += tp[(size_t)j * nPmax + p];
+        for (int j = 0; j < slots; ++j) t += tp[(size_t)j * nPmax + p];
         const float a = aloc[p];
         const int ry = p / W, cx = p - ry * W;
         dpre[(3 + ry) * TWp + 4 + cx] = k1 * t * a * (1.0f - a);
@@ -708,17 +852,17 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __res
 
     // ---- phase 2: dpre halo through DSMEM; dcat = conv7x7^T(dpre); dWsam partials
     stamp(3);
-    if (nP > 0) cl_fetch_halo(cluster, dpre, 1, gm, y0, rows, H, W);
+    if (nP > 0) cl_fetch_halo<NT>(cluster, dpre, 1, gm, y0, rows, H, W);
     __syncthreads();
     {
-        const int grp = tid / kConvGroup, gl = tid - grp * kConvGroup;
+        const int grp = tid / kGrp, gl = tid - grp * kGrp;
         const int spr = W / 4, nStrips = rows * spr;
         const float invC = 1.0f / (float)C;
         if (grp < 3) {
             const float* wv = wsm + grp * kMaxK * kMaxK;
             float* dst = grp == 0 ? d0 : (grp == 1 ? d1s : d2);
             const float sc = grp == 1 ? invC : 1.0f;
-            for (int s = gl; s < nStrips; s += kConvGroup) {
+            for (int s = gl; s < nStrips; s += kGrp) {
                 const int ry = s / spr, x0 = (s - ry * spr) * 4;
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 strip_conv7(dpre + ry * TWp + x0, TWp, wv, acc);
@@ -761,7 +905,7 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __res
                 bs.convpart[(size_t)cta * kStride + (pl * k + ii) * k + jj] = t;
             }
         }
-        const double at = cl_block_sum_d(at_acc, redd);
+        const double at = block_sum_d(at_acc, redd);
         if (tid == 0) bs.atpart[cta] = at;
     }
     __syncthreads();
@@ -770,32 +914,29 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __res
     //      sum_{p: idx_p = c} dcat0_p x_cp s_c = sum_{p: idx_p = c} dcat0_p pmax_p   (binned per channel, deterministic)
     stamp(4);
     if (multiply) {
-        for (int cb = w * CPW; cb < C; cb += kCW * CPW) {
-            const int c = cb + sub;
-            const bool cok = c < C;
-            uint4 xr[K];
+        if (slot < slots) {
+            for (int c = slot; c < C; c += slots) {
+                const char* xrow = xbytes + (size_t)c * rowB;
+                uint4 xr[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int u = ul + (k << lsh);
-                if (cok && u < nU) xr[k] = ldg128<kPolKeep>(xb + (size_t)c * S + (size_t)u * VEC, pol);
-            }
-            float qv = 0.0f;
+                for (int k = 0; k < K; ++k)
+                    if (k < nk) xr[k] = ldg128<kPolKeep>(addw(xrow, offk[k]), pol);
+                float qv = 0.0f;
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int u = ul + (k << lsh);
-                if (cok && u < nU) {
-                    float xv[VEC], wv[VEC];
-                    unpack<T, VEC>(xr[k], xv);
-                    lds_f<VEC>(d1s + u * VEC, wv);
+                for (int k = 0; k < K; ++k) {
+                    if (k < nk) {
+                        float xv[VEC], wv[VEC];
+                        unpack<T, VEC>(xr[k], xv);
+                        lds_f<VEC>(d1s + (ul + k * LPT) * VEC, wv);
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) qv = fmaf(xv[i], wv[i], qv);
+                        for (int i = 0; i < VEC; ++i) qv = fmaf(xv[i], wv[i], qv);
+                    }
                 }
+                stage[c * LPTp + ul] = qv;
             }
-            for (int of = LPT >> 1; of > 0; of >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, of);
-            if (ul == 0 && cok) q_loc[c] = qv;
         }
         // warp-private bins: lanes with the same arg-max channel are summed in lane order by their lowest lane
-        for (int base = w * 32; base < nP; base += kCT) {
+        for (int base = w * 32; base < nP; base += NT) {
             const int p = base + lane;
             const bool ok = p < nP;
             const int key = ok ? idxl[p] : -1 - lane;
@@ -810,20 +951,22 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __res
             if (ok && lane == __ffs(peers) - 1 && key >= 0 && key < C) binw[w * C + key] += acc;
             __syncwarp();
         }
+        __syncthreads();
+        cl_stage_sum<NT>(stage, q_loc, C, LPT);
     }
     __syncthreads();
-    for (int c = tid; c < C; c += kCT) {
+    for (int c = tid; c < C; c += NT) {
         float t = 0.0f;
         if (multiply) {
 #pragma unroll
-            for (int j = 0; j < kCW; ++j) t += binw[j * C + c];
+            for (int j = 0; j < NW; ++j) t += binw[j * C + c];
         } else {
             q_loc[c] = 0.0f;
         }
         bin_loc[c] = t;
     }
-    const double gx_cta = cl_block_sum_d((double)gxs, redd);  // (barriers inside)
-    for (int i = tid; i < C * CS; i += kCT) {
+    const double gx_cta = block_sum_d((double)gxs, redd);  // (barriers inside)
+    for (int i = tid; i < C * CS; i += NT) {
         const int rr = i / C, c = i - rr * C;
         cluster.map_shared_rank(epart, rr)[r * C + c] = e_loc[c];
         cluster.map_shared_rank(qpart, rr)[r * C + c] = q_loc[c];
@@ -840,7 +983,7 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __res
         double gx_tot = 0.0;
         for (int rr = 0; rr < CS; ++rr) gx_tot += gxpart[rr];
         double se_acc = 0.0;
-        for (int c = tid; c < C; c += kCT) {
+        for (int c = tid; c < C; c += NT) {
             float es = 0.0f, qs = 0.0f, bn = 0.0f;
             for (int rr = 0; rr < CS; ++rr) { es += epart[rr * C + c]; qs += qpart[rr * C + c]; bn += binpart[rr * C + c]; }
             const float s = s_s[c];
@@ -849,10 +992,10 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __res
             if (r == 0) bs.dz[b * C + c] = dz;
             if (!multiply) se_acc += (double)s * (double)es;  // add mode: sum_c s_c sum_p g x
         }
-        const double ssum = cl_block_sum_d(se_acc, redd);
+        const double ssum = block_sum_d(se_acc, redd);
         if (r == 0 && tid == 0) bs.alphapart[b] = ssum - (sh.pyramid_multiply() ? 0.0 : gx_tot);
         __syncthreads();
-        for (int j = w; j < Hd; j += kCW) {
+        for (int j = w; j < Hd; j += NW) {
             float acc = 0.0f;
 #pragma unroll 4
             for (int c = lane; c < C; c += 32) acc = fmaf(s_dz[c], __ldg(prm.w2 + (size_t)c * Hd + j), acc);
@@ -871,7 +1014,7 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __res
         const float pass = (has_mask && ctx.msum[b] >= sh.eps) ? 1.0f : 0.0f;  // clamp_min backward
         const float invS = 1.0f / (float)S;
         float kacc = 0.0f;
-        for (int c = tid; c < C; c += kCT) {
+        for (int c = tid; c < C; c += NT) {
             float davg = 0.0f, dmx = 0.0f;
 #pragma unroll 4
             for (int j = 0; j < Hd; ++j) {
@@ -886,10 +1029,12 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __res
             const float cG = ((1.0f - use) * davg + (dead ? dmx : 0.0f)) * invS;
             const float cM = dead ? 0.0f : dmx;
             const float s = s_s[c];
+            const int gi = cl_gm(c, G, CG);
             // dL/dout * gate: multiply: k0 + k1*s*a ; add: k0 + k1*(s + a)
-            chA[c] = make_float4(multiply ? k1 * s : k1, multiply ? k0 : fmaf(k1, s, k0), multiply ? s : 1.0f, cA);
-            chB[c] = make_float2(cG, cM);
+            chA[gi] = make_float4(multiply ? k1 * s : k1, multiply ? k0 : fmaf(k1, s, k0), multiply ? s : 1.0f, cA);
+            chG[gi] = cG;
             amx[c] = am;
+            s_cM[c] = cM;
             kacc = fmaf(cA, ctx.apool[i] * pass, kacc);
         }
         kb = block_sum(kacc, reinterpret_cast<float*>(redd));
@@ -899,7 +1044,6 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __res
     // ---- phase 5 (T2) over (x,g): dx (streaming store) and R_p = sum_c cA_c x -> dmask
     stamp(7);
     const int g2 = tid / nUmax, ul2 = tid - g2 * nUmax;
-    const int G = gm.G;
     const bool act2 = g2 < G && ul2 < nU;
     const bool want_dmask = has_mask && dmask != nullptr;
     {
@@ -915,50 +1059,71 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __res
             lds_f<VEC>(mloc + ul2 * VEC, mv);
             lds_i<VEC>(idxl + ul2 * VEC, ix);
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) wdv[i] += wv[i];
-            const int pbase = p0 + ul2 * VEC;
-            constexpr int KB = (VEC == 4) ? 4 : 2;
-            const T* xp = xb + (size_t)ul2 * VEC;
-            const T* gp = gb + (size_t)ul2 * VEC;
-            T* op = dx + sbase + (size_t)ul2 * VEC;
-            for (int c0 = g2; c0 < C; c0 += G * KB) {
+            for (int i = 0; i < VEC; ++i) {
+                wdv[i] += wv[i];
+                // channel -> position in this thread's walk (g2, g2+G, ...); other groups never match
+                const int d = ix[i] - g2;
+                ix[i] = (d >= 0 && d % G == 0) ? d / G : -1;
+            }
+            constexpr int KB = 4;
+            const int nj = (C - g2 + G - 1) / G;
+            const unsigned gstep = (unsigned)G * rowB;
+            const size_t toff = (size_t)g2 * rowB + (size_t)ul2 * 16;
+            const char* xp = xbytes + toff;
+            const char* gp = gbytes + toff;
+            char* op = reinterpret_cast<char*>(dx + sbase) + toff;
+            const float4* ca = chA + g2 * CG;
+            const float* cg = chG + g2 * CG;
+            int j = 0;
+            for (; j + KB <= nj; j += KB) {
                 uint4 xr[KB], gr[KB];
 #pragma unroll
                 for (int kc = 0; kc < KB; ++kc) {
-                    const int c = c0 + kc * G;
-                    if (c < C) {
-                        xr[kc] = ldg128<kPolLast>(xp + (size_t)c * S, pol);
-                        gr[kc] = ldg128<kPolLast>(gp + (size_t)c * S, pol);
-                    }
+                    xr[kc] = ldg128<kPolLast>(addw(xp, kc * gstep), pol);
+                    gr[kc] = ldg128<kPolLast>(addw(gp, kc * gstep), pol);
                 }
+                float cgv[KB];
+                lds_f<KB>(cg + j, cgv);
 #pragma unroll
                 for (int kc = 0; kc < KB; ++kc) {
-                    const int c = c0 + kc * G;
-                    if (c < C) {
-                        float xv[VEC], gv[VEC], ov[VEC];
-                        unpack<T, VEC>(xr[kc], xv);
-                        unpack<T, VEC>(gr[kc], gv);
-                        const float4 ca = chA[c];
-                        const float2 cb2 = chB[c];
-                        const int am = amx[c];
+                    float xv[VEC], gv[VEC], ov[VEC];
+                    unpack<T, VEC>(xr[kc], xv);
+                    unpack<T, VEC>(gr[kc], gv);
+                    const float4 c4 = ca[j + kc];
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i) {
-                            const float gate = fmaf(ca.x, av[i], ca.y);
-                            const float sel = (ix[i] == c) ? wdv[i] : wv[i];
-                            float v = fmaf(ca.w, mv[i], cb2.x);
-                            v = fmaf(ca.z, sel, v);
-                            ov[i] = fmaf(gv[i], gate, v);
-                            racc[i] = fmaf(ca.w, xv[i], racc[i]);
-                        }
-                        const int dlt = am - pbase;
-                        if ((unsigned)dlt < (unsigned)VEC) {
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i)
-                                if (i == dlt) ov[i] += cb2.y;
-                        }
-                        __stcs(reinterpret_cast<uint4*>(op + (size_t)c * S), pack<T, VEC>(ov));
+                    for (int i = 0; i < VEC; ++i) {
+                        const float gate = fmaf(c4.x, av[i], c4.y);
+                        const float sel = (ix[i] == j + kc) ? wdv[i] : wv[i];
+                        float v = fmaf(c4.w, mv[i], cgv[kc]);
+                        v = fmaf(c4.z, sel, v);
+                        ov[i] = fmaf(gv[i], gate, v);
+                        racc[i] = fmaf(c4.w, xv[i], racc[i]);
                     }
+                    __stcs(reinterpret_cast<uint4*>(addw(op, kc * gstep)), pack<T, VEC>(ov));
                 }
+                xp += (size_t)KB * gstep;
+                gp += (size_t)KB * gstep;
+                op += (size_t)KB * gstep;
+            }
+            for (; j < nj; ++j) {
+                float xv[VEC], gv[VEC], ov[VEC];
+                unpack<T, VEC>(ldg128<kPolLast>(xp, pol), xv);
+                unpack<T, VEC>(ldg128<kPolLast>(gp, pol), gv);
+                const float4 c4 = ca[j];
+                const float cgq = cg[j];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float gate = fmaf(c4.x, av[i], c4.y);
+                    const float sel = (ix[i] == j) ? wdv[i] : wv[i];
+                    float v = fmaf(c4.w, mv[i], cgq);
+                    v = fmaf(c4.z, sel, v);
+                    ov[i] = fmaf(gv[i], gate, v);
+                    racc[i] = fmaf(c4.w, xv[i], racc[i]);
+                }
+                __stcs(reinterpret_cast<uint4*>(op), pack<T, VEC>(ov));
+                xp += gstep;
+                gp += gstep;
+                op += gstep;
             }
         }
         if (want_dmask && g2 < G && ul2 < nUmax) {
@@ -966,9 +1131,17 @@ __global__ void __launch_bounds__(kCT, MGA_CL_MINB) cl_bwd_kernel(const T* __res
             for (int i = 0; i < VEC; ++i) tp[(size_t)g2 * nPmax + ul2 * VEC + i] = racc[i];
         }
     }
+    __syncthreads();  // dx of this CTA's pixel range is written (visible to the block): arg-max pixel fix-up below
+    for (int c = tid; c < C; c += NT) {
+        const int am = amx[c];
+        const float cM = s_cM[c];
+        if (am >= p0 && am < p0 + nP && cM != 0.0f) {  // dx[c][argmax pixel] += dMx_c (masked_cbam.py:116-117 backward)
+            T* e = dx + ((size_t)b * C + c) * S + am;
+            *e = from_f<T>(to_f<T>(__ldcg(e)) + cM);
+        }
+    }
     if (want_dmask) {
-        __syncthreads();
-        for (int p = tid; p < nP; p += kCT) {
+        for (int p = tid; p < nP; p += NT) {
             float rsum = 0.0f;
             for (int j = 0; j < G; ++j) rsum += tp[(size_t)j * nPmax + p];
             float dm = (rsum - kb) + d2[p];

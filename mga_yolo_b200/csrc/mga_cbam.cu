@@ -326,12 +326,14 @@ static int env_int(const char* name, int dflt) {
 // Chosen from the per-sample shape only (never from B).  false -> the one-kernel-per-phase path is used.
 static bool cl_geometry(const Shape& sh, int esize, bool bwd, ClGeom* out) {
     static const int enabled = env_int("MGA_CL", 1);
-    static const int kb_f = env_int("MGA_CL_KB_F", 224), kb_b = env_int("MGA_CL_KB_B", 224);
+    static const int kb_f = env_int("MGA_CL_KB_F", 224), kb_b = env_int("MGA_CL_KB_B", 448);
     static const int cs_f = env_int("MGA_CL_CS_F", 0), cs_b = env_int("MGA_CL_CS_B", 0);  // tuning overrides
+    static const int pf_f = env_int("MGA_CL_PREFETCH_F", 0), pf_b = env_int("MGA_CL_PREFETCH_B", 0);
     if (!enabled || sh.gates_only()) return false;
+    static const int max_kb_f = env_int("MGA_CL_MAXKB_F", 1 << 30), max_kb_b = env_int("MGA_CL_MAXKB_B", 1 << 30);  // tuning: larger samples -> split path
+    if ((double)sh.C * sh.S * esize > 1024.0 * (bwd ? max_kb_b : max_kb_f)) return false;
     const int vec = 16 / esize;
     if (sh.S % vec || sh.W % 4 || sh.C < 1) return false;
-    const int K = vec == 4 ? 7 : 4;
     int rowq = 1;
     while ((rowq * sh.W) % vec) ++rowq;
     const double bytes = (double)sh.C * sh.S * esize * (bwd ? 2.0 : 1.0);
@@ -344,19 +346,23 @@ static bool cl_geometry(const Shape& sh, int esize, bool bwd, ClGeom* out) {
         rowsPer = (rowsPer + rowq - 1) / rowq * rowq;
         if (CS > 1 && (CS - 1) * rowsPer >= sh.H) break;  // trailing ranks would own nothing
         const int nP = rowsPer * sh.W, nU = nP / vec;
-        if (nU > 32 * K || nU > kCT) continue;
+        const int NT = bwd ? kClNTB : kClNTF;
+        if (nU > NT) continue;
         ClGeom g{};
+        g.NT = NT;
         g.CS = CS;
         g.rowsPer = rowsPer;
         g.nUmax = nU;
         g.nPmax = nP;
-        g.G = std::max(1, std::min(kCT / nU, sh.C));
-        g.lsh = 0;
-        while ((K << g.lsh) < nU) ++g.lsh;
+        g.G = std::max(1, std::min(NT / nU, sh.C));
+        g.CG = (((sh.C + g.G - 1) / g.G) + 7) & ~7;
+        g.LPT = (nU + kClK - 1) / kClK;
+        g.slots = NT / g.LPT;
         g.tileRows = rowsPer + kMaxK - 1;
         g.TWp = sh.W + 8;
         g.planeT = (g.tileRows * g.TWp + 31) & ~31;
         g.smem_bytes = 4 * (bwd ? cl_bwd_off(sh.C, sh.hidden, g).total : cl_fwd_off(sh.C, sh.hidden, g).total);
+        g.prefetch = bwd ? pf_b : pf_f;
         if (g.smem_bytes > kSmemLimit) continue;
         best = g;
         have = true;
@@ -364,6 +370,10 @@ static bool cl_geometry(const Shape& sh, int esize, bool bwd, ClGeom* out) {
     }
     if (!have) return false;
     if (!forced && bytes / best.CS > 2.0 * target) return false;  // sample too large to stay L2-resident: split path
+    static const int debug = env_int("MGA_CL_DEBUG", 0);
+    if (debug)
+        fprintf(stderr, "[mga] cluster %s C=%d %dx%d e=%d: CS=%d rows=%d nU=%d G=%d CG=%d LPT=%d slots=%d smem=%d B\n", bwd ? "bwd" : "fwd", sh.C, sh.H,
+                sh.W, esize, best.CS, best.rowsPer, best.nUmax, best.G, best.CG, best.LPT, best.slots, best.smem_bytes);
     *out = best;
     return true;
 }
@@ -382,7 +392,7 @@ static int launch_cl(const char* name, Kern kernel, const ClGeom& gm, int nClust
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(nClusters * gm.CS));
-    cfg.blockDim = dim3(kCT);
+    cfg.blockDim = dim3((unsigned)gm.NT);
     cfg.dynamicSmemBytes = (size_t)gm.smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -395,7 +405,7 @@ static int launch_cl(const char* name, Kern kernel, const ClGeom& gm, int nClust
     cudaError_t e;
     {
         LaunchScope ls(name, st);
-        e = cudaLaunchKernelEx(&cfg, kernel, args...);
+        e = cudaLaunchKernelEx(&cfg, kernel, args..., gm);  // the geometry is always the last kernel argument
     }
     if (e != cudaSuccess) return fail(MGA_ERR_CUDA, "%s: launch (cluster %d, %d B smem): %s", name, gm.CS, gm.smem_bytes, cudaGetErrorString(e));
     return MGA_OK;
@@ -532,7 +542,7 @@ static int forward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, con
         return forward_flow<T>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, flow_ctl, st);
     ClGeom cgm;
     if (vec > 1 && !(d->flags & MGA_FORCE_SPLIT) && cl_geometry(sh, (int)sizeof(T), false, &cgm))
-        return launch_cl("cl_fwd", cl_fwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), mask, d->mask_dtype, static_cast<T*>(out), sh, p, ctx, cgm);
+        return launch_cl("cl_fwd", cl_fwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), mask, d->mask_dtype, static_cast<T*>(out), sh, p, ctx);
     if (vec == 1) return forward_split<T, 1>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
     return forward_split<T, VecOf<T>::V>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
 }
@@ -593,7 +603,7 @@ static int backward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, co
     ClGeom cgm;
     if (vec > 1 && !(d->flags & MGA_FORCE_SPLIT) && cl_geometry(sh, (int)sizeof(T), true, &cgm)) {
         if (int rc = launch_cl("cl_bwd", cl_bwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), static_cast<const T*>(g), mask, d->mask_dtype,
-                               static_cast<T*>(dx), dmask, sh, p, ctx, bs, cgm))
+                               static_cast<T*>(dx), dmask, sh, p, ctx, bs))
             return rc;
         const int nw = 2 * sh.C * sh.hidden + sh.C + sh.hidden;
         const int nMlpBlocks = (nw + kWarpsPerBlock - 1) / kWarpsPerBlock;

@@ -1,0 +1,23 @@
+#!/bin/bash
+# bench the step under several library builds / env settings: "name|LIB|ENV..." lines on stdin or args
+run() {
+  name=$1; lib=$2; shift 2
+  out=$(env MGA_LIBNAME=$lib "$@" timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu --no-variant --no-e2e $BENCH_ARGS 2>gpurun_out/var_$name.err)
+  echo "$out" > gpurun_out/var_$name.json
+  python - "$name" <<P
+import json,sys
+try:
+    d=json.load(open("gpurun_out/var_"+sys.argv[1]+".json"))
+    print(f"{sys.argv[1]:28s} ms {d['ms_per_step']:.4f}  GB/s {d['value']:.0f}  frac {d['value']/6453.4:.3f} ", [(k['kernel'][:6],k['level'],round(k['ms']*1e3)) for k in d['kernels'] if k['kernel']!='bwd_wgrad'])
+except Exception as e:
+    print(sys.argv[1], "FAILED", e)
+P
+}
+L=libmga_cbam.so
+for kf in 224 448; do for kb in 448 896; do
+run f${kf}_b${kb} $L MGA_CL_KB_F=$kf MGA_CL_KB_B=$kb
+BENCH_ARGS=--one-stream run f${kf}_b${kb}_one $L MGA_CL_KB_F=$kf MGA_CL_KB_B=$kb
+done; done
+run f112_b448 $L MGA_CL_KB_F=112 MGA_CL_KB_B=448
+run f224_b448_pf $L MGA_CL_PREFETCH_F=1 MGA_CL_PREFETCH_B=1
+MGA_CL_DEBUG=1 MGA_CL_KB_F=448 MGA_CL_KB_B=896 python tools/run_level.py cfg2 0 both 1 2>&1 | grep mga | sort -u
