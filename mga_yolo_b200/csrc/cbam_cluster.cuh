@@ -246,6 +246,34 @@ __device__ __forceinline__ void cl_prefetch_share(const void* sample, size_t sam
     }
 }
 
+template <int NT>
+__device__ __forceinline__ void cl_load_weights7(const float* __restrict__ wsam, int k, bool flip, float* w /* [3][49] */) {
+    const int off = (kMaxK - k) / 2;
+    for (int t = threadIdx.x; t < 3 * kMaxK * kMaxK; t += NT) {
+        const int pl = t / (kMaxK * kMaxK);
+        int ii = (t / kMaxK) % kMaxK, jj = t % kMaxK;
+        if (flip) { ii = kMaxK - 1 - ii; jj = kMaxK - 1 - jj; }
+        ii -= off; jj -= off;
+        w[t] = (ii >= 0 && ii < k && jj >= 0 && jj < k) ? __ldg(wsam + (pl * k + ii) * k + jj) : 0.0f;
+    }
+}
+// the three planes [pmax, pavg, m] of rows [y_lo, y_lo + rows): float4 chunks, zero outside the image / in the pad columns
+template <int NT>
+__device__ __forceinline__ void cl_stage_three(float* tile, int planeT, const float* const (&planes)[3], int y_lo, int rows, int H, int W, int TWp) {
+    const int cpr = TWp / 4, total = rows * cpr;
+    for (int i = threadIdx.x; i < total; i += NT) {
+        const int r = i / cpr, c = i - r * cpr, yy = y_lo + r;
+        const bool in = yy >= 0 && yy < H && c >= 1 && c < cpr - 1;
+        const int o = yy * W + (c - 1) * 4;
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in && planes[pl] != nullptr) v = __ldcg(reinterpret_cast<const float4*>(planes[pl] + o));
+            reinterpret_cast<float4*>(tile + pl * planeT)[i] = v;
+        }
+    }
+}
+
 // position of channel c in the group-major constant arrays: thread group g walks g, g+G, g+2G ... -> consecutive floats
 __device__ __forceinline__ int cl_gm(int c, int G, int CG) { const int j = c / G; return (c - j * G) * CG + j; }
 
