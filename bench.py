@@ -74,6 +74,8 @@ KERNEL_BYTES = {
     "flow_fwd": lambda N, BS, e: 2 * N * e + BS * 4,      # the whole forward: read x, mask; write out
     "flow_bwd": lambda N, BS, e: 3 * N * e + 2 * BS * 4,  # the whole backward: read x, g, mask; write dx, dmask
     "fused_bwd": lambda N, BS, e: 3 * N * e + 3 * BS * 4,
+    "cl_fwd": lambda N, BS, e: 2 * N * e + BS * 4,        # cluster-per-sample forward: read x, mask; write out
+    "cl_bwd": lambda N, BS, e: 3 * N * e + 2 * BS * 4,    # cluster-per-sample backward: read x, g, mask; write dx, dmask
 }
 
 
@@ -282,17 +284,17 @@ def gpu_arm(args, rank, world, local_rank):
     dtype = DT[dtname]
     esize = torch.empty((), dtype=dtype).element_size()
 
-    def flags_of(scf):
+    def flags_of(scf, split=False):
         f = _lib.SAMCAM_ADD if scf == "add" else 0
-        return f | (_lib.FORCE_SPLIT if args.force_split else 0) | (_lib.USE_FUSED if args.use_fused else 0) | (_lib.USE_FLOW if args.use_flow else 0)
+        return f | (_lib.FORCE_SPLIT if (args.force_split or split) else 0) | (_lib.USE_FUSED if args.use_fused else 0) | (_lib.USE_FLOW if args.use_flow else 0)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     alg_bytes = algorithmic_bytes(levels, B, esize)
     results = {}
 
-    def measure(scf, steps, warmup):
-        sets = build_plans(levels, B, dtype, flags_of(scf), dev, nsets=2)
+    def measure(scf, steps, warmup, split=False):
+        sets = build_plans(levels, B, dtype, flags_of(scf, split), dev, nsets=2)
         stream = torch.cuda.current_stream(dev)
         sptr = stream.cuda_stream
         sides = [torch.cuda.Stream(dev) for _ in levels[1:]] if not args.one_stream else []
@@ -398,6 +400,9 @@ def gpu_arm(args, rank, world, local_rank):
         t1w = time.time()
     other = "add" if args.sam_cam_fusion == "multiply" else "multiply"
     variant = measure(other, max(10, args.steps // 2), max(3, args.warmup)) if not args.no_variant else None
+    # the other launch path of the library (one kernel per phase), same step, same timing rules
+    variant_split = measure(args.sam_cam_fusion, max(10, args.steps // 2), max(3, args.warmup), split=True) \
+        if not (args.no_variant or args.force_split) else None
 
     # ---- roofline of the dominant kernel
     peaks_path = ROOT / "MEASURED_PEAKS.json"
@@ -446,6 +451,7 @@ def gpu_arm(args, rank, world, local_rank):
                    "sam_cam_fusion": args.sam_cam_fusion, "mga_pyramid_fusion": "add", "parallelism": f"dp{world} (batch sharded; all-reduce of {sum(LevelPlan.n_params(c) for c,_,_ in levels)} fp32 weight grads)",
                    "l2": "two rotating input/output sets per level (2 x 0.73 GB touched per pair of steps) >> 126 MB L2",
                    "cuda_graph": main["graph"], "streams": main["streams"], "algorithmic_bytes_per_step": alg_bytes,
+                   "launch_path": "one kernel per phase (MGA_FORCE_SPLIT)" if args.force_split else "cluster-per-sample fused kernels (cl_fwd / cl_bwd) + bwd_wgrad; shapes the cluster path does not take fall back to one kernel per phase",
                    "step_order": "forward of all levels (one stream per level), join, backward of all levels, join"},
         "gpu_launches": main["launches_per_step"] * args.steps,
         "launches_per_step": main["launches_per_step"],
@@ -458,6 +464,11 @@ def gpu_arm(args, rank, world, local_rank):
         line["variants"] = {other: {"ms_per_step": round(variant["ms"], 5), "value": round(world * alg_bytes / (variant["ms"] * 1e-3) / 1e9, 1),
                                     "images_per_sec": round(world * B / (variant["ms"] * 1e-3), 1),
                                     "note": "oracle: in-repo PyTorch composition; reference parity unpinned" if other == "add" else "reference-equivalent MaskCBAM"}}
+    if variant_split is not None:
+        line.setdefault("variants", {})["one_kernel_per_phase"] = {
+            "ms_per_step": round(variant_split["ms"], 5), "value": round(world * alg_bytes / (variant_split["ms"] * 1e-3) / 1e9, 1),
+            "launches_per_step": variant_split["launches_per_step"],
+            "note": "MGA_FORCE_SPLIT: 12 kernels per level and direction; HBM traffic 10N instead of 5N"}
     if args.sam_cam_fusion == "add":
         line["config"]["note"] = "oracle: in-repo PyTorch composition; reference parity unpinned"
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -492,11 +503,26 @@ def e2e_module(args, dev, levels, B, dtype, world, alg_bytes):
     h2d = sum(t.numel() * t.element_size() for trip in host for t in trip)
     d2h = hgrad.numel() * 4
 
+    # Input pipeline of a training loop: the host->device copies run on their own stream, level by level; the compute stream
+    # waits for the copy of ITS level only, so the copies of the later levels (and of the next step) overlap the kernels.
+    # Each device buffer is rewritten only after the kernels that read it have finished (ev_done).
+    main_s = torch.cuda.current_stream(dev)
+    copy_s = torch.cuda.Stream(dev)
+    ev_copied = [torch.cuda.Event() for _ in levels]
+    ev_done = [torch.cuda.Event() for _ in levels]
+    for e in ev_done:
+        e.record(main_s)
+
     def step():
-        for m, (hx, hm, hg), (dx_, dm_, dg_) in zip(mods, host, devb):
-            dx_.copy_(hx, non_blocking=True)
-            dm_.copy_(hm, non_blocking=True)
-            dg_.copy_(hg, non_blocking=True)
+        with torch.cuda.stream(copy_s):
+            for li, ((hx, hm, hg), (dx_, dm_, dg_)) in enumerate(zip(host, devb)):
+                copy_s.wait_event(ev_done[li])
+                dx_.copy_(hx, non_blocking=True)
+                dm_.copy_(hm, non_blocking=True)
+                dg_.copy_(hg, non_blocking=True)
+                ev_copied[li].record(copy_s)
+        for li, (m, (dx_, dm_, dg_)) in enumerate(zip(mods, devb)):
+            main_s.wait_event(ev_copied[li])
             xin = dx_.requires_grad_(True)
             min_ = dm_.requires_grad_(True)
             out = m([xin, min_])
@@ -505,6 +531,7 @@ def e2e_module(args, dev, levels, B, dtype, world, alg_bytes):
             min_.grad = None
             dx_.requires_grad_(False)
             dm_.requires_grad_(False)
+            ev_done[li].record(main_s)
         if world > 1:
             reducer.all_reduce()
         hgrad.copy_(reducer.flat, non_blocking=True)
@@ -530,7 +557,7 @@ def e2e_module(args, dev, levels, B, dtype, world, alg_bytes):
         ms = float(tmax.item())
     return {"value": round(world * alg_bytes / (ms * 1e-3) / 1e9, 2), "unit": "GB/s", "ms_per_step": round(ms, 4), "steps": steps,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "images_per_sec": round(world * B / (ms * 1e-3), 1),
-            "api": "mga_yolo_b200.MaskGuidedCBAM forward + torch.autograd backward, pinned host x/mask/grad_out in, flat weight grads out"}
+            "api": "mga_yolo_b200.MaskGuidedCBAM forward + torch.autograd backward, pinned host x/mask/grad_out in (copy stream, overlapped with the kernels of the previous level), flat weight grads out"}
 
 
 def reference_arm(args, rank):

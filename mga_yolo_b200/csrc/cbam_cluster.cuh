@@ -72,8 +72,11 @@ struct ClGeom {
     int prefetch;  // 1: bulk L2 prefetch of the sample at kernel start, so the HBM stream overlaps the latency-bound prologue
 };
 
+// the two weight matrices of the shared MLP are staged in shared memory when they are small (always for YOLO necks up to C = 512, r = 16)
+__host__ __device__ inline bool cl_mlp_in_smem(int C, int Hd) { return (C * Hd) % 4 == 0 && 2 * C * Hd * 4 <= 40 * 1024; }
+
 // ---------------------------------------------------------------- shared-memory layouts (float offsets)
-struct ClFwdOff { int wk, red, avg, mx, ha, hm, sAB, q, part, msum, mloc, aloc, tile, mg, stage, total; };
+struct ClFwdOff { int wk, red, avg, mx, ha, hm, sAB, q, part, msum, mloc, aloc, tile, mg, stage, mlpw, total; };
 __host__ __device__ inline ClFwdOff cl_fwd_off(int C, int Hd, const ClGeom& g) {
     ClFwdOff o;
     int p = 0;
@@ -93,13 +96,14 @@ __host__ __device__ inline ClFwdOff cl_fwd_off(int C, int Hd, const ClGeom& g) {
     o.mg = take(3 * g.G * g.nPmax);  // T2 merge buffers [max | sum | idx][G][nPmax]; later the conv's per-plane partials [3][nPmax]
     const int stage_end = o.stage + ((4 * C * (g.LPT | 1) + 3) & ~3);
     if (p < stage_end) p = stage_end;
+    o.mlpw = cl_mlp_in_smem(C, Hd) ? take(2 * C * Hd) : -1;  // cam_mlp weights [W1 (Hd,C) | W2 (C,Hd)], staged with cp.async at kernel start
     o.total = p;
     return o;
 }
 
 struct ClBwdOff {
     int wsm, red, s, chA, chG, amx, cM, dz, eloc, qloc, binloc, dha, dhm, q, epart, qpart, binpart, gxpart;
-    int aloc, ae, mloc, idx, pmx, d0, d1s, d2, dpre, cat, tp, dwp, binw, stage, total;
+    int aloc, ae, mloc, idx, pmx, d0, d1s, d2, dpre, cat, tp, dwp, binw, stage, mlpw, total;
 };
 __host__ __device__ inline ClBwdOff cl_bwd_off(int C, int Hd, const ClGeom& g) {
     ClBwdOff o;
@@ -127,6 +131,7 @@ __host__ __device__ inline ClBwdOff cl_bwd_off(int C, int Hd, const ClGeom& g) {
     o.dwp = o.tp;
     o.binw = take((g.NT / 32) * C);
     o.stage = take(C * (g.LPT | 1));
+    o.mlpw = (cl_mlp_in_smem(C, Hd) && 2 * C * Hd * 4 <= 4096) ? take(2 * C * Hd) : -1;  // cam_mlp weights [W1 | W2] staged with cp.async (small ones only)
     o.total = p;
     return o;
 }
@@ -355,13 +360,43 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
     const unsigned rowB = (unsigned)S * (unsigned)sizeof(T);  // bytes per channel plane
 
     const size_t bS = (size_t)b * S;
-    // ---- phase 0: zero the tile (padding), conv weights, mask -> m (own pixels), sum(m)
+    // ---- phase 0: conv weights, MLP weights (async), first pooling loads in flight, mask -> m (own pixels), sum(m)
     stamp(0);
     cluster.barrier_arrive();  // #0 (waited before the first push): every CTA of the cluster has started
     if (gm.prefetch) cl_prefetch_share(x + (size_t)b * C * S, (size_t)C * rowB, r, CS);
+    const float* w1p = prm.w1;
+    const float* w2p = prm.w2;
+    if (o.mlpw >= 0 && ((reinterpret_cast<uintptr_t>(prm.w1) | reinterpret_cast<uintptr_t>(prm.w2)) & 15) == 0) {  // 16-byte asynchronous copies: no registers, waited for just before the MLP
+        float* mw = csm + o.mlpw;
+        const int n4 = C * Hd / 4;
+        for (int i = tid; i < n4; i += NT) {
+            cp_async16(mw + 4 * i, prm.w1 + 4 * i);
+            cp_async16(mw + C * Hd + 4 * i, prm.w2 + 4 * i);
+        }
+        cp_async_commit();
+        w1p = mw;
+        w2p = mw + C * Hd;
+    }
+    const int LPT = gm.LPT, LPTp = LPT | 1, slots = gm.slots;
+    const int slot = tid / LPT, ul = tid - slot * LPT;
+    const char* xbytes = reinterpret_cast<const char*>(x + (size_t)b * C * S + p0);  // the CTA's pixel range of channel 0
+    unsigned offk[K];
+    int nk = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int u = ul + k * LPT;
+        offk[k] = (unsigned)u * 16u;
+        nk += (slot < slots && u < nU) ? 1 : 0;
+    }
+    uint4 raw[K];  // the first channel of this thread's walk: in flight while the mask is prepared
+    if (slot < C) {
+        const char* row = xbytes + (size_t)slot * rowB;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (k < nk) raw[k] = ldg128<kPolKeep>(addw(row, offk[k]), pol);
+    }
     for (int i = nP + tid; i < gm.LPT * K * VEC; i += NT) mloc[i] = 0.0f;  // padding of the T1 footprint
     cl_load_weights7<NT>(prm.wsam, sh.k, false, wk);
-    __syncthreads();
     float mtot = 0.0f;
     {
         float macc = 0.0f;
@@ -382,35 +417,13 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
 
     // ---- phase 1 (T1): per channel over the CTA's pixels: sum x*m, sum x, masked max + arg max
     stamp(1);
-    const int LPT = gm.LPT, LPTp = LPT | 1, slots = gm.slots;
-    const int slot = tid / LPT, ul = tid - slot * LPT;
-    const char* xbytes = reinterpret_cast<const char*>(x + (size_t)b * C * S + p0);  // the CTA's pixel range of channel 0
-    if (slot < slots) {
-        unsigned offk[K];
-        int nk = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int u = ul + k * LPT;
-            offk[k] = (unsigned)u * 16u;
-            nk += (u < nU) ? 1 : 0;
-        }
-        // software pipelined: the loads of the next channel are in flight while this one is reduced
-        uint4 nxt[K];
-        if (slot < C) {
-            const char* row = xbytes + (size_t)slot * rowB;
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                if (k < nk) nxt[k] = ldg128<kPolKeep>(addw(row, offk[k]), pol);
-        }
+    if (nk > 0) {
         for (int c = slot; c < C; c += slots) {
-            uint4 raw[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) raw[k] = nxt[k];
-            if (c + slots < C) {
-                const char* row = xbytes + (size_t)(c + slots) * rowB;
+            if (c != slot) {
+                const char* row = xbytes + (size_t)c * rowB;
 #pragma unroll
                 for (int k = 0; k < K; ++k)
-                    if (k < nk) nxt[k] = ldg128<kPolKeep>(addw(row, offk[k]), pol);
+                    if (k < nk) raw[k] = ldg128<kPolKeep>(addw(row, offk[k]), pol);
             }
             float sxm = 0.0f, sx = 0.0f, best = -INFINITY;
             int bpos = -1;
@@ -436,28 +449,44 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
             st[2 * C * LPTp] = best;
             st[3 * C * LPTp] = __int_as_float(bidx);
         }
+    } else if (slot < slots) {
+        for (int c = slot; c < C; c += slots) {  // this thread owns no valid unit (short last rank): neutral partials
+            float* st = stage + c * LPTp + ul;
+            st[0] = 0.0f;
+            st[C * LPTp] = 0.0f;
+            st[2 * C * LPTp] = -INFINITY;
+            st[3 * C * LPTp] = __int_as_float(-1);
+        }
     }
     __syncthreads();
-    // per channel: combine the LPT thread partials (fixed order; max ties -> lower pixel index), then push to every rank
+    // per channel: combine the LPT thread partials (4 threads per channel, fixed order; max ties -> lower pixel index), push to every rank
     cluster.barrier_wait();  // #0
     if (has_mask && tid < CS) cluster.map_shared_rank(msum_part, tid)[r] = mtot;
-    for (int c = tid; c < C; c += NT) {
-        const float* st = stage + c * LPTp;
+    for (int c0 = 0; c0 < C; c0 += NT / 4) {
+        const int c = c0 + tid / 4, sl = tid & 3;
         float sxm = 0.0f, sx = 0.0f, best = -INFINITY;
         int bidx = -1;
-        for (int j = 0; j < LPT; ++j) {
-            sxm += st[j];
-            sx += st[C * LPTp + j];
-            const float ob = st[2 * C * LPTp + j];
-            const int oi = __float_as_int(st[3 * C * LPTp + j]);
+        if (c < C) {
+            const float* st = stage + c * LPTp;
+            for (int j = sl; j < LPT; j += 4) {
+                sxm += st[j];
+                sx += st[C * LPTp + j];
+                const float ob = st[2 * C * LPTp + j];
+                const int oi = __float_as_int(st[3 * C * LPTp + j]);
+                if ((oi >= 0) && (bidx < 0 || ob > best || (ob == best && oi < bidx))) { best = ob; bidx = oi; }
+            }
+        }
+#pragma unroll
+        for (int of = 2; of > 0; of >>= 1) {
+            sxm += __shfl_xor_sync(0xffffffffu, sxm, of);
+            sx += __shfl_xor_sync(0xffffffffu, sx, of);
+            const float ob = __shfl_xor_sync(0xffffffffu, best, of);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, of);
             if ((oi >= 0) && (bidx < 0 || ob > best || (ob == best && oi < bidx))) { best = ob; bidx = oi; }
         }
-        for (int rr = 0; rr < CS; ++rr) {
-            float* dst = cluster.map_shared_rank(part, rr) + r * 4 * C;
-            dst[c] = sxm;
-            dst[C + c] = sx;
-            dst[2 * C + c] = best;
-            dst[3 * C + c] = __int_as_float(bidx);
+        if (c < C) {
+            const float val = sl == 0 ? sxm : (sl == 1 ? sx : (sl == 2 ? best : __int_as_float(bidx)));
+            for (int rr = 0; rr < CS; ++rr) cluster.map_shared_rank(part, rr)[r * 4 * C + sl * C + c] = val;  // lane sl pushes quantity sl
         }
     }
     const float beta = __ldg(prm.beta);
@@ -511,13 +540,14 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
     const float alpha = softplusf_acc(beta);
     const float k0 = sh.pyramid_multiply() ? 0.0f : 1.0f - alpha, k1 = alpha;
     if (b == 0 && r == 0 && tid == 0) { ctx.consts[0] = k0; ctx.consts[1] = k1; ctx.consts[2] = alpha; ctx.consts[3] = sigmoidf_acc(beta); }
-    __syncthreads();
+    cp_async_wait_all();  // the staged MLP weights of this thread ...
+    __syncthreads();      // ... and of every other thread
     for (int j = w; j < Hd; j += NW) {
-        const float* wr = prm.w1 + (size_t)j * C;
+        const float* wr = w1p + (size_t)j * C;
         float pa = 0.0f, pm = 0.0f;
 #pragma unroll 4
         for (int c = lane; c < C; c += 32) {
-            const float wv = __ldg(wr + c);
+            const float wv = wr[c];
             pa = fmaf(wv, s_avg[c], pa);
             pm = fmaf(wv, s_mx[c], pm);
         }
@@ -535,11 +565,11 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
     {
         const bool add = sh.samcam_add();
         for (int c = tid; c < C; c += NT) {
-            const float* wr = prm.w2 + (size_t)c * Hd;
+            const float* wr = w2p + (size_t)c * Hd;
             float za = 0.0f, zm = 0.0f;
 #pragma unroll 4
             for (int j = 0; j < Hd; ++j) {
-                const float wv = __ldg(wr + j);
+                const float wv = wr[j];
                 za = fmaf(wv, s_ha[j], za);
                 zm = fmaf(wv, s_hm[j], zm);
             }
@@ -768,40 +798,12 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
     const unsigned rowB = (unsigned)S * (unsigned)sizeof(T);
 
     const size_t bS = (size_t)b * S;
-    // ---- phase 0: per-sample vectors and planes of the saved context
+    // ---- phase 0: first (x,g) loads in flight, MLP weights (async), per-sample vectors and planes of the saved context
     stamp(0);
     if (gm.prefetch) {
         cl_prefetch_share(x + (size_t)b * C * S, (size_t)C * rowB, r, CS);
         cl_prefetch_share(g + (size_t)b * C * S, (size_t)C * rowB, r, CS);
     }
-    cl_load_weights7<NT>(prm.wsam, sh.k, true, wsm);
-    for (int i = tid; i < planeT; i += NT) dpre[i] = 0.0f;
-    for (int i = tid; i < NW * C; i += NT) binw[i] = 0.0f;
-    for (int c = tid; c < C; c += NT) {
-        const float s = ctx.s[b * C + c];
-        s_s[c] = s;
-        s_q[c] = multiply ? s : 1.0f;
-    }
-    for (int p = tid; p < gm.LPT * K * VEC; p += NT) {
-        const bool in = p < nP;
-        const float a = in ? ctx.a[bS + p0 + p] : 0.0f;
-        ae[p] = in ? (multiply ? a : 1.0f) : 0.0f;
-        d1s[p] = 0.0f;
-        if (in) {
-            aloc[p] = a;
-            mloc[p] = has_mask ? ctx.m[bS + p0 + p] : 0.0f;
-            idxl[p] = ctx.idx[bS + p0 + p];
-            pmx[p] = ctx.pmax[bS + p0 + p];
-        }
-    }
-    {
-        const float* const planes[3] = {ctx.pmax + bS, ctx.pavg + bS, has_mask ? ctx.m + bS : nullptr};
-        cl_stage_three<NT>(cat, planeT, planes, y0 - kMaxK / 2, gm.tileRows, H, W, TWp);
-    }
-    __syncthreads();
-
-    // ---- phase 1 (T1) over (x,g): T_p = sum_c g x q_c (per pixel), E_c = sum_p g x (a | 1) (per channel), sum g x
-    stamp(1);
     const int LPT = gm.LPT, LPTp = LPT | 1, slots = gm.slots;
     const int slot = tid / LPT, ul = tid - slot * LPT;
     const size_t sbase = (size_t)b * C * S + p0;
@@ -815,6 +817,71 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
         offk[k] = (unsigned)u * 16u;
         nk += (slot < slots && u < nU) ? 1 : 0;
     }
+    uint4 xr[K], gr[K];  // the first channel of this thread's walk: in flight while the context is staged
+    if (slot < C) {
+        const char* xrow = xbytes + (size_t)slot * rowB;
+        const char* grow = gbytes + (size_t)slot * rowB;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (k < nk) {
+                xr[k] = ldg128<kPolKeep>(addw(xrow, offk[k]), pol);
+                gr[k] = ldg128<kPolKeep>(addw(grow, offk[k]), pol);
+            }
+    }
+    const float* w1p = prm.w1;
+    const float* w2p = prm.w2;
+    if (o.mlpw >= 0 && ((reinterpret_cast<uintptr_t>(prm.w1) | reinterpret_cast<uintptr_t>(prm.w2)) & 15) == 0) {
+        float* mw = csm + o.mlpw;
+        const int n4 = C * Hd / 4;
+        for (int i = tid; i < n4; i += NT) {
+            cp_async16(mw + 4 * i, prm.w1 + 4 * i);
+            cp_async16(mw + C * Hd + 4 * i, prm.w2 + 4 * i);
+        }
+        cp_async_commit();
+        w1p = mw;
+        w2p = mw + C * Hd;
+    }
+    cl_load_weights7<NT>(prm.wsam, sh.k, true, wsm);
+    for (int i = tid; i < planeT; i += NT) dpre[i] = 0.0f;
+    for (int i = tid; i < NW * C; i += NT) binw[i] = 0.0f;
+    for (int c = tid; c < C; c += NT) {
+        const float s = ctx.s[b * C + c];
+        s_s[c] = s;
+        s_q[c] = multiply ? s : 1.0f;
+    }
+    for (int q0 = 0; q0 < gm.LPT * K * VEC; q0 += 4 * NT) {  // four pixels per thread: all loads first
+        float av[4], mv[4], pv[4];
+        int iv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int p = q0 + j * NT + tid;
+            av[j] = 0.0f; mv[j] = 0.0f; pv[j] = 0.0f; iv[j] = 0;
+            if (p < nP) {
+                av[j] = ctx.a[bS + p0 + p];
+                if (has_mask) mv[j] = ctx.m[bS + p0 + p];
+                iv[j] = ctx.idx[bS + p0 + p];
+                pv[j] = ctx.pmax[bS + p0 + p];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int p = q0 + j * NT + tid;
+            if (p < gm.LPT * K * VEC) {
+                const bool in = p < nP;
+                ae[p] = in ? (multiply ? av[j] : 1.0f) : 0.0f;
+                d1s[p] = 0.0f;
+                if (in) { aloc[p] = av[j]; mloc[p] = mv[j]; idxl[p] = iv[j]; pmx[p] = pv[j]; }
+            }
+        }
+    }
+    {
+        const float* const planes[3] = {ctx.pmax + bS, ctx.pavg + bS, has_mask ? ctx.m + bS : nullptr};
+        cl_stage_three<NT>(cat, planeT, planes, y0 - kMaxK / 2, gm.tileRows, H, W, TWp);
+    }
+    __syncthreads();
+
+    // ---- phase 1 (T1) over (x,g): T_p = sum_c g x q_c (per pixel), E_c = sum_p g x (a | 1) (per channel), sum g x
+    stamp(1);
     float gxs = 0.0f;
     {
         float tacc[K][VEC];
@@ -824,15 +891,16 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
             for (int i = 0; i < VEC; ++i) tacc[k][i] = 0.0f;
         if (slot < slots) {
             for (int c = slot; c < C; c += slots) {
-                const char* xrow = xbytes + (size_t)c * rowB;
-                const char* grow = gbytes + (size_t)c * rowB;
-                uint4 xr[K], gr[K];
+                if (c != slot) {
+                    const char* xrow = xbytes + (size_t)c * rowB;
+                    const char* grow = gbytes + (size_t)c * rowB;
 #pragma unroll
-                for (int k = 0; k < K; ++k)
-                    if (k < nk) {
-                        xr[k] = ldg128<kPolKeep>(addw(xrow, offk[k]), pol);
-                        gr[k] = ldg128<kPolKeep>(addw(grow, offk[k]), pol);
-                    }
+                    for (int k = 0; k < K; ++k)
+                        if (k < nk) {
+                            xr[k] = ldg128<kPolKeep>(addw(xrow, offk[k]), pol);
+                            gr[k] = ldg128<kPolKeep>(addw(grow, offk[k]), pol);
+                        }
+                }
                 const float q = s_q[c];
                 float e = 0.0f;
 #pragma unroll
@@ -945,7 +1013,6 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
         if (slot < slots) {
             for (int c = slot; c < C; c += slots) {
                 const char* xrow = xbytes + (size_t)c * rowB;
-                uint4 xr[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k)
                     if (k < nk) xr[k] = ldg128<kPolKeep>(addw(xrow, offk[k]), pol);
@@ -1006,6 +1073,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
 
     // ---- phase 4: ds -> dz -> MLP backward -> per-channel coefficients (recomputed by every CTA)
     stamp(6);
+    cp_async_wait_all();  // staged MLP weights (made visible to the other threads by the barriers below)
     float kb = 0.0f;
     {
         double gx_tot = 0.0;
@@ -1026,7 +1094,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
         for (int j = w; j < Hd; j += NW) {
             float acc = 0.0f;
 #pragma unroll 4
-            for (int c = lane; c < C; c += 32) acc = fmaf(s_dz[c], __ldg(prm.w2 + (size_t)c * Hd + j), acc);
+            for (int c = lane; c < C; c += 32) acc = fmaf(s_dz[c], w2p[(size_t)c * Hd + j], acc);
             acc = warp_sum(acc);
             if (lane == 0) {
                 const float da = ctx.ha[b * Hd + j] > 0.0f ? acc : 0.0f;
@@ -1046,7 +1114,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
             float davg = 0.0f, dmx = 0.0f;
 #pragma unroll 4
             for (int j = 0; j < Hd; ++j) {
-                const float wv = __ldg(prm.w1 + (size_t)j * C + c);
+                const float wv = w1p[(size_t)j * C + c];
                 davg = fmaf(s_dha[j], wv, davg);
                 dmx = fmaf(s_dhm[j], wv, dmx);
             }

@@ -363,6 +363,8 @@ static bool cl_geometry(const Shape& sh, int esize, bool bwd, ClGeom* out) {
         g.planeT = (g.tileRows * g.TWp + 31) & ~31;
         g.smem_bytes = 4 * (bwd ? cl_bwd_off(sh.C, sh.hidden, g).total : cl_fwd_off(sh.C, sh.hidden, g).total);
         g.prefetch = bwd ? pf_b : pf_f;
+        static const int min_smem_f = env_int("MGA_CL_MINSMEM_F", 0), min_smem_b = env_int("MGA_CL_MINSMEM_B", 0);  // tuning: caps the CTAs per SM
+        g.smem_bytes = std::max(g.smem_bytes, bwd ? min_smem_b : min_smem_f);
         if (g.smem_bytes > kSmemLimit) continue;
         best = g;
         have = true;

@@ -1,0 +1,36 @@
+"""The cluster-per-sample kernels with FORCED cluster sizes on shapes whose rows do not divide evenly: ragged last rank,
+halo rows that come from more than one neighbour, 16-bit units that span image rows (W = 20), cluster size 16.
+Every case runs in a child process because the tuning overrides are read once per process.  Oracle: oracle/cbam_oracle.py
+(fp64); tolerances as in test_gpu_cbam.py."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+CASES = [
+    # B, C,  H,  W, dtype,      scf,        pyr,        CS_F, CS_B
+    (3, 48, 22, 24, "float32", "multiply", "add", 4, 4),     # rows 6,6,6,4
+    (2, 40, 20, 20, "float32", "multiply", "add", 8, 8),     # rows 3 x6 + 2: halo from two ranks away never needed, last rank short
+    (2, 32, 16, 16, "float32", "add", "multiply", 16, 16),   # one row per CTA: the 3 halo rows come from three different ranks
+    (2, 24, 80, 80, "float32", "multiply", "add", 16, 16),   # cluster of 16, 5 rows each
+    (2, 64, 20, 20, "bfloat16", "multiply", "add", 4, 2),    # W = 20 with 8-element units: rows per CTA must be even
+    (2, 64, 40, 40, "float16", "add", "add", 8, 4),
+    (5, 128, 40, 40, "float32", "multiply", "multiply", 2, 8),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[1]}x{c[2]}x{c[3]}-{c[4]}-cs{c[7]}/{c[8]}")
+def test_forced_cluster_sizes_match_oracle(case):
+    B, C, H, W, dt, scf, pyr, csf, csb = case
+    env = dict(os.environ, MGA_CL_CS_F=str(csf), MGA_CL_CS_B=str(csb), MGA_CL_DEBUG="1", PYTHONPATH=str(ROOT))
+    for k in ("MGA_FORCE_SPLIT", "MGA_USE_FUSED", "MGA_USE_FLOW", "MGA_CL"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, "-m", "tests._cluster_case", str(B), str(C), str(H), str(W), dt, scf, pyr], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "[mga] cluster fwd" in r.stderr and "[mga] cluster bwd" in r.stderr, "the cluster path did not run:\n" + r.stderr

@@ -14,10 +14,5 @@ except Exception as e:
 P
 }
 L=libmga_cbam.so
-for kf in 224 448; do for kb in 448 896; do
-run f${kf}_b${kb} $L MGA_CL_KB_F=$kf MGA_CL_KB_B=$kb
-BENCH_ARGS=--one-stream run f${kf}_b${kb}_one $L MGA_CL_KB_F=$kf MGA_CL_KB_B=$kb
-done; done
-run f112_b448 $L MGA_CL_KB_F=112 MGA_CL_KB_B=448
-run f224_b448_pf $L MGA_CL_PREFETCH_F=1 MGA_CL_PREFETCH_B=1
-MGA_CL_DEBUG=1 MGA_CL_KB_F=448 MGA_CL_KB_B=896 python tools/run_level.py cfg2 0 both 1 2>&1 | grep mga | sort -u
+run base $L
+BENCH_ARGS=--one-stream run base_one $L
