@@ -612,10 +612,22 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    # stdout carries exactly ONE line (the JSON record): everything libraries print while we run (NCCL's version banner,
+    # Ultralytics-style loggers ...) goes to stderr -- file descriptor 1 is pointed at stderr until the record is ready.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
         line = reference_arm(args, rank)
         if line is not None:
-            print(json.dumps(line), flush=True)
+            emit(line)
         return 0
 
     if not torch.cuda.is_available():
@@ -630,7 +642,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     line = gpu_arm(args, rank, world, local_rank)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         import torch.distributed as dist
 

@@ -53,6 +53,11 @@ __device__ __forceinline__ void stamp(int k) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         g_timeline[(size_t)blockIdx.x * 16 + k] = t;
+        if (k == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_timeline[(size_t)blockIdx.x * 16 + 15] = smid;
+        }
     }
 }
 
