@@ -48,7 +48,9 @@ enum {
     MGA_FORCE_SPLIT = 1 << 8,      /* never take the cluster-resident fused forward kernel */
     MGA_USE_FUSED = 1 << 9,        /* opt in to the cluster-resident fused forward kernel (experimental) */
     MGA_USE_FLOW = 1 << 11,        /* one wavefront-ordered dataflow kernel per direction instead of one kernel per phase */
-    MGA_GATES_ONLY = 1 << 10       /* internal: compute / differentiate the two gates s(B,C), a(B,HW) only (concat fusion modes) */
+    MGA_GATES_ONLY = 1 << 10,      /* internal: compute / differentiate the two gates s(B,C), a(B,HW) only (concat fusion modes) */
+    MGA_NO_SAVE = 1 << 12          /* inference (model.eval() + no_grad, predictor.py:7-24): the forward may skip the saved-for-backward
+                                      planes; ctx is then NOT valid for mga_cbam_backward (s and a are still written) */
 };
 
 typedef struct mga_cbam_desc {

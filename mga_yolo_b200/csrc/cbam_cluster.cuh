@@ -43,10 +43,22 @@ namespace cgx = cooperative_groups;
 #endif
 constexpr int kClNTF = MGA_CL_NT_F, kClNTB = MGA_CL_NT_B;
 constexpr int kClWmax = 16;  // most warps per CTA (sizes the warp-private bins of the backward kernel)
-constexpr int kClK = 5;   // T1: units per thread and channel
+#ifndef MGA_CL_K_F
+#define MGA_CL_K_F 5
+#endif
+#ifndef MGA_CL_K_B
+#define MGA_CL_K_B 5
+#endif
+#ifndef MGA_CL_DXKB
+#define MGA_CL_DXKB 4
+#endif
+constexpr int kClKF = MGA_CL_K_F, kClKB = MGA_CL_K_B;  // T1: units per thread and channel (forward / backward)
 
 #ifndef MGA_CL_HINTS
 #define MGA_CL_HINTS 1  // L2 eviction-priority hints: first touch of x/g = keep, last read = evict first
+#endif
+#ifndef MGA_CL_GPOL
+#define MGA_CL_GPOL kPolKeep  // L2 policy of the FIRST read of grad_out in the backward kernel
 #endif
 #ifndef MGA_CL_MINB_F
 #define MGA_CL_MINB_F 2  // resident CTAs per SM the register allocation of the forward kernel must allow
@@ -88,7 +100,7 @@ __host__ __device__ inline ClFwdOff cl_fwd_off(int C, int Hd, const ClGeom& g) {
     o.q = take(g.G * g.CG);         // group-major q
     o.part = take(4 * C * g.CS);    // pool partials of every rank (pushed)
     o.msum = take(16);
-    o.mloc = take(g.LPT * kClK * 8);  // m of the own pixels, zero padded to the T1 footprint
+    o.mloc = take(g.LPT * kClKF * 8);  // m of the own pixels, zero padded to the T1 footprint
     // the T1 per-thread partials [4][C][LPT|1] of the pooling phase are dead before the planes exist: same storage
     o.stage = p;
     o.aloc = take(g.nPmax);
@@ -120,7 +132,7 @@ __host__ __device__ inline ClBwdOff cl_bwd_off(int C, int Hd, const ClGeom& g) {
     o.q = take(C);
     o.epart = take(C * g.CS); o.qpart = take(C * g.CS); o.binpart = take(C * g.CS);
     o.gxpart = take(2 * 16);  // doubles
-    const int padP = g.LPT * kClK * 8;  // T1 footprint in pixels (>= nPmax), zero padded
+    const int padP = g.LPT * kClKB * 8;  // T1 footprint in pixels (>= nPmax), zero padded
     o.aloc = take(g.nPmax); o.ae = take(padP); o.mloc = take(g.nPmax); o.idx = take(g.nPmax); o.pmx = take(g.nPmax);
     o.d0 = take(g.nPmax); o.d1s = take(padP); o.d2 = take(g.nPmax);
     o.dpre = take(g.planeT);
@@ -323,7 +335,7 @@ template <typename T>
 __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* __restrict__ x, const void* __restrict__ mask, int mdt,
                                                                   T* __restrict__ out, Shape sh, mga_cbam_params prm, Ctx ctx, ClGeom gm) {
     constexpr int VEC = 16 / sizeof(T);
-    constexpr int K = kClK;
+    constexpr int K = kClKF;
     constexpr int NT = kClNTF, NW = NT / 32;
     constexpr int kGrp = NT / 3;  // conv: threads per input plane
     extern __shared__ __align__(128) float clsm[];
@@ -340,6 +352,7 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
     const int nPmax = gm.nPmax, nUmax = gm.nUmax, TWp = gm.TWp, planeT = gm.planeT;
     const int G = gm.G, CG = gm.CG;
     const bool has_mask = sh.has_mask();
+    const bool save = !sh.no_save();  // inference: the planes only the backward reads are not written
     const ClFwdOff o = cl_fwd_off(C, Hd, gm);
     float* wk = csm + o.wk;
     float* red = csm + o.red;
@@ -406,7 +419,7 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
                 v = load_mask_any(mask, mdt, bS + p0 + i);
                 if (sh.gate_clamp()) v = fminf(fmaxf(v, 0.0f), 1.0f);
                 if (sh.sigmoid_mask()) v = sigmoidf_acc(v);
-                ctx.m[bS + p0 + i] = v;
+                if (save) ctx.m[bS + p0 + i] = v;
                 macc += v;
             }
             mloc[i] = v;
@@ -658,9 +671,11 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
             const int ry = p / W, cx = p - ry * W;
             tile[(3 + ry) * TWp + 4 + cx] = bm;
             tile[planeT + (3 + ry) * TWp + 4 + cx] = pavg;
-            ctx.pmax[bS + p0 + p] = bm;
-            ctx.pavg[bS + p0 + p] = pavg;
-            ctx.idx[bS + p0 + p] = bi;
+            if (save) {
+                ctx.pmax[bS + p0 + p] = bm;
+                ctx.pavg[bS + p0 + p] = pavg;
+                ctx.idx[bS + p0 + p] = bi;
+            }
         }
     }
     stamp(5);
@@ -741,7 +756,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
                                                                   int mdt, T* __restrict__ dx, void* __restrict__ dmask, Shape sh,
                                                                   mga_cbam_params prm, Ctx ctx, BwdScratch bs, ClGeom gm) {
     constexpr int VEC = 16 / sizeof(T);
-    constexpr int K = kClK;
+    constexpr int K = kClKB;
     constexpr int NT = kClNTB, NW = NT / 32;
     constexpr int kGrp = NT / 3;  // conv: threads per input plane
     constexpr int kStride = 3 * kMaxK * kMaxK + 1;
@@ -825,7 +840,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
         for (int k = 0; k < K; ++k)
             if (k < nk) {
                 xr[k] = ldg128<kPolKeep>(addw(xrow, offk[k]), pol);
-                gr[k] = ldg128<kPolKeep>(addw(grow, offk[k]), pol);
+                gr[k] = ldg128<MGA_CL_GPOL>(addw(grow, offk[k]), pol);
             }
     }
     const float* w1p = prm.w1;
@@ -898,7 +913,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
                     for (int k = 0; k < K; ++k)
                         if (k < nk) {
                             xr[k] = ldg128<kPolKeep>(addw(xrow, offk[k]), pol);
-                            gr[k] = ldg128<kPolKeep>(addw(grow, offk[k]), pol);
+                            gr[k] = ldg128<MGA_CL_GPOL>(addw(grow, offk[k]), pol);
                         }
                 }
                 const float q = s_q[c];
@@ -1161,7 +1176,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
                 const int d = ix[i] - g2;
                 ix[i] = (d >= 0 && d % G == 0) ? d / G : -1;
             }
-            constexpr int KB = 4;
+            constexpr int KB = MGA_CL_DXKB;
             const int nj = (C - g2 + G - 1) / G;
             const unsigned gstep = (unsigned)G * rowB;
             const size_t toff = (size_t)g2 * rowB + (size_t)ul2 * 16;

@@ -356,7 +356,8 @@ static bool cl_geometry(const Shape& sh, int esize, bool bwd, ClGeom* out) {
         g.nPmax = nP;
         g.G = std::max(1, std::min(NT / nU, sh.C));
         g.CG = (((sh.C + g.G - 1) / g.G) + 7) & ~7;
-        g.LPT = (nU + kClK - 1) / kClK;
+        const int K = bwd ? kClKB : kClKF;
+        g.LPT = (nU + K - 1) / K;
         g.slots = NT / g.LPT;
         g.tileRows = rowsPer + kMaxK - 1;
         g.TWp = sh.W + 8;

@@ -269,6 +269,10 @@ def cbam_gates(x, mask, w1, b1, w2, b2, wsam, *, flags: int, tiny_mask_thr: floa
 def mask_guided_cbam(x: torch.Tensor, mask: Optional[torch.Tensor], w1, b1, w2, b2, wsam, beta, *, flags: int,
                      tiny_mask_thr: float = 1e-4, eps: float = 1e-6) -> torch.Tensor:
     """Functional entry: out = MaskCBAM([x, mask]) with the given parameters (autograd-aware)."""
+    needs_grad = torch.is_grad_enabled() and any(
+        isinstance(t, torch.Tensor) and t.requires_grad for t in (x, mask, w1, b1, w2, b2, wsam, beta))
+    if not needs_grad:  # inference (predictor / validator): nothing is saved for a backward that will never run
+        flags = int(flags) | _lib.NO_SAVE
     return _CbamFn.apply(x, mask, w1, b1, w2, b2, wsam, beta, int(flags), float(tiny_mask_thr), float(eps))
 
 

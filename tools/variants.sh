@@ -13,6 +13,7 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 P
 }
-L=libmga_cbam.so
-run base $L
-BENCH_ARGS=--one-stream run base_one $L
+for L in libmga_cbam.so libmga_b512k3.so libmga_b512k4.so libmga_b512k5.so; do
+run $L $L
+BENCH_ARGS=--one-stream run ${L}_one $L
+done
