@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* 
 }
 
 // ------------------------------------------------------------------ B6
-// blocks [0,nMlpBlocks): one thread per MLP-gradient element, summing over the batch;
+// blocks [0,nMlpBlocks): 32 MLP-gradient elements per block, summing over the batch;
 // blocks after that: one block per spatial-conv tap (and one for d beta), summing the per-CTA partials.
 __global__ void __launch_bounds__(kBlock) bwd_wgrad_kernel(Shape sh, Ctx ctx, BwdScratch bs, mga_cbam_grads gp, int nConvCta, int nMlpBlocks,
                                                            int nAlphaPart) {
@@ -464,40 +464,41 @@ __global__ void __launch_bounds__(kBlock) bwd_wgrad_kernel(Shape sh, Ctx ctx, Bw
         }
         return;
     }
-    // one WARP per MLP-gradient element: lanes stride over the batch (one memory round trip), then a shuffle sum
+    // 32 consecutive MLP-gradient elements per block (lanes: coalesced along the fast index of avg / mx / dz / ha / hm);
+    // the 8 warps split the batch, their partial sums meet in shared memory and are added in warp order (deterministic).
+    __shared__ float part[kWarpsPerBlock][32];
     const int n_w1 = Hd * C, n_b1 = Hd, n_w2 = C * Hd, n_b2 = C;
     const int total = n_w1 + n_b1 + n_w2 + n_b2;
-    const int lane = threadIdx.x & 31;
-    int i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (i >= total) return;
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    int i = blockIdx.x * 32 + lane;
     float acc = 0.0f;
-    if (i < n_w1) {  // dW1[j][c] = sum_b dha[b][j] avg[b][c] + dhm[b][j] mx[b][c]
-        const int j = i / C, c = i % C;
-        for (int b = lane; b < B; b += 32)
-            acc = fmaf(__ldg(bs.dha + b * Hd + j), __ldg(ctx.avg + b * C + c), fmaf(__ldg(bs.dhm + b * Hd + j), __ldg(ctx.mx + b * C + c), acc));
-        acc = warp_sum(acc);
-        if (lane == 0) gp.w1[i] = acc;
-        return;
+    if (i < total) {
+        if (i < n_w1) {  // dW1[j][c] = sum_b dha[b][j] avg[b][c] + dhm[b][j] mx[b][c]
+            const int j = i / C, c = i - j * C;
+            for (int b = wq; b < B; b += kWarpsPerBlock)
+                acc = fmaf(__ldg(bs.dha + b * Hd + j), __ldg(ctx.avg + b * C + c), fmaf(__ldg(bs.dhm + b * Hd + j), __ldg(ctx.mx + b * C + c), acc));
+        } else if (i < n_w1 + n_b1) {
+            const int j = i - n_w1;
+            for (int b = wq; b < B; b += kWarpsPerBlock) acc += __ldg(bs.dha + b * Hd + j) + __ldg(bs.dhm + b * Hd + j);
+        } else if (i < n_w1 + n_b1 + n_w2) {  // dW2[c][j] = sum_b dz[b][c] (ha + hm)[b][j]
+            const int q = i - n_w1 - n_b1, c = q / Hd, j = q - c * Hd;
+            for (int b = wq; b < B; b += kWarpsPerBlock)
+                acc = fmaf(__ldg(bs.dz + b * C + c), __ldg(ctx.ha + b * Hd + j) + __ldg(ctx.hm + b * Hd + j), acc);
+        } else {
+            const int c = i - n_w1 - n_b1 - n_w2;
+            for (int b = wq; b < B; b += kWarpsPerBlock) acc += __ldg(bs.dz + b * C + c);
+            acc *= 2.0f;  // b2 enters the forward twice (masked_cbam.py:128)
+        }
     }
-    i -= n_w1;
-    if (i < n_b1) {
-        for (int b = lane; b < B; b += 32) acc += __ldg(bs.dha + b * Hd + i) + __ldg(bs.dhm + b * Hd + i);
-        acc = warp_sum(acc);
-        if (lane == 0) gp.b1[i] = acc;
-        return;
+    part[wq][lane] = acc;
+    __syncthreads();
+    if (wq == 0 && i < total) {
+        float t = 0.0f;
+#pragma unroll
+        for (int q = 0; q < kWarpsPerBlock; ++q) t += part[q][lane];
+        float* dst = i < n_w1 ? gp.w1 + i : (i < n_w1 + n_b1 ? gp.b1 + (i - n_w1) : (i < n_w1 + n_b1 + n_w2 ? gp.w2 + (i - n_w1 - n_b1) : gp.b2 + (i - n_w1 - n_b1 - n_w2)));
+        *dst = t;
     }
-    i -= n_b1;
-    if (i < n_w2) {  // dW2[c][j] = sum_b dz[b][c] (ha + hm)[b][j]
-        const int c = i / Hd, j = i % Hd;
-        for (int b = lane; b < B; b += 32) acc = fmaf(__ldg(bs.dz + b * C + c), __ldg(ctx.ha + b * Hd + j) + __ldg(ctx.hm + b * Hd + j), acc);
-        acc = warp_sum(acc);
-        if (lane == 0) gp.w2[i] = acc;
-        return;
-    }
-    i -= n_w2;
-    for (int b = lane; b < B; b += 32) acc += __ldg(bs.dz + b * C + i);
-    acc = warp_sum(acc);
-    if (lane == 0) gp.b2[i] = 2.0f * acc;
 }
 
 }  // namespace mga

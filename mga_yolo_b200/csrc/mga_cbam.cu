@@ -594,7 +594,7 @@ static int backward_split(const Shape& sh, const T* x, const void* mask, int mas
     MGA_TILE_DISPATCH(tc1, MGA_CALL);
 #undef MGA_CALL
     const int nw = 2 * sh.C * sh.hidden + sh.C + sh.hidden;
-    const int nMlpBlocks = (nw + kWarpsPerBlock - 1) / kWarpsPerBlock;  // one warp per element
+    const int nMlpBlocks = (nw + 31) / 32;  // 32 elements per block
     MGA_LAUNCH("bwd_wgrad", st, bwd_wgrad_kernel<<<nMlpBlocks + 3 * sh.k * sh.k + 1, kBlock, 0, st>>>(sh, ctx, bs, gp, nconv, nMlpBlocks, sh.B));
     return check_launch("mga_cbam_backward");
 }
@@ -609,7 +609,7 @@ static int backward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, co
                                static_cast<T*>(dx), dmask, sh, p, ctx, bs))
             return rc;
         const int nw = 2 * sh.C * sh.hidden + sh.C + sh.hidden;
-        const int nMlpBlocks = (nw + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        const int nMlpBlocks = (nw + 31) / 32;
         MGA_LAUNCH("bwd_wgrad", st, bwd_wgrad_kernel<<<nMlpBlocks + 3 * sh.k * sh.k + 1, kBlock, 0, st>>>(sh, ctx, bs, gp, sh.B * cgm.CS, nMlpBlocks, sh.B));
         return check_launch("mga_cbam_backward(cluster)");
     }
