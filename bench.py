@@ -460,6 +460,8 @@ def gpu_arm(args, rank, world, local_rank):
         "e2e": e2e,
         "clocks": clocks,
     }
+    if rank == 0 and world == 1 and not args.no_cpu and args.workload == "cfg2":
+        line["mask_pipeline"] = mask_pipeline(dev, B, 640, peak)
     if variant is not None:
         line["variants"] = {other: {"ms_per_step": round(variant["ms"], 5), "value": round(world * alg_bytes / (variant["ms"] * 1e-3) / 1e9, 1),
                                     "images_per_sec": round(world * B / (variant["ms"] * 1e-3), 1),
@@ -558,6 +560,49 @@ def e2e_module(args, dev, levels, B, dtype, world, alg_bytes):
     return {"value": round(world * alg_bytes / (ms * 1e-3) / 1e9, 2), "unit": "GB/s", "ms_per_step": round(ms, 4), "steps": steps,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "images_per_sec": round(world * B / (ms * 1e-3), 1),
             "api": "mga_yolo_b200.MaskGuidedCBAM forward + torch.autograd backward, pinned host x/mask/grad_out in (copy stream, overlapped with the kernels of the previous level), flat weight grads out"}
+
+
+def mask_pipeline(dev, B, imgsz, peak):
+    """Group 2 of the hot path: binary mask (B, imgsz, imgsz) uint8 -> the three pyramid masks (strides 8/16/32, default method =
+    occupancy + 3x3 close, mga_yolo/data/dataset.py:95-103 + utils/mask_utils.py:64-141) in one kernel, next to the per-stride
+    kernels and to the oracle port on the host (numpy restatement of the cv2 calls the reference makes per sample)."""
+    import numpy as np
+
+    from mga_yolo_b200 import MaskUtils
+    from oracle import mask_oracle as mo
+
+    rng = np.random.default_rng(0)
+    nbuf = 6  # 6 x 26 MB of masks > 126 MB L2
+    bufs = [torch.from_numpy((rng.random((B, imgsz, imgsz)) > 0.7).astype(np.uint8)).to(dev) for _ in range(nbuf)]
+    alg = B * imgsz * imgsz + B * sum((imgsz // s) ** 2 for s in (8, 16, 32))
+
+    def timed(fn, reps=30):
+        for i in range(3):
+            fn(bufs[i % nbuf])
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(bufs[i % nbuf])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    ms_one = timed(lambda m: MaskUtils.masks_multi(m))
+    ms_per = timed(lambda m: [MaskUtils.downsample_mask(m, s) for s in (8, 16, 32)])
+    host = bufs[0][:8].cpu().numpy()
+    t0 = time.perf_counter()
+    for b in range(host.shape[0]):
+        for s in (8, 16, 32):
+            mo.downsample_mask(host[b], s)
+    cpu_s = (time.perf_counter() - t0) / host.shape[0]
+    return {"workload": f"{B} binary masks {imgsz}x{imgsz} uint8 -> strides 8/16/32, default method (block max + 3x3 close)",
+            "one_pass_ms": round(ms_one, 5), "per_stride_ms": round(ms_per, 5), "masks_per_sec": round(B / (ms_one * 1e-3), 1),
+            "roofline": {"bound": "hbm", "achieved": round(alg / (ms_one * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(alg / (ms_one * 1e-3) / 1e9 / peak, 4), "alg_bytes_per_launch": alg,
+                         "note": "one CTA per image: 64 CTAs on 148 SMs, launch-latency bound at this batch"},
+            "cpu_baseline": {"masks_per_sec": round(1.0 / cpu_s, 1), "cores": 1, "kind": "port",
+                             "sample": "8 masks, oracle/mask_oracle.py (numpy restatement of cv2.resize / morphologyEx)"}}
 
 
 def reference_arm(args, rank):

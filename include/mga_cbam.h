@@ -135,6 +135,13 @@ enum {
 int mga_mask_downsample(const uint8_t* src, void* dst, void* tmp, int32_t B, int32_t H, int32_t W, int32_t stride,
                         int32_t method, float thresh, int32_t close3x3, int32_t out_dtype, void* stream);
 
+/* All three pyramid masks of MGADataset.__getitem__ (mga_yolo/data/dataset.py:95-103: `for s in (8, 16, 32): downsample_mask[_prob]`)
+ * in ONE pass over the (B,H,W) uint8 {0,1} masks: dst8 (B,H/8,W/8), dst16 (B,H/16,W/16), dst32 (B,H/32,W/32), uint8 or float32.
+ * Same methods / thresh / close3x3 as mga_mask_downsample, bit-identical results.  Needs H % 32 == 0 and W % 32 == 0
+ * (letterboxed inputs); returns MGA_ERR_UNSUPPORTED otherwise (call mga_mask_downsample per stride). */
+int mga_masks_multi(const uint8_t* src, void* dst8, void* dst16, void* dst32, int32_t B, int32_t H, int32_t W, int32_t method,
+                    float thresh, int32_t close3x3, int32_t out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,128 @@ __global__ void __launch_bounds__(kBlock) morph3x3_kernel(const uint8_t* __restr
     else dst_u8[i] = (uint8_t)v;
 }
 
+
+// ------------------------------------------------------------------ all three pyramid masks in ONE pass over the image
+// One CTA per image.  The (H,W) mask is read once with 64-bit loads as 8x8 blocks: per block the pixel count and the
+// top-left pixel.  16x16 and 32x32 blocks are sums of 2x2 children, so the strides 8/16/32 come out of one read:
+//   nearest  = top-left pixel (H % s == 0: cv2.INTER_NEAREST picks src[i*s][j*s])
+//   maxpool  = count > 0;   avgpool = count / s^2 (exact in fp32)
+//   area     = rne(count / s^2) on uint8, then "> thresh"     (cv2.INTER_AREA on an integer factor = block mean)
+// followed by the optional 3x3 close (dilate, erode; neighbours outside the map ignored) in shared memory.
+// Needs H % 32 == 0, W % 32 == 0 (letterboxed YOLO inputs are) and (H/8)*(W/8) <= kMultiMaxBlocks.
+constexpr int kMultiThreads = 512;
+constexpr int kMultiMaxBlocks = 32768;
+
+struct MultiArgs {
+    int B, H, W, method, close3x3, out_f32, binarise;
+    float thresh;
+};
+
+__device__ __forceinline__ void multi_morph(const uint8_t* src, uint8_t* dst, int h, int w, int op) {
+    for (int i = threadIdx.x; i < h * w; i += kMultiThreads) {
+        const int y = i / w, x = i - y * w;
+        int v = op ? 255 : 0;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int yy = y + dy, xx = x + dx;
+                if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+                const int q = src[yy * w + xx];
+                v = op ? min(v, q) : max(v, q);
+            }
+        dst[i] = (uint8_t)v;
+    }
+}
+
+__global__ void __launch_bounds__(kMultiThreads) masks_multi_kernel(const uint8_t* __restrict__ src, void* __restrict__ d8, void* __restrict__ d16,
+                                                                   void* __restrict__ d32, MultiArgs a) {
+    extern __shared__ __align__(16) uint8_t msm[];
+    const int b = blockIdx.x;
+    const int h8 = a.H / 8, w8 = a.W / 8, n8 = h8 * w8;
+    const int h16 = h8 / 2, w16 = w8 / 2, n16 = h16 * w16;
+    const int h32 = h16 / 2, w32 = w16 / 2, n32 = h32 * w32;
+    uint8_t* c8 = msm;             // counts (<= 64 fits a byte; 16x16 and 32x32 counts need 16 bits)
+    uint8_t* t8 = c8 + n8;         // top-left pixels
+    uint16_t* c16 = reinterpret_cast<uint16_t*>(t8 + n8 + ((2 * n8) & 1));
+    uint16_t* c32 = c16 + n16;
+    uint8_t* wa = reinterpret_cast<uint8_t*>(c32 + n32);  // work planes for the close: [n8] x 2
+    uint8_t* wb = wa + n8;
+    const uint8_t* sp = src + (size_t)b * a.H * a.W;
+    for (int i = threadIdx.x; i < n8; i += kMultiThreads) {
+        const int by = i / w8, bx = i - by * w8;
+        const uint8_t* p = sp + (size_t)(by * 8) * a.W + bx * 8;
+        int cnt = 0;
+        unsigned first = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p + (size_t)r * a.W));
+            // the mask is {0,1} bytes: the byte sum of a word is its popcount
+            cnt += __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u);
+            if (r == 0) first = v.x & 0xffu;
+        }
+        c8[i] = (uint8_t)cnt;
+        t8[i] = (uint8_t)(first != 0);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n16; i += kMultiThreads) {
+        const int y = i / w16, x = i - y * w16;
+        const int o = (2 * y) * w8 + 2 * x;
+        c16[i] = (uint16_t)(c8[o] + c8[o + 1] + c8[o + w8] + c8[o + w8 + 1]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n32; i += kMultiThreads) {
+        const int y = i / w32, x = i - y * w32;
+        const int o = (2 * y) * w16 + 2 * x;
+        c32[i] = (uint16_t)(c16[o] + c16[o + 1] + c16[o + w16] + c16[o + w16 + 1]);
+    }
+    __syncthreads();
+    // per stride: raw map -> (close) -> store
+    for (int lvl = 0; lvl < 3; ++lvl) {
+        const int h = lvl == 0 ? h8 : (lvl == 1 ? h16 : h32), w = lvl == 0 ? w8 : (lvl == 1 ? w16 : w32), n = h * w;
+        const int s = 8 << lvl;
+        void* dst = lvl == 0 ? d8 : (lvl == 1 ? d16 : d32);
+        uint8_t* du = static_cast<uint8_t*>(dst) + (size_t)b * n;
+        float* df = static_cast<float*>(dst) + (size_t)b * n;
+        const bool direct_f = a.out_f32 && !a.close3x3;
+        // raw map into wa (counts / top-left of this level)
+        for (int i = threadIdx.x; i < n; i += kMultiThreads) {
+            int c;
+            uint8_t tl;
+            if (lvl == 0) { c = c8[i]; tl = t8[i]; }
+            else {
+                const int y = i / w, x = i - y * w;
+                c = lvl == 1 ? c16[i] : c32[i];
+                tl = t8[(y << lvl) * w8 + (x << lvl)];
+            }
+            const int s2 = s * s;
+            uint8_t u;
+            float f;
+            if (a.method == MGA_DS_NEAREST) { u = tl; f = (float)u; }
+            else if (a.method == MGA_DS_MAXPOOL) { u = (uint8_t)(c > 0); f = (float)u; }
+            else if (a.method == MGA_DS_AVGPOOL) { f = __fdiv_rn((float)c, (float)s2); u = (uint8_t)(f > 0.0f); }
+            else {
+                u = sat_u8_rne(__fmul_rn((float)c, __fdiv_rn(1.0f, (float)s2)));
+                if (a.binarise) { u = (uint8_t)((float)u > a.thresh); f = (float)u; }
+                else f = fminf(fmaxf((float)u, 0.0f), 1.0f);
+            }
+            if (a.close3x3) wa[i] = u;
+            else if (direct_f) df[i] = f;
+            else du[i] = u;
+        }
+        if (a.close3x3) {
+            __syncthreads();
+            multi_morph(wa, wb, h, w, 0);
+            __syncthreads();
+            multi_morph(wb, wa, h, w, 1);
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += kMultiThreads) {
+                if (a.out_f32) df[i] = (float)wa[i];
+                else du[i] = wa[i];
+            }
+            __syncthreads();
+        }
+    }
+}
+
 }  // namespace mga
 
 using namespace mga;
@@ -144,6 +266,32 @@ extern "C" int mga_mask_downsample(const uint8_t* src, void* dst, void* tmp, int
         if (out_dtype == MGA_F32) morph3x3_kernel<<<grid, kBlock, 0, st>>>(t1, nullptr, static_cast<float*>(dst), B, a.nh, a.nw, 1);
         else morph3x3_kernel<<<grid, kBlock, 0, st>>>(t1, static_cast<uint8_t*>(dst), nullptr, B, a.nh, a.nw, 1);
     }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bad(MGA_ERR_CUDA, cudaGetErrorString(e));
+    return MGA_OK;
+}
+
+extern "C" int mga_masks_multi(const uint8_t* src, void* dst8, void* dst16, void* dst32, int32_t B, int32_t H, int32_t W, int32_t method,
+                               float thresh, int32_t close3x3, int32_t out_dtype, void* stream) {
+    auto bad = [&](int code, const char* msg) { return fail(code, "mga_masks_multi: %s", msg); };
+    if (!src || !dst8 || !dst16 || !dst32) return bad(MGA_ERR_ARG, "null pointer argument");
+    if (B <= 0 || H <= 0 || W <= 0) return bad(MGA_ERR_ARG, "bad mask shape");
+    if (method < MGA_DS_NEAREST || method > MGA_DS_AREA_RAW) return bad(MGA_ERR_ARG, "unknown downsample method");
+    if (out_dtype != MGA_U8 && out_dtype != MGA_F32) return bad(MGA_ERR_ARG, "mask output dtype must be u8 or f32");
+    if (close3x3 && method == MGA_DS_AVGPOOL) return bad(MGA_ERR_ARG, "close3x3 is defined on binary outputs only");
+    if (H % 32 || W % 32 || (H / 8) * (W / 8) > kMultiMaxBlocks || (reinterpret_cast<uintptr_t>(src) & 7))
+        return bad(MGA_ERR_UNSUPPORTED, "needs H % 32 == 0, W % 32 == 0, (H/8)*(W/8) <= 32768 and an 8-byte aligned source: use mga_mask_downsample per stride");
+    MultiArgs a;
+    a.B = B; a.H = H; a.W = W; a.method = method; a.close3x3 = close3x3; a.out_f32 = out_dtype == MGA_F32;
+    a.binarise = method == MGA_DS_AREA; a.thresh = thresh;
+    const int n8 = (H / 8) * (W / 8);
+    const size_t smem = (size_t)2 * n8 + 2 + (size_t)2 * (n8 / 4 + n8 / 16) + (size_t)2 * n8 + 16;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(masks_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+    }
+    masks_multi_kernel<<<B, kMultiThreads, smem, static_cast<cudaStream_t>(stream)>>>(src, dst8, dst16, dst32, a);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bad(MGA_ERR_CUDA, cudaGetErrorString(e));
     return MGA_OK;

@@ -54,9 +54,35 @@ class MaskUtils:
         return torch.ops.mga.mask_downsample(mask, stride, code, 0.0, False, True)
 
     @staticmethod
+    def _method_args(prob: bool):
+        """(method code, thresh, close3x3, out_float) of downsample_mask / downsample_mask_prob for the current environment."""
+        if prob:
+            method = os.getenv("MGA_MASK_METHOD", "area")
+            code = {"avgpool": _lib.DS_AVGPOOL, "nearest": _lib.DS_NEAREST}.get(method, _lib.DS_AREA_RAW)
+            return code, 0.0, False, True
+        method = os.getenv("MGA_MASK_METHOD", "skeleton_bresenham").lower()
+        bridge = os.getenv("MGA_MASK_BRIDGE", "1") not in {"0", "false", "False"}
+        thresh = float(os.getenv("MGA_MASK_THRESH", "0.0"))
+        if method == "nearest":
+            return _lib.DS_NEAREST, 0.0, False, False
+        if method == "area":
+            return _lib.DS_AREA, thresh, bridge, False
+        if method == "maxpool":
+            return _lib.DS_MAXPOOL, 0.0, False, False
+        if method == "pyrdown" or os.getenv("MGA_SKELETON_STRICT", "0").lower() in {"1", "true", "yes"}:
+            return None
+        return _lib.DS_MAXPOOL, 0.0, bridge, False
+
+    @staticmethod
     def masks_multi(bin_masks: torch.Tensor, strides: Sequence[int] = (8, 16, 32), prob: bool = False) -> list:
         """Batch form of MGADataset.__getitem__'s loop (mga_yolo/data/dataset.py:95-103):
-        (B,H,W) uint8 -> [ (B,1,Hs,Ws) for s in strides ]."""
+        (B,H,W) uint8 -> [ (B,1,Hs,Ws) for s in strides ].  Letterboxed sizes (H, W multiples of 32) with the default
+        strides take ONE kernel that reads every mask once (torch.ops.mga.masks_multi); anything else goes stride by stride."""
+        args = MaskUtils._method_args(prob)
+        if tuple(strides) == (8, 16, 32) and bin_masks.dim() == 3 and args is not None and ops.masks_multi_supported(*bin_masks.shape[-2:]):
+            code, thresh, close, out_f = args
+            outs = torch.ops.mga.masks_multi(_binary_u8(bin_masks), code, thresh, close, out_f)
+            return [o.unsqueeze(-3) for o in outs]
         method = os.getenv("MGA_MASK_METHOD", "area")
         outs = []
         for s in strides:

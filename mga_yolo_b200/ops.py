@@ -38,6 +38,7 @@ _LIBDEF.define(
     "Tensor ctx, int flags, float tiny_thr, float eps, bool need_mask_grad) -> (Tensor, Tensor?, Tensor)"
 )
 _LIBDEF.define("mask_downsample(Tensor src, int stride, int method, float thresh, bool close3x3, bool out_float) -> Tensor")
+_LIBDEF.define("masks_multi(Tensor src, int method, float thresh, bool close3x3, bool out_float) -> (Tensor, Tensor, Tensor)")
 
 
 @lru_cache(maxsize=256)
@@ -146,6 +147,29 @@ def _mask_downsample_cuda(src, stride, method, thresh, close3x3, out_float):
     return out[0] if squeeze else out
 
 
+def masks_multi_supported(H: int, W: int) -> bool:
+    """Shapes the one-pass kernel takes (include/mga_cbam.h: mga_masks_multi)."""
+    return H % 32 == 0 and W % 32 == 0 and (H // 8) * (W // 8) <= 32768
+
+
+def _masks_multi_cuda(src, method, thresh, close3x3, out_float):
+    """(B,H,W) uint8 {0,1} -> three maps at strides 8 / 16 / 32 from ONE read of the masks (dataset.py:95-103)."""
+    lib = _lib.load()
+    if src.dtype != torch.uint8 or src.dim() != 3:
+        raise RuntimeError("masks_multi expects a (B,H,W) uint8 {0,1} batch of masks")
+    s3 = src.contiguous()
+    B, H, W = s3.shape
+    if not masks_multi_supported(H, W):
+        raise RuntimeError(f"masks_multi needs H, W divisible by 32 (got {H}x{W}); use mask_downsample per stride")
+    dt = torch.float32 if out_float else torch.uint8
+    with torch.cuda.device(src.device):
+        outs = [torch.empty((B, H // s, W // s), dtype=dt, device=src.device) for s in (8, 16, 32)]
+        rc = lib.mga_masks_multi(s3.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), B, H, W, method, float(thresh),
+                                 int(close3x3), _lib.F32 if out_float else _lib.U8, _stream(src))
+    _lib.check(rc, "mga_masks_multi")
+    return tuple(outs)
+
+
 def _cbam_gates_fwd_cuda(x, mask, w1, b1, w2, b2, wsam, flags, tiny_thr, eps):
     lib = _lib.load()
     x = x.contiguous()
@@ -202,6 +226,7 @@ _LIBIMPL.impl("cbam_gates_bwd", _cbam_gates_bwd_cuda, "CUDA")
 _LIBIMPL.impl("cbam_fwd", _cbam_fwd_cuda, "CUDA")
 _LIBIMPL.impl("cbam_bwd", _cbam_bwd_cuda, "CUDA")
 _LIBIMPL.impl("mask_downsample", _mask_downsample_cuda, "CUDA")
+_LIBIMPL.impl("masks_multi", _masks_multi_cuda, "CUDA")
 
 
 class _CbamFn(torch.autograd.Function):
