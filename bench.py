@@ -462,6 +462,7 @@ def gpu_arm(args, rank, world, local_rank):
     }
     if rank == 0 and world == 1 and not args.no_cpu and args.workload == "cfg2":
         line["mask_pipeline"] = mask_pipeline(dev, B, 640, peak)
+        line["inference_b1"] = inference_b1(dev, levels, dtype, os.cpu_count() or 1)
     if variant is not None:
         line["variants"] = {other: {"ms_per_step": round(variant["ms"], 5), "value": round(world * alg_bytes / (variant["ms"] * 1e-3) / 1e9, 1),
                                     "images_per_sec": round(world * B / (variant["ms"] * 1e-3), 1),
@@ -603,6 +604,59 @@ def mask_pipeline(dev, B, imgsz, peak):
                          "note": "one CTA per image: 64 CTAs on 148 SMs, launch-latency bound at this batch"},
             "cpu_baseline": {"masks_per_sec": round(1.0 / cpu_s, 1), "cores": 1, "kind": "port",
                              "sample": "8 masks, oracle/mask_oracle.py (numpy restatement of cv2.resize / morphologyEx)"}}
+
+
+def inference_b1(dev, levels, dtype, threads):
+    """BASELINE configs[0] at module level: the three MaskCBAM calls of one YOLOv8n inference (imgsz 640, batch 1), eval + no_grad,
+    through the public nn.Module (MGA_NO_SAVE forward), next to the oracle port on the host."""
+    from mga_yolo_b200 import MaskGuidedCBAM
+    from oracle import cbam_oracle as co
+
+    mods, xs, ms = [], [], []
+    gen = torch.Generator().manual_seed(7)
+    for (Cc, H, W) in levels:
+        torch.manual_seed(Cc)
+        mods.append(MaskGuidedCBAM(Cc).to(dev).eval())
+        xs.append(torch.randn(1, Cc, H, W, generator=gen).to(dtype))
+        ms.append(torch.randn(1, 1, H, W, generator=gen))
+    dx = [t.to(dev) for t in xs]
+    dm = [t.to(dev) for t in ms]
+
+    def fwd():
+        with torch.no_grad():
+            return [m([x, k]) for m, x, k in zip(mods, dx, dm)]
+
+    for _ in range(5):
+        fwd()
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fwd()
+    reps = 200
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_graph = e0.elapsed_time(e1) / reps
+    t0 = time.perf_counter()
+    for _ in range(50):
+        fwd()
+    torch.cuda.synchronize(dev)
+    ms_eager = (time.perf_counter() - t0) / 50 * 1e3
+    torch.set_num_threads(threads)
+    ps = [co.default_params(Cc, seed=Cc) for (Cc, _, _) in levels]
+    with torch.no_grad():
+        for _ in range(2):
+            [co.cbam_forward(x.float(), k, p)[0] for x, k, p in zip(xs, ms, ps)]
+        t0 = time.perf_counter()
+        for _ in range(10):
+            [co.cbam_forward(x.float(), k, p)[0] for x, k, p in zip(xs, ms, ps)]
+        cpu_ms = (time.perf_counter() - t0) / 10 * 1e3
+    return {"workload": "BASELINE configs[0] at module level: the three MaskCBAM forwards of one YOLOv8n inference, imgsz 640, batch 1, eval + no_grad",
+            "gpu_ms_cuda_graph": round(ms_graph, 5), "gpu_ms_eager_module_calls": round(ms_eager, 4),
+            "cpu_baseline": {"ms": round(cpu_ms, 3), "cores": threads, "kind": "port", "sample": "10 forwards, oracle/cbam_oracle.py"}}
 
 
 def reference_arm(args, rank):
