@@ -325,16 +325,30 @@ def gpu_arm(args, rank, world, local_rank):
                 print(f"[bench] CUDA graph capture failed ({e}); timing direct launches", file=sys.stderr)
                 graphs = None
 
+        pending = [None, None]  # all-reduce in flight on each buffer set
+
         def one(i):
+            if pending[i & 1] is not None:  # this set's previous gradients must have been reduced before they are overwritten
+                pending[i & 1].wait()
+                pending[i & 1] = None
             if graphs is not None:
                 graphs[i & 1].replay()
             else:
                 step_on(sets[i & 1][0], stream)
             if world > 1:
-                dist.all_reduce(sets[i & 1][1])  # the only collective: flat weight-gradient buffer
+                # the only collective: the flat weight-gradient buffer; asynchronous (NCCL's stream waits for this step's kernels,
+                # the next step's kernels -- on the other buffer set -- do not wait for NCCL), like DDP's bucket overlap
+                pending[i & 1] = dist.all_reduce(sets[i & 1][1], async_op=True)
+
+        def drain():
+            for k in (0, 1):
+                if pending[k] is not None:
+                    pending[k].wait()
+                    pending[k] = None
 
         for i in range(warmup):
             one(i)
+        drain()
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -344,6 +358,7 @@ def gpu_arm(args, rank, world, local_rank):
         e0.record()
         for i in range(steps):
             one(i)
+        drain()  # every all-reduce of the timed steps is inside the timed region
         e1.record()
         torch.cuda.synchronize(dev)
         t_wall1 = time.time()
