@@ -30,3 +30,21 @@ def rel_err(got: torch.Tensor, ref: torch.Tensor) -> float:
     ref = ref.double()
     den = ref.abs().max().item()
     return (got.double() - ref).abs().max().item() / (den if den > 0 else 1.0)
+
+
+# ---- full-size YOLOv8n neck shapes at batch 2: inputs are regenerated from seeds (not stored), the reference's outputs are
+# stored sampled (oracle/gen_golden_large.py).  These shapes run multi-CTA clusters in both directions (DSMEM + halo rows).
+LARGE_CASES = {"p3": (2, 64, 80, 80), "p4": (2, 128, 40, 40), "p5": (2, 256, 20, 20)}
+LARGE_SAMPLES = 4096
+
+
+def large_inputs(tag: str):
+    """(x, mask, g, beta, module seed, sample index) of a large case -- the same code runs in the generator and in the tests."""
+    B, C, H, W = LARGE_CASES[tag]
+    gen = torch.Generator().manual_seed(1000 + C)
+    x = torch.randn(B, C, H, W, generator=gen)
+    mask = torch.randn(B, 1, H, W, generator=gen) * 2.0
+    mask[1, :, : H // 4] = -9.0  # a band that is masked out
+    g = torch.randn(B, C, H, W, generator=gen)
+    idx = torch.randperm(B * C * H * W, generator=gen)[:LARGE_SAMPLES]
+    return x, mask, g, 0.35, C, idx

@@ -82,3 +82,23 @@ def test_mask_oracle_bit_exact_vs_cv2_goldens():
                 assert np.array_equal(got, ref), (tuple(sizes[si]), int(s), method)
                 checked += 1
     assert checked == len(sizes) * len(strides) * 9
+
+
+@pytest.mark.parametrize("tag", ["p3", "p4", "p5"])
+def test_oracle_matches_reference_on_full_size_neck_shapes(tag):
+    """oracle/cbam_oracle.py against outputs of the reference itself on the YOLOv8n P3/P4/P5 shapes (batch 2; inputs regenerated
+    from seeds, reference outputs stored sampled by oracle/gen_golden_large.py)."""
+    import numpy as np
+
+    from tests._golden import GOLDEN, LARGE_CASES, large_inputs
+
+    z = np.load(GOLDEN / f"cbam_large_{tag}.npz")
+    x, mask, g, beta, seed, idx = large_inputs(tag)
+    p = co.CbamParams.from_state_dict({k[2:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("p.")})
+    out, sv = co.cbam_forward(x.double(), mask.double(), p)
+    gr = co.cbam_backward(g.double(), p, sv)
+    assert rel_err(out.reshape(-1)[idx], t(z["out_f64"])) * float(np.abs(z["out_f64"]).max()) / float(z["out_absmax_f64"]) <= 1e-12
+    assert rel_err(gr["dx"].reshape(-1)[idx], t(z["dx_f64"])) <= 1e-11
+    assert rel_err(gr["dmask"], t(z["dmask_f64"])) <= 1e-11
+    for k in PARAM_KEYS:
+        assert rel_err(gr[k], t(z["d." + k + "_f64"])) <= 1e-10, k
