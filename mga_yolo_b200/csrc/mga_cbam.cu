@@ -407,6 +407,20 @@ static int launch_cl(const char* name, Kern kernel, const ClGeom& gm, int nClust
     cfg.numAttrs = 1;
     cudaError_t e;
     {
+        // can at least one cluster of this size / shared-memory footprint be resident?  (cached; 0 -> the caller takes the per-phase path)
+        struct Occ { const void* k; int cs, smem, n; };
+        static thread_local Occ cache[32] = {};
+        int n = -1;
+        for (const Occ& c : cache)
+            if (c.k == (const void*)kernel && c.cs == gm.CS && c.smem == gm.smem_bytes) n = c.n;
+        if (n < 0) {
+            if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+            for (Occ& c : cache)
+                if (!c.k) { c = Occ{(const void*)kernel, gm.CS, gm.smem_bytes, n}; break; }
+        }
+        if (n <= 0) return MGA_ERR_UNSUPPORTED;
+    }
+    {
         LaunchScope ls(name, st);
         e = cudaLaunchKernelEx(&cfg, kernel, args..., gm);  // the geometry is always the last kernel argument
     }
@@ -544,8 +558,10 @@ static int forward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, con
     if (vec > 1 && (d->flags & MGA_USE_FLOW) && !(d->flags & (MGA_FORCE_SPLIT | MGA_GATES_ONLY)) && flow_fwd_supported<T>(sh))
         return forward_flow<T>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, flow_ctl, st);
     ClGeom cgm;
-    if (vec > 1 && !(d->flags & MGA_FORCE_SPLIT) && cl_geometry(sh, (int)sizeof(T), false, &cgm))
-        return launch_cl("cl_fwd", cl_fwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), mask, d->mask_dtype, static_cast<T*>(out), sh, p, ctx);
+    if (vec > 1 && !(d->flags & MGA_FORCE_SPLIT) && cl_geometry(sh, (int)sizeof(T), false, &cgm)) {
+        const int rc = launch_cl("cl_fwd", cl_fwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), mask, d->mask_dtype, static_cast<T*>(out), sh, p, ctx);
+        if (rc != MGA_ERR_UNSUPPORTED) return rc;  // no cluster of that shape fits this device: one kernel per phase
+    }
     if (vec == 1) return forward_split<T, 1>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
     return forward_split<T, VecOf<T>::V>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
 }
@@ -605,13 +621,15 @@ static int backward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, co
     const int vec = pick_vec(sh, d->dtype, {x, g, dx});
     ClGeom cgm;
     if (vec > 1 && !(d->flags & MGA_FORCE_SPLIT) && cl_geometry(sh, (int)sizeof(T), true, &cgm)) {
-        if (int rc = launch_cl("cl_bwd", cl_bwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), static_cast<const T*>(g), mask, d->mask_dtype,
-                               static_cast<T*>(dx), dmask, sh, p, ctx, bs))
-            return rc;
+        const int rc = launch_cl("cl_bwd", cl_bwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), static_cast<const T*>(g), mask, d->mask_dtype,
+                                 static_cast<T*>(dx), dmask, sh, p, ctx, bs);
+        if (rc != MGA_OK && rc != MGA_ERR_UNSUPPORTED) return rc;
+        if (rc == MGA_OK) {
         const int nw = 2 * sh.C * sh.hidden + sh.C + sh.hidden;
         const int nMlpBlocks = (nw + 31) / 32;
         MGA_LAUNCH("bwd_wgrad", st, bwd_wgrad_kernel<<<nMlpBlocks + 3 * sh.k * sh.k + 1, kBlock, 0, st>>>(sh, ctx, bs, gp, sh.B * cgm.CS, nMlpBlocks, sh.B));
         return check_launch("mga_cbam_backward(cluster)");
+        }
     }
     if (vec == 1)
         return backward_split<T, 1>(sh, static_cast<const T*>(x), mask, d->mask_dtype, static_cast<const T*>(g), p, ctx, static_cast<T*>(dx),
