@@ -332,6 +332,8 @@ static bool cl_geometry(const Shape& sh, int esize, bool bwd, ClGeom* out) {
     if (!enabled || sh.gates_only()) return false;
     static const int max_kb_f = env_int("MGA_CL_MAXKB_F", 1 << 30), max_kb_b = env_int("MGA_CL_MAXKB_B", 1 << 30);  // tuning: larger samples -> split path
     if ((double)sh.C * sh.S * esize > 1024.0 * (bwd ? max_kb_b : max_kb_f)) return false;
+    static const int min_kb_f = env_int("MGA_CL_MINKB_F", 0), min_kb_b = env_int("MGA_CL_MINKB_B", 0);              // tuning: smaller samples -> split path
+    if ((double)sh.C * sh.S * esize < 1024.0 * (bwd ? min_kb_b : min_kb_f)) return false;
     const int vec = 16 / esize;
     if (sh.S % vec || sh.W % 4 || sh.C < 1) return false;
     int rowq = 1;

@@ -13,7 +13,12 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 P
 }
-for L in libmga_cbam.so libmga_b512k3.so libmga_b512k4.so libmga_b512k5.so; do
-run $L $L
-BENCH_ARGS=--one-stream run ${L}_one $L
-done
+L=libmga_cbam.so
+run all_cluster $L
+run p5_split $L MGA_CL_MINKB_F=500 MGA_CL_MINKB_B=500
+run p45_split $L MGA_CL_MINKB_F=1000 MGA_CL_MINKB_B=1000
+run p5fwd_split $L MGA_CL_MINKB_F=500
+run p5bwd_split $L MGA_CL_MINKB_B=500
+run p3_split $L MGA_CL_MAXKB_F=1000 MGA_CL_MAXKB_B=1000
+run p3fwd_split $L MGA_CL_MAXKB_F=1000
+run all_split $L MGA_CL=0
