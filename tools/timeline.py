@@ -14,6 +14,8 @@ lib.mga_debug_timeline.argtypes = [C.c_void_p]
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 which = sys.argv[2] if len(sys.argv) > 2 else "fwd"
 levels, B, dtname, _ = WORKLOADS[wl]
+import os
+B = int(os.environ.get("MGA_TL_BATCH", B))
 dev = torch.device("cuda:0")
 for li, (Cc, H, W) in enumerate(levels):
     flat = torch.zeros(LevelPlan.n_params(Cc), device=dev)
@@ -39,5 +41,8 @@ for li, (Cc, H, W) in enumerate(levels):
     print(f"level P{3+li} C={Cc} {H}x{W}: {len(t)} CTAs, kernel span {rel.max():.1f} us")
     print("  phase durations (us) median:", np.round(np.median(d, axis=0), 2))
     print("  phase durations (us) max   :", np.round(d.max(axis=0), 2))
+    late = t[:, 0] > np.percentile(t[:, 0], 60)  # CTAs of the later waves (steady state)
+    if late.sum() > 8:
+        print("  phase durations (us) median, later waves:", np.round(np.median(d[late], axis=0), 2), " lifetime", round(float(np.median(rel[late, nst - 1] - rel[late, 0])), 2))
     print("  CTA start (us) pctl 0/50/100:", np.round(np.percentile(rel[:, 0], [0, 50, 100]), 1),
           " CTA lifetime median:", round(float(np.median(rel[:, nst - 1] - rel[:, 0])), 2))
