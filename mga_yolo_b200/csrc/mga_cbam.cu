@@ -343,10 +343,11 @@ static bool cl_geometry(const Shape& sh, int esize, bool bwd, ClGeom* out) {
     const int forced = bwd ? cs_b : cs_f;
     ClGeom best{};
     bool have = false;
-    for (int CS = 1; CS <= 16; CS *= 2) {
+    static const int any_cs = env_int("MGA_CL_ANYCS", 0);  // tuning: cluster sizes that are not powers of two
+    for (int CS = 1; CS <= 16; CS = any_cs ? CS + 1 : CS * 2) {
         int rowsPer = (sh.H + CS - 1) / CS;
         rowsPer = (rowsPer + rowq - 1) / rowq * rowq;
-        if (CS > 1 && (CS - 1) * rowsPer >= sh.H) break;  // trailing ranks would own nothing
+        if (CS > 1 && (CS - 1) * rowsPer >= sh.H) { if (any_cs) continue; break; }  // trailing ranks would own nothing
         const int nP = rowsPer * sh.W, nU = nP / vec;
         const int NT = bwd ? kClNTB : kClNTF;
         if (nU > NT) continue;

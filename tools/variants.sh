@@ -14,11 +14,11 @@ except Exception as e:
 P
 }
 L=libmga_cbam.so
-run all_cluster $L
-run p5_split $L MGA_CL_MINKB_F=500 MGA_CL_MINKB_B=500
-run p45_split $L MGA_CL_MINKB_F=1000 MGA_CL_MINKB_B=1000
-run p5fwd_split $L MGA_CL_MINKB_F=500
-run p5bwd_split $L MGA_CL_MINKB_B=500
-run p3_split $L MGA_CL_MAXKB_F=1000 MGA_CL_MAXKB_B=1000
-run p3fwd_split $L MGA_CL_MAXKB_F=1000
-run all_split $L MGA_CL=0
+run base $L
+run any_b330 $L MGA_CL_ANYCS=1 MGA_CL_KB_B=330
+run any_b380 $L MGA_CL_ANYCS=1 MGA_CL_KB_B=380
+run any_b280 $L MGA_CL_ANYCS=1 MGA_CL_KB_B=280
+run any_f190 $L MGA_CL_ANYCS=1 MGA_CL_KB_F=190
+run any_f170 $L MGA_CL_ANYCS=1 MGA_CL_KB_F=170
+run any_f300 $L MGA_CL_ANYCS=1 MGA_CL_KB_F=300
+MGA_CL_DEBUG=1 MGA_CL_ANYCS=1 MGA_CL_KB_B=330 MGA_CL_KB_F=190 python tools/run_level.py cfg2 0 both 1 2>&1 | grep mga | sort -u
