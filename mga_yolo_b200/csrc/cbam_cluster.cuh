@@ -52,7 +52,10 @@ constexpr int kClWmax = 16;  // most warps per CTA (sizes the warp-private bins 
 #ifndef MGA_CL_DXKB
 #define MGA_CL_DXKB 4
 #endif
-constexpr int kClKF = MGA_CL_K_F, kClKB = MGA_CL_K_B;  // T1: units per thread and channel (forward / backward)
+#ifndef MGA_CL_K_B16
+#define MGA_CL_K_B16 3  // 16-bit backward: 8-element units double the per-slot T partials; 3 units keep 2 CTAs per SM (shared memory)
+#endif
+constexpr int kClKF = MGA_CL_K_F, kClKB = MGA_CL_K_B, kClKB16 = MGA_CL_K_B16;  // T1: units per thread and channel
 
 #ifndef MGA_CL_HINTS
 #define MGA_CL_HINTS 1  // L2 eviction-priority hints: first touch of x/g = keep, last read = evict first
@@ -75,6 +78,7 @@ struct ClGeom {
     int nPmax;     // pixels per CTA
     int G;         // T2: channel groups = NT / nUmax
     int CG;        // T2: channels per group, rounded up to a multiple of 8 (group-major constant arrays)
+    int K;         // T1: units per thread and channel of this launch
     int LPT;       // T1: threads per channel slot = ceil(nUmax / K)
     int slots;     // T1: channel slots = NT / LPT
     int tileRows;  // rowsPer + 6
@@ -100,7 +104,7 @@ __host__ __device__ inline ClFwdOff cl_fwd_off(int C, int Hd, const ClGeom& g) {
     o.q = take(g.G * g.CG);         // group-major q
     o.part = take(4 * C * g.CS);    // pool partials of every rank (pushed)
     o.msum = take(16);
-    o.mloc = take(g.LPT * kClKF * 8);  // m of the own pixels, zero padded to the T1 footprint
+    o.mloc = take(g.LPT * g.K * 8);  // m of the own pixels, zero padded to the T1 footprint
     // the T1 per-thread partials [4][C][LPT|1] of the pooling phase are dead before the planes exist: same storage
     o.stage = p;
     o.aloc = take(g.nPmax);
@@ -132,7 +136,7 @@ __host__ __device__ inline ClBwdOff cl_bwd_off(int C, int Hd, const ClGeom& g) {
     o.q = take(C);
     o.epart = take(C * g.CS); o.qpart = take(C * g.CS); o.binpart = take(C * g.CS);
     o.gxpart = take(2 * 16);  // doubles
-    const int padP = g.LPT * kClKB * 8;  // T1 footprint in pixels (>= nPmax), zero padded
+    const int padP = g.LPT * g.K * 8;  // T1 footprint in pixels (>= nPmax), zero padded
     o.aloc = take(g.nPmax); o.ae = take(padP); o.mloc = take(g.nPmax); o.idx = take(g.nPmax); o.pmx = take(g.nPmax);
     o.d0 = take(g.nPmax); o.d1s = take(padP); o.d2 = take(g.nPmax);
     o.dpre = take(g.planeT);
@@ -756,7 +760,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
                                                                   int mdt, T* __restrict__ dx, void* __restrict__ dmask, Shape sh,
                                                                   mga_cbam_params prm, Ctx ctx, BwdScratch bs, ClGeom gm) {
     constexpr int VEC = 16 / sizeof(T);
-    constexpr int K = kClKB;
+    constexpr int K = (VEC == 4) ? kClKB : kClKB16;
     constexpr int NT = kClNTB, NW = NT / 32;
     constexpr int kGrp = NT / 3;  // conv: threads per input plane
     constexpr int kStride = 3 * kMaxK * kMaxK + 1;

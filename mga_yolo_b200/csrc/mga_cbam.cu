@@ -359,7 +359,8 @@ static bool cl_geometry(const Shape& sh, int esize, bool bwd, ClGeom* out) {
         g.nPmax = nP;
         g.G = std::max(1, std::min(NT / nU, sh.C));
         g.CG = (((sh.C + g.G - 1) / g.G) + 7) & ~7;
-        const int K = bwd ? kClKB : kClKF;
+        const int K = bwd ? (esize == 4 ? kClKB : kClKB16) : kClKF;
+        g.K = K;
         g.LPT = (nU + K - 1) / K;
         g.slots = NT / g.LPT;
         g.tileRows = rowsPer + kMaxK - 1;
