@@ -85,11 +85,13 @@ struct ClGeom {
     int TWp;       // W + 8
     int planeT;    // floats per tile plane (multiple of 32)
     int smem_bytes;
+    int stage_w;   // 1: the cam_mlp weight matrices are staged in shared memory (decided on the host: only when the second resident CTA per SM survives)
     int prefetch;  // 1: bulk L2 prefetch of the sample at kernel start, so the HBM stream overlaps the latency-bound prologue
 };
 
-// the two weight matrices of the shared MLP are staged in shared memory when they are small (always for YOLO necks up to C = 512, r = 16)
-__host__ __device__ inline bool cl_mlp_in_smem(int C, int Hd) { return (C * Hd) % 4 == 0 && 2 * C * Hd * 4 <= 40 * 1024; }
+// the two weight matrices of the shared MLP may be staged in shared memory (16-byte cp.async copies) when they are small
+__host__ __device__ inline bool cl_mlp_in_smem(int C, int Hd) { return (C * Hd) % 4 == 0 && 2 * C * Hd * 4 <= 16 * 1024; }
+constexpr int kClTwoCtaSmem = 114 * 1024;  // dynamic shared memory per CTA up to which two CTAs fit one SM (228 KB, 1 KB reserved each)
 
 // ---------------------------------------------------------------- shared-memory layouts (float offsets)
 struct ClFwdOff { int wk, red, avg, mx, ha, hm, sAB, q, part, msum, mloc, aloc, tile, mg, stage, mlpw, total; };
@@ -112,7 +114,7 @@ __host__ __device__ inline ClFwdOff cl_fwd_off(int C, int Hd, const ClGeom& g) {
     o.mg = take(3 * g.G * g.nPmax);  // T2 merge buffers [max | sum | idx][G][nPmax]; later the conv's per-plane partials [3][nPmax]
     const int stage_end = o.stage + ((4 * C * (g.LPT | 1) + 3) & ~3);
     if (p < stage_end) p = stage_end;
-    o.mlpw = cl_mlp_in_smem(C, Hd) ? take(2 * C * Hd) : -1;  // cam_mlp weights [W1 (Hd,C) | W2 (C,Hd)], staged with cp.async at kernel start
+    o.mlpw = g.stage_w ? take(2 * C * Hd) : -1;  // cam_mlp weights [W1 (Hd,C) | W2 (C,Hd)], staged with cp.async at kernel start
     o.total = p;
     return o;
 }
@@ -147,7 +149,7 @@ __host__ __device__ inline ClBwdOff cl_bwd_off(int C, int Hd, const ClGeom& g) {
     o.dwp = o.tp;
     o.binw = take((g.NT / 32) * C);
     o.stage = take(C * (g.LPT | 1));
-    o.mlpw = (cl_mlp_in_smem(C, Hd) && 2 * C * Hd * 4 <= 4096) ? take(2 * C * Hd) : -1;  // cam_mlp weights [W1 | W2] staged with cp.async (small ones only)
+    o.mlpw = g.stage_w ? take(2 * C * Hd) : -1;  // cam_mlp weights [W1 | W2] staged with cp.async
     o.total = p;
     return o;
 }

@@ -366,7 +366,12 @@ static bool cl_geometry(const Shape& sh, int esize, bool bwd, ClGeom* out) {
         g.tileRows = rowsPer + kMaxK - 1;
         g.TWp = sh.W + 8;
         g.planeT = (g.tileRows * g.TWp + 31) & ~31;
+        g.stage_w = 0;
         g.smem_bytes = 4 * (bwd ? cl_bwd_off(sh.C, sh.hidden, g).total : cl_fwd_off(sh.C, sh.hidden, g).total);
+        if (cl_mlp_in_smem(sh.C, sh.hidden) && g.smem_bytes + 8 * sh.C * sh.hidden <= kClTwoCtaSmem) {  // staging must not cost the 2nd CTA per SM
+            g.stage_w = 1;
+            g.smem_bytes = 4 * (bwd ? cl_bwd_off(sh.C, sh.hidden, g).total : cl_fwd_off(sh.C, sh.hidden, g).total);
+        }
         g.prefetch = bwd ? pf_b : pf_f;
         static const int min_smem_f = env_int("MGA_CL_MINSMEM_F", 0), min_smem_b = env_int("MGA_CL_MINSMEM_B", 0);  // tuning: caps the CTAs per SM
         g.smem_bytes = std::max(g.smem_bytes, bwd ? min_smem_b : min_smem_f);
