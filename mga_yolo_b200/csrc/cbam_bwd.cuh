@@ -238,6 +238,34 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce2_kernel(cons
     }
 }
 
+// ------------------------------------------------------------------ B3' (large planes): sum the per-tile partial rows
+// grid (ceil(C/32), B): lanes = 32 consecutive channels (coalesced rows of the (B,nT,C) partial arrays), the 8 warps split the
+// tiles, their sums meet in shared memory and are added in warp order (deterministic).  Output psum (3,B,C) = [e | gx | q].
+__global__ void __launch_bounds__(kBlock) bwd_partsum_kernel(Shape sh, BwdScratch bs, int nT, int nT2) {
+    __shared__ float part[3][kWarpsPerBlock][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane, b = blockIdx.y, C = sh.C;
+    float e = 0.0f, gx = 0.0f, q = 0.0f;
+    if (c < C) {
+#pragma unroll 4
+        for (int t = w; t < nT; t += kWarpsPerBlock) {
+            const size_t o = ((size_t)b * nT + t) * C + c;
+            e += __ldg(bs.epart + o);
+            gx += __ldg(bs.gxpart + o);
+        }
+#pragma unroll 4
+        for (int t = w; t < nT2; t += kWarpsPerBlock) q += __ldg(bs.qpart + ((size_t)b * nT2 + t) * C + c);
+    }
+    part[0][w][lane] = e; part[1][w][lane] = gx; part[2][w][lane] = q;
+    __syncthreads();
+    if (w < 3 && c < C) {
+        float t = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kWarpsPerBlock; ++j) t += part[w][j][lane];
+        bs.psum[(size_t)w * sh.B * C + (size_t)b * C + c] = t;
+    }
+}
+
 // ------------------------------------------------------------------ B4 (one CTA per sample)
 __global__ void __launch_bounds__(kBlock) bwd_mlp_kernel(Shape sh, mga_cbam_params prm, Ctx ctx, BwdScratch bs, int nT, int nT2) {
     extern __shared__ float smem[];

@@ -344,6 +344,7 @@ struct BwdScratch {
     float* epart;    // (B,nT,C) partial sum_p g*x*(a or 1)
     float* gxpart;   // (B,nT,C) partial sum_p g*x
     float* qpart;    // (B,nT,C) partial sum_p x*dy1            (multiply mode)
+    float* psum;     // (3,B,C) the three partial arrays summed over their tiles (large planes: bwd_partsum_kernel)
     float* cA;       // (B,C) use*davg/den
     float* cG;       // (B,C) ((1-use)*davg + dead*dmx)/S
     float* cM;       // (B,C) (1-dead)*dmx

@@ -173,6 +173,7 @@ static size_t carve_bwd(const Shape& s, void* base, BwdScratch* b) {
     b->epart = k.take<float>((size_t)s.B * nT * s.C);
     b->gxpart = k.take<float>((size_t)s.B * nT * s.C);
     b->qpart = k.take<float>((size_t)s.B * nT * s.C);
+    b->psum = k.take<float>(3 * BC);
     b->cA = k.take<float>(BC);
     b->cG = k.take<float>(BC);
     b->cM = k.take<float>(BC);
@@ -614,7 +615,18 @@ static int backward_split(const Shape& sh, const T* x, const void* mask, int mas
 #undef MGA_CALL
     }
     const size_t mlp_smem = ((size_t)sh.C + 2 * sh.hidden + 3 * kBlock) * sizeof(float);
-    MGA_LAUNCH("bwd_mlp", st, bwd_mlp_kernel<<<sh.B, kBlock, mlp_smem, st>>>(sh, p, ctx, bs, nT, nT2));
+    if (!gates && std::max(nT, nT2) > 8) {
+        // large planes: many per-tile partial rows per channel -- sum them with a grid of their own first (one CTA per 32 channels and
+        // sample) instead of inside the one-CTA-per-sample MLP kernel
+        const dim3 gsum((sh.C + 31) / 32, sh.B);
+        MGA_LAUNCH("bwd_partsum", st, bwd_partsum_kernel<<<gsum, kBlock, 0, st>>>(sh, bs, nT, sh.samcam_add() ? 0 : nT2));
+        BwdScratch b2 = bs;
+        const size_t BC = (size_t)sh.B * sh.C;
+        b2.epart = bs.psum; b2.gxpart = bs.psum + BC; b2.qpart = bs.psum + 2 * BC;
+        MGA_LAUNCH("bwd_mlp", st, bwd_mlp_kernel<<<sh.B, kBlock, mlp_smem, st>>>(sh, p, ctx, b2, 1, 1));
+    } else {
+        MGA_LAUNCH("bwd_mlp", st, bwd_mlp_kernel<<<sh.B, kBlock, mlp_smem, st>>>(sh, p, ctx, bs, nT, nT2));
+    }
 #define MGA_CALL(L, P) MGA_LAUNCH("bwd_dx", st, (bwd_dx_kernel<T, VEC, L><<<gtile, kBlock, 0, st>>>(x, g, mask, mask_dtype, dx, dmask, sh, ctx, bs)))
     MGA_TILE_DISPATCH(tc1, MGA_CALL);
 #undef MGA_CALL
