@@ -13,6 +13,6 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 P
 }
-for L in libmga_cbam.so libmga_f448.so libmga_f384.so; do
+for L in libmga_cbam.so libmga_k7n512.so libmga_k7n448.so libmga_k8n384.so; do
 run $L $L
 done
