@@ -903,7 +903,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
 
     // ---- phase 1 (T1) over (x,g): T_p = sum_c g x q_c (per pixel), E_c = sum_p g x (a | 1) (per channel), sum g x
     stamp(1);
-    float gxs = 0.0f;
+    double gxs = 0.0;  // sum g x over everything this thread touches: it enters d beta, which cancels heavily -> fp64 across channels
     {
         float tacc[K][VEC];
 #pragma unroll
@@ -923,7 +923,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
                         }
                 }
                 const float q = s_q[c];
-                float e = 0.0f;
+                float e = 0.0f, gxc = 0.0f;  // (sum g x: per channel first, then across channels -- two short fp32 chains instead of one long one)
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     if (k < nk) {
@@ -936,10 +936,11 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
                             const float gx = gv[i] * xv[i];
                             tacc[k][i] = fmaf(gx, q, tacc[k][i]);
                             e = fmaf(gx, av[i], e);
-                            gxs += gx;
+                            gxc += gx;
                         }
                     }
                 }
+                gxs += (double)gxc;
                 stage[c * LPTp + ul] = e;
             }
             // per-pixel partials of this channel slot
@@ -1081,7 +1082,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
         }
         bin_loc[c] = t;
     }
-    const double gx_cta = block_sum_d((double)gxs, redd);  // (barriers inside)
+    const double gx_cta = block_sum_d(gxs, redd);  // (barriers inside)
     for (int i = tid; i < C * CS; i += NT) {
         const int rr = i / C, c = i - rr * C;
         cluster.map_shared_rank(epart, rr)[r * C + c] = e_loc[c];

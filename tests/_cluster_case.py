@@ -40,7 +40,12 @@ def main():
     grads = {n: q.grad.detach().cpu() for n, q in mod.named_parameters()}
     for k in PARAM_KEYS:
         errs["d." + k] = rel_err(grads[k], ref[k])
-    bad = {k: v for k, v in errs.items() if v > (ptol if k.startswith("d.") and k not in ("dx", "dmask") else tol)}
+    # parameter gradients are long cancelling fp32 sums (d beta sums all N elements): same tie-breaker as test_gpu_cbam.py -- when the
+    # fp32 ORACLE itself is further than the gate from fp64, the kernel may be up to 4x the fp32 oracle's own error away
+    _, sv32 = co.cbam_forward(x.float(), mask, p, sam_cam_fusion=scf, mga_pyramid_fusion=pyr, feature_dtype=dtype)
+    ref32 = co.cbam_backward(g.float(), p, sv32)
+    slack = {"d." + k: 4.0 * rel_err(ref32[k], ref[k]) for k in PARAM_KEYS}
+    bad = {k: v for k, v in errs.items() if v > (max(ptol, slack[k]) if k in slack else tol)}
     print("ERRS", {k: float(f"{v:.3g}") for k, v in errs.items()})
     if bad:
         print("FAIL", bad)
