@@ -37,7 +37,9 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce1_kernel(cons
     // channels are taken KB at a time: all loads of a batch are issued before anything consumes them
     constexpr int KB0 = VEC == 8 ? MGA_KB2 / 2 : MGA_KB2;
     constexpr int KB = KB0 / UPT > 0 ? KB0 / UPT : 1;
-    for (int c0 = tm.chan0(); c0 < C; c0 += TM_::kChanStep * KB) {
+    // (warp-uniform bound: the shuffles inside need every lane, also when C is not a multiple of the channels per warp load)
+    for (int cw = tm.w * TM_::CPW; cw < C; cw += TM_::kChanStep * KB) {
+        const int c0 = cw + tm.sub;
         float xv[KB][UPT][VEC], gv[KB][UPT][VEC], e[KB], gxs[KB];
 #pragma unroll
         for (int kc = 0; kc < KB; ++kc) {
@@ -202,7 +204,9 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce2_kernel(cons
     const size_t base = ((size_t)b * C) * sh.S;
     constexpr int KB0 = VEC == 8 ? MGA_KB1 / 2 : MGA_KB1;
     constexpr int KB = KB0 / UPT > 0 ? KB0 / UPT : 1;
-    for (int c0 = tm.chan0(); c0 < C; c0 += TM_::kChanStep * KB) {
+    // (warp-uniform bound: the shuffles inside need every lane, also when C is not a multiple of the channels per warp load)
+    for (int cw = tm.w * TM_::CPW; cw < C; cw += TM_::kChanStep * KB) {
+        const int c0 = cw + tm.sub;
         float xv[KB][UPT][VEC], qv[KB];
 #pragma unroll
         for (int kc = 0; kc < KB; ++kc) {
