@@ -30,13 +30,24 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[1]}x{c[2]}x{c[3]}-{c[4]}-cs{c[7]}/{c[8]}")
+# the other input modes of the block on multi-CTA clusters: no mask (vanilla CBAM, masked_cbam.py:90-91,107-108,137-138), a raw
+# {0,1} mask with use_sigmoid_mask=False, a mask that needs no gradient (ground-truth masks)
+CASES += [
+    (2, 48, 24, 24, "float32", "multiply", "add", 4, 4, "nomask"),
+    (2, 48, 24, 24, "float32", "multiply", "add", 4, 4, "rawmask"),
+    (2, 48, 24, 24, "float32", "add", "add", 4, 2, "nograd_mask"),
+    (2, 64, 40, 40, "bfloat16", "multiply", "add", 2, 2, "rawmask"),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[1]}x{c[2]}x{c[3]}-{c[4]}-cs{c[7]}/{c[8]}" + (f"-{c[9]}" if len(c) > 9 else ""))
 def test_forced_cluster_sizes_match_oracle(case):
-    B, C, H, W, dt, scf, pyr, csf, csb = case
+    B, C, H, W, dt, scf, pyr, csf, csb = case[:9]
+    variant = case[9] if len(case) > 9 else "default"
     env = dict(os.environ, MGA_CL_CS_F=str(csf), MGA_CL_CS_B=str(csb), MGA_CL_DEBUG="1", PYTHONPATH=str(ROOT))
     for k in ("MGA_FORCE_SPLIT", "MGA_USE_FUSED", "MGA_USE_FLOW", "MGA_CL"):
         env.pop(k, None)
-    r = subprocess.run([sys.executable, "-m", "tests._cluster_case", str(B), str(C), str(H), str(W), dt, scf, pyr], cwd=ROOT, env=env,
+    r = subprocess.run([sys.executable, "-m", "tests._cluster_case", str(B), str(C), str(H), str(W), dt, scf, pyr, variant], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     if csf and csb:  # forced sizes must really have gone through the cluster kernels (default geometry may pick the per-phase path)
