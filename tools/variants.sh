@@ -13,6 +13,9 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 P
 }
-for L in libmga_cbam.so libmga_k7n512.so libmga_k7n448.so libmga_k8n384.so; do
-run $L $L
-done
+# ---- edit below: one `run <name> <library> [ENV=value ...]` line per variant (BENCH_ARGS adds bench.py flags)
+L=libmga_cbam.so
+run default $L
+run per_phase $L MGA_CL=0
+BENCH_ARGS=--one-stream run default_one_stream $L
+BENCH_ARGS=--one-stream run per_phase_one_stream $L MGA_CL=0
