@@ -408,13 +408,19 @@ static int launch_cl(const char* name, Kern kernel, const ClGeom& gm, int nClust
     cfg.blockDim = dim3((unsigned)gm.NT);
     cfg.dynamicSmemBytes = (size_t)gm.smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)gm.CS;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    static const int policy = env_int("MGA_CL_POLICY", 0);  // tuning: 1 = spread, 2 = load balancing (default: the driver's choice)
+    if (policy == 1 || policy == 2) {
+        attr[1].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
+        attr[1].val.clusterSchedulingPolicyPreference = policy == 1 ? cudaClusterSchedulingPolicySpread : cudaClusterSchedulingPolicyLoadBalancing;
+        cfg.numAttrs = 2;
+    }
     cudaError_t e;
     {
         // can at least one cluster of this size / shared-memory footprint be resident?  (cached; 0 -> the caller takes the per-phase path)
