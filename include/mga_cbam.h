@@ -96,6 +96,19 @@ int mga_profile_enable(int on);
 int mga_profile_count(void);
 int mga_profile_read(int index, const char** name, float* ms);
 
+/* Which launch path mga_cbam_forward (direction 0) / mga_cbam_backward (direction 1) takes for this descriptor, and its geometry.
+ * Host-only (no CUDA call): the choice depends on the per-sample shape and element type, never on B.  The device may still
+ * send a cluster launch to the per-phase path when no cluster of that shape can be resident (not the case on B200). */
+typedef struct mga_cbam_plan_info {
+    int32_t path;          /* 0 = one kernel per phase, 1 = one thread-block cluster per sample */
+    int32_t cluster_size;  /* CTAs per sample (path 1) */
+    int32_t rows_per_cta;  /* image rows per CTA (path 1) */
+    int32_t threads;       /* threads per CTA (path 1) */
+    int32_t smem_bytes;    /* dynamic shared memory per CTA (path 1) */
+    int32_t launches;      /* kernel launches of the call */
+} mga_cbam_plan_info;
+int mga_cbam_plan(const mga_cbam_desc* d, int direction, mga_cbam_plan_info* info);
+
 /* bytes of the saved-for-backward context and of the transient scratch for this shape */
 int mga_cbam_workspace(const mga_cbam_desc* d, size_t* ctx_bytes, size_t* scratch_bytes);
 

@@ -698,6 +698,34 @@ int mga_profile_read(int i, const char** name, float* ms) {
     return MGA_OK;
 }
 
+int mga_cbam_plan(const mga_cbam_desc* d, int direction, mga_cbam_plan_info* info) {
+    Shape sh;
+    if (int rc = validate(d, &sh)) return rc;
+    if (!info || (direction != 0 && direction != 1)) return fail(MGA_ERR_ARG, "mga_cbam_plan: bad argument");
+    const int esize = d->dtype == MGA_F32 ? 4 : 2;
+    const bool bwd = direction == 1;
+    ClGeom g{};
+    std::memset(info, 0, sizeof(*info));
+    const bool vec_ok = sh.S % (16 / esize) == 0;  // (pointer alignment is checked at call time)
+    if (vec_ok && !(d->flags & (MGA_FORCE_SPLIT | MGA_USE_FUSED | MGA_USE_FLOW)) && cl_geometry(sh, esize, bwd, &g)) {
+        info->path = 1;
+        info->cluster_size = g.CS;
+        info->rows_per_cta = g.rowsPer;
+        info->threads = g.NT;
+        info->smem_bytes = g.smem_bytes;
+        info->launches = bwd ? 2 : 1;
+        return MGA_OK;
+    }
+    info->path = 0;
+    {
+        const int vec = vec_ok ? 16 / esize : 1, U = sh.S / vec;
+        const TileCfg tc = pick_tiles(sh, U, vec);
+        const bool partsum = (U + tc.lpt - 1) / tc.lpt > 8;  // bwd_partsum_kernel (large planes)
+        info->launches = bwd ? 5 + (sh.samcam_add() ? 0 : 1) + (partsum ? 1 : 0) : 5 + (sh.has_mask() ? 1 : 0);
+    }
+    return MGA_OK;
+}
+
 int mga_cbam_workspace(const mga_cbam_desc* d, size_t* ctx_bytes, size_t* scratch_bytes) {
     Shape sh;
     if (int rc = validate(d, &sh)) return rc;

@@ -301,6 +301,19 @@ def mask_guided_cbam(x: torch.Tensor, mask: Optional[torch.Tensor], w1, b1, w2, 
     return _CbamFn.apply(x, mask, w1, b1, w2, b2, wsam, beta, int(flags), float(tiny_mask_thr), float(eps))
 
 
+def plan(x_shape: Tuple[int, int, int, int], dtype=torch.float32, *, r: int = 16, k: int = 7, flags: int = 0, backward: bool = False) -> dict:
+    """Which launch path (and cluster geometry) the library takes for a feature map of this shape: host-only, no GPU needed.
+    {'path': 'cluster' | 'per_phase', 'cluster_size', 'rows_per_cta', 'threads', 'smem_bytes', 'launches'}."""
+    lib = _lib.load()
+    B, Cc, H, W = x_shape
+    d = _lib.Desc(B, Cc, H, W, max(1, Cc // r), k, _DT[dtype], _lib.F32, int(flags) | _lib.HAS_MASK | _lib.SIGMOID_MASK, 1e-4, 1e-6)
+    info = _lib.PlanInfo()
+    _lib.check(lib.mga_cbam_plan(C.byref(d), 1 if backward else 0, C.byref(info)), "mga_cbam_plan")
+    out = {n: int(getattr(info, n)) for n, _ in _lib.PlanInfo._fields_}
+    out["path"] = "cluster" if info.path == 1 else "per_phase"
+    return out
+
+
 def ctx_view(x_shape: Tuple[int, int, int, int], dtype, hidden: int, k: int, flags: int, ctx: torch.Tensor, which: int,
              tiny=1e-4, eps=1e-6, mask_dtype=torch.float32) -> torch.Tensor:
     """Copy a small saved quantity out of a forward context (tests / logging): 0 s(B,C), 1 a(B,HW)."""

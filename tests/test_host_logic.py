@@ -220,3 +220,34 @@ def test_shard_range_partitions_batch():
         parts = [list(shard_range(n, r, w)) for r in range(w)]
         assert sum(parts, []) == list(range(n))
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_launch_plan_is_a_function_of_the_sample_shape_only():
+    """mga_cbam_plan (host-only): which launch path / cluster geometry a shape gets.  The YOLOv8n levels of BASELINE configs[1] run
+    one cluster per sample with 8 / 4 / 2 CTAs (10 image rows each) and shared memory that lets two CTAs share an SM; samples too
+    large to stay L2-resident, ragged planes and widths that are not multiples of 4 take the per-phase kernels; the batch size
+    never matters (a sample must give the same bits alone or inside any batch)."""
+    import torch
+
+    from mga_yolo_b200 import _lib, ops
+
+    for (C, H, W), cs in (((64, 80, 80), 8), ((128, 40, 40), 4), ((256, 20, 20), 2)):
+        for bwd in (False, True):
+            p = ops.plan((64, C, H, W), torch.float32, backward=bwd)
+            assert p["path"] == "cluster" and p["cluster_size"] == cs and p["rows_per_cta"] == 10, (C, bwd, p)
+            assert p["smem_bytes"] <= 114 * 1024 and p["threads"] == (256 if bwd else 512)
+            assert p["launches"] == (2 if bwd else 1)
+            assert ops.plan((1, C, H, W), torch.float32, backward=bwd) == ops.plan((256, C, H, W), torch.float32, backward=bwd) == p
+    # YOLOv8s bf16 (BASELINE configs[2]): same slices in bytes, two CTAs per SM in both directions
+    for (C, H, W) in ((128, 80, 80), (256, 40, 40), (512, 20, 20)):
+        for bwd in (False, True):
+            p = ops.plan((256, C, H, W), torch.bfloat16, backward=bwd)
+            assert p["path"] == "cluster" and p["smem_bytes"] <= 114 * 1024, (C, bwd, p)
+    # YOLOv8x at 1280 (BASELINE configs[4]): 19.7 MB / 9.8 MB samples are not L2-resident -> per-phase; P5 (2.4 MB) -> cluster
+    assert ops.plan((8, 384, 160, 160), torch.bfloat16)["path"] == "per_phase"
+    assert ops.plan((8, 768, 80, 80), torch.bfloat16, backward=True)["path"] == "per_phase"
+    assert ops.plan((8, 768, 40, 40), torch.bfloat16)["path"] == "cluster"
+    assert ops.plan((2, 96, 17, 13))["path"] == "per_phase"       # H*W = 221: not a whole number of 16-byte units
+    assert ops.plan((2, 64, 10, 10))["path"] == "per_phase"       # W % 4 != 0
+    assert ops.plan((2, 64, 80, 80), flags=_lib.FORCE_SPLIT)["path"] == "per_phase"
+    assert ops.plan((2, 64, 80, 80), flags=_lib.FORCE_SPLIT, backward=True)["launches"] == 7  # 5 + reduce2 + partial sums
