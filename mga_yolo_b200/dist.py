@@ -34,16 +34,31 @@ class FlatGradReducer:
         self.average = average
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self._bind(copy=False)
+
+    def _bind(self, copy: bool) -> None:
+        """Make every .grad a view into the flat buffer.  `optimizer.zero_grad()` / `Module.zero_grad()` default to
+        set_to_none=True and the next backward then allocates fresh .grad tensors OUTSIDE the buffer: those are copied in
+        and re-bound here, so the collective never reduces a stale buffer."""
         o = 0
         for p in self.params:
             n = p.numel()
-            p.grad = self.flat[o:o + n].view_as(p)
+            view = self.flat[o:o + n].view_as(p)
+            g = p.grad
+            if g is None:
+                if copy:
+                    view.zero_()  # no gradient this step: contributes zero
+                p.grad = view
+            elif g.data_ptr() != view.data_ptr() or g.dtype != torch.float32:
+                view.copy_(g)
+                p.grad = view
             o += n
 
     def zero(self) -> None:
         self.flat.zero_()
 
     def all_reduce(self, async_op: bool = False):
+        self._bind(copy=True)
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return None
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)

@@ -32,40 +32,96 @@ from .module import MaskGuidedCBAM
 MaskArg = Union[None, torch.Tensor, Sequence[Optional[torch.Tensor]], Dict[str, Optional[torch.Tensor]]]
 
 
+class _MaskState:
+    """The per-batch masks.  ONE state object is shared by every deep copy of the slot that owns it, so masks set through
+    the manager also reach ModelEMA's copy (ultralytics/utils/torch_utils.py:752) and any validation / checkpoint copy."""
+
+    __slots__ = ("full", "per_level", "by_stride", "keep", "fired")
+
+    def __init__(self):
+        self.full: Optional[torch.Tensor] = None  # (B,H,W) uint8 image-resolution mask
+        self.per_level: Dict[str, Optional[torch.Tensor]] = {}
+        self.by_stride: Dict[int, torch.Tensor] = {}
+        self.keep = False   # True: masks survive the forward that used them (set_masks(..., persistent=True))
+        self.fired = 0      # hooked levels served since the last set_masks
+
+    def clear(self) -> None:
+        self.full, self.per_level, self.by_stride, self.fired = None, {}, {}, 0
+
+
 class _MaskSlot(nn.Module):
     """Per-batch mask holder living inside the model tree (no parameters, nothing in state_dict)."""
 
-    def __init__(self, levels: Sequence[str], resize: str):
+    def __init__(self, levels: Sequence[str], resize: str, state: Optional[_MaskState] = None):
         super().__init__()
         self.levels = tuple(levels)
         self.resize = resize
-        self.full: Optional[torch.Tensor] = None          # (B,H,W) uint8 image-resolution mask
-        self.per_level: Dict[str, Optional[torch.Tensor]] = {}
+        self.state = state if state is not None else _MaskState()
+
+    # kept for callers that poke the slot directly
+    @property
+    def full(self):
+        return self.state.full
+
+    @property
+    def per_level(self):
+        return self.state.per_level
 
     def clear(self) -> None:
-        self.full, self.per_level = None, {}
+        self.state.clear()
+
+    def _downsampled(self, stride: int) -> torch.Tensor:
+        st = self.state
+        if stride in st.by_stride:
+            return st.by_stride[stride]
+        code = {"nearest": 0, "area": 1, "maxpool": 2}[self.resize]
+        full = st.full
+        from . import ops
+        if stride in (8, 16, 32) and ops.masks_multi_supported(*full.shape[-2:]):
+            # one kernel reads every mask once and emits the three pyramid strides (dataset.py:95-103 as a batch op)
+            outs = torch.ops.mga.masks_multi(full, code, 0.0, False, True)
+            for s_, o in zip((8, 16, 32), outs):
+                st.by_stride[s_] = o.unsqueeze(1)
+        else:
+            st.by_stride[stride] = torch.ops.mga.mask_downsample(full, stride, code, 0.0, False, True).unsqueeze(1)
+        return st.by_stride[stride]
 
     def mask_for(self, level: str, feat: torch.Tensor) -> Optional[torch.Tensor]:
-        if level in self.per_level:
-            return self.per_level[level]
-        if self.full is None:
-            return None
-        H, W = feat.shape[-2:]
-        stride = max(1, round(self.full.shape[-2] / H))
-        code = {"nearest": 0, "area": 1, "maxpool": 2}[self.resize]
-        m = torch.ops.mga.mask_downsample(self.full, stride, code, 0.0, False, True)  # (B,h,w) float {0,1}
-        if tuple(m.shape[-2:]) != (H, W):
-            raise RuntimeError(f"mask of size {tuple(self.full.shape[-2:])} does not reduce to feature size {(H, W)} at stride {stride}")
-        self.per_level[level] = m.unsqueeze(1)
-        return self.per_level[level]
+        st = self.state
+        try:
+            if level in st.per_level:
+                m = st.per_level[level]
+                if m is not None and (m.shape[0] != feat.shape[0] or tuple(m.shape[-2:]) != tuple(feat.shape[-2:])):
+                    raise RuntimeError(f"stale or mismatched mask for level {level}: mask {tuple(m.shape)} vs feature {tuple(feat.shape)}; "
+                                       "call set_masks() for every batch")
+                return m
+            if st.full is None:
+                return None
+            H, W = feat.shape[-2:]
+            fH, fW = st.full.shape[-2:]
+            if st.full.shape[0] != feat.shape[0]:
+                raise RuntimeError(f"stale masks: batch {st.full.shape[0]} was set, the model runs batch {feat.shape[0]}; call set_masks() per batch")
+            stride = -(-fH // H)  # the reference's sizes are ceil(H / s) (mask_utils.py:84-85)
+            if stride < 1 or -(-fH // stride) != H or -(-fW // stride) != W:
+                raise RuntimeError(f"mask of size {(fH, fW)} does not reduce to feature size {(H, W)} by an integer stride")
+            return self._downsampled(stride)
+        finally:
+            st.fired += 1
+            if st.fired >= len(self.levels) and not st.keep:
+                st.clear()  # consumed: a forward without a fresh set_masks() runs mask-free instead of re-using old masks
 
-    def __deepcopy__(self, memo):  # masks are transient: copies start empty
-        return _MaskSlot(self.levels, self.resize)
+    def __deepcopy__(self, memo):  # copies share the live state (masks are transient and never part of a checkpoint)
+        return _MaskSlot(self.levels, self.resize, self.state)
 
     def __getstate__(self):
         st = dict(self.__dict__)
-        st["full"], st["per_level"] = None, {}
+        st["state"] = None
         return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        if self.__dict__.get("state") is None:
+            self.__dict__["state"] = _MaskState()
 
 
 class _OutputHook:
@@ -224,23 +280,41 @@ class MGAHookManager:
         return bool(self._handles)
 
     # -- per-batch masks ---------------------------------------------------------------
-    def set_masks(self, masks: MaskArg) -> None:
-        self.slot.clear()
+    def set_masks(self, masks: MaskArg, *, model: Optional[nn.Module] = None, persistent: bool = False) -> None:
+        """Masks of the NEXT forward.  They are consumed by that forward (every hooked level served once) unless
+        `persistent=True`.  `model=` addresses the slot of another model object (e.g. one rebuilt from a checkpoint);
+        deep copies of the managed model (ModelEMA) share the manager's own slot state and need nothing."""
+        slot = self.slot if model is None else self.slot_of(model)
+        st = slot.state
+        st.clear()
+        st.keep = bool(persistent)
         if masks is None:
             return
         if isinstance(masks, torch.Tensor):
             m = masks
             if m.dim() == 4:
                 m = m[:, 0]
-            self.slot.full = (m > 0).to(torch.uint8).contiguous()
+            st.full = (m > 0).to(torch.uint8).contiguous()
             return
         if isinstance(masks, dict):
-            self.slot.per_level = {str(k): v for k, v in masks.items()}
+            st.per_level = {str(k): v for k, v in masks.items()}
             return
         masks = list(masks)
         if len(masks) != len(self.levels):
             raise ValueError(f"expected {len(self.levels)} per-level masks, got {len(masks)}")
-        self.slot.per_level = dict(zip(self.levels, masks))
+        st.per_level = dict(zip(self.levels, masks))
+
+    @classmethod
+    def slot_of(cls, model: nn.Module) -> _MaskSlot:
+        inner = model
+        for _ in range(4):
+            slot = getattr(inner, cls.ATTR + "_masks", None)
+            if isinstance(slot, _MaskSlot):
+                return slot
+            inner = getattr(inner, "model", None)
+            if inner is None:
+                break
+        raise AttributeError("model carries no MGA mask slot (was MGAHookManager constructed on it?)")
 
     def alphas(self) -> Dict[str, float]:
         return {lvl: float(self.blocks[lvl].alpha.detach()) for lvl in self.levels}

@@ -11,7 +11,9 @@ from __future__ import annotations
 import sys
 from typing import Dict, Tuple
 
-from .module import MaskCBAM
+import functools
+
+from .module import MaskCBAM, shape_probe
 
 _TARGETS = (
     "mga_yolo.nn.modules.masked_cbam",
@@ -23,8 +25,33 @@ _TARGETS = (
 _saved: Dict[Tuple[str, str], object] = {}
 
 
+def _wrap_builder(cls) -> None:
+    """DetectionModel.__init__ runs a CPU forward of zeros to read the output strides (ultralytics/nn/tasks.py:418-426)
+    before the model can be on a GPU: run it inside shape_probe(), where the block answers with shapes only."""
+    init = cls.__dict__.get("__init__")
+    if init is None or getattr(init, "_mga_shape_probe", False):
+        return
+
+    @functools.wraps(init)
+    def __init__(self, *args, **kwargs):
+        with shape_probe():
+            return init(self, *args, **kwargs)
+
+    __init__._mga_shape_probe = True
+    __init__._mga_original = init
+    cls.__init__ = __init__
+
+
+def _unwrap_builder(cls) -> None:
+    init = cls.__dict__.get("__init__")
+    if init is not None and getattr(init, "_mga_shape_probe", False):
+        cls.__init__ = init._mga_original
+
+
 def install(strict: bool = False) -> list:
-    """Patch every already-imported module that exposes `MaskCBAM`; returns the patched module names."""
+    """Patch every already-imported module that exposes `MaskCBAM`; returns the patched module names.
+    The graph builder's `DetectionModel.__init__` (the base of MGAModel, mga_yolo/model/model.py:40) is wrapped so that
+    its CPU stride probe passes through the block as a shape-only call."""
     done = []
     for name in _TARGETS:
         mod = sys.modules.get(name)
@@ -34,6 +61,8 @@ def install(strict: bool = False) -> list:
         if key not in _saved:
             _saved[key] = getattr(mod, "MaskCBAM")
         setattr(mod, "MaskCBAM", MaskCBAM)
+        if name.endswith("nn.tasks") and isinstance(getattr(mod, "DetectionModel", None), type):
+            _wrap_builder(mod.DetectionModel)
         done.append(name)
     if strict and not any(n.endswith("nn.tasks") for n in done):
         raise RuntimeError("ultralytics.nn.tasks is not imported yet: import the reference's ultralytics first, then install()")
@@ -45,4 +74,6 @@ def uninstall() -> None:
         mod = sys.modules.get(name)
         if mod is not None:
             setattr(mod, attr, obj)
+            if name.endswith("nn.tasks") and isinstance(getattr(mod, "DetectionModel", None), type):
+                _unwrap_builder(mod.DetectionModel)
         del _saved[(name, attr)]

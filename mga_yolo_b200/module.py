@@ -8,11 +8,21 @@ MGATrainer logs (mga_yolo/model/trainer.py:274-321).  The north-star keyword nam
 (`reduction_ratio`, `sam_cam_fusion`, `mga_pyramid_fusion`) are accepted too.
 
 The forward/backward math does not live here: it is one call into the CUDA library
-through `ops.mask_guided_cbam`.  CPU tensors raise -- there is no fallback.
+through `ops.mask_guided_cbam`.  CPU tensors raise -- there is no compute fallback.
+
+Two non-CUDA cases are answered WITHOUT computing anything, because graph builders ask for
+shapes before the model is on a GPU:
+  * meta tensors -> `torch.ops.mga.*` Meta kernels (shape/dtype propagation only);
+  * inside `shape_probe()` -- which `install()` wraps around the reference's
+    `DetectionModel.__init__` (ultralytics/nn/tasks.py:418-426: a CPU forward of zeros whose only
+    use is `s / x.shape[-2]` per output level) -- a CPU feature map gets an all-zeros tensor of
+    its own shape and dtype.  Outside that context a CPU tensor is an error.
 """
 from __future__ import annotations
 
+import contextlib
 import os
+import threading
 from typing import Optional, Sequence, Union
 
 import torch
@@ -34,6 +44,23 @@ _GATE_MODES = ("deterministic", "gumbel", "hard_st", "bernoulli_detach")
 SAM_CAM_FUSIONS = ("multiply", "add", "concat")
 PYRAMID_FUSIONS = ("add", "multiply", "concat")
 _BETA_ALPHA_ONE = 0.5413248546129181  # softplus(.) == 1: lets the fused op return the bare refined feature R = x*s*a
+
+_probe = threading.local()
+
+
+@contextlib.contextmanager
+def shape_probe():
+    """While active (per thread), a CPU forward of the block answers with zeros of the input's shape: the stride probe of
+    the reference's graph builder (ultralytics/nn/tasks.py:418-426) only reads output shapes.  Nothing is computed."""
+    _probe.depth = getattr(_probe, "depth", 0) + 1
+    try:
+        yield
+    finally:
+        _probe.depth -= 1
+
+
+def in_shape_probe() -> bool:
+    return getattr(_probe, "depth", 0) > 0
 
 
 class MaskGate(nn.Module):
@@ -131,12 +158,8 @@ class MaskGuidedCBAM(nn.Module):
             f |= _lib.SAMCAM_ADD
         if self.mga_pyramid_fusion == "multiply":
             f |= _lib.PYRAMID_MULTIPLY
-        if os.getenv("MGA_FORCE_SPLIT", ""):  # one kernel per phase (the default launch path)
+        if os.getenv("MGA_FORCE_SPLIT", ""):  # one kernel per phase instead of the cluster-per-sample kernels
             f |= _lib.FORCE_SPLIT
-        elif os.getenv("MGA_USE_FUSED", ""):  # experimental cluster-resident fused forward kernel
-            f |= _lib.USE_FUSED
-        elif os.getenv("MGA_USE_FLOW", ""):  # wavefront-ordered dataflow kernels
-            f |= _lib.USE_FLOW
         return f
 
     def forward(self, x: Union[torch.Tensor, Sequence[torch.Tensor]]) -> torch.Tensor:
@@ -146,6 +169,13 @@ class MaskGuidedCBAM(nn.Module):
         else:
             feat, mask = x, None
         assert isinstance(feat, torch.Tensor) and feat.dim() == 4
+        if feat.device.type == "cpu":
+            if in_shape_probe():
+                return torch.zeros_like(feat)  # shape-only answer (see module docstring); no math runs on the CPU
+            raise RuntimeError(
+                "mga_yolo_b200: the mask-guided CBAM path runs on CUDA tensors only (no CPU fallback); move the model and its "
+                "inputs to a GPU.  Shape probes of a graph builder go through mga_yolo_b200.shape_probe() (install() does that "
+                "for the reference's DetectionModel.__init__) or through meta tensors.")
         flags = self._flags()
         if mask is not None:
             if os.getenv("MGA_PROB_MODE", False) and hasattr(self, "gater"):

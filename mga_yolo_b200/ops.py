@@ -1,7 +1,8 @@
 """Torch-facing operators of the mask-guided CBAM path.
 
 `torch.ops.mga.cbam_fwd / cbam_bwd / mask_downsample` are registered for the CUDA
-dispatch key only, so CPU tensors fail inside the dispatcher ("no CPU fallback").
+dispatch key (the kernels) and the Meta key (shape propagation only), so CPU tensors fail
+inside the dispatcher ("no CPU fallback").
 Each op is a thin shim: it allocates outputs with the caching allocator and hands raw
 device pointers + the current stream to the C ABI (include/mga_cbam.h).
 
@@ -220,7 +221,55 @@ def _cbam_gates_bwd_cuda(grad_s, grad_a, x, mask, w1, b1, w2, b2, wsam, ctx, fla
     return dx, dmask, flat
 
 
+# ---- Meta ("fake") kernels: shape / dtype propagation only, so meta tensors, FakeTensorMode and graph capture see the ops.
+def _ctx_bytes_of(x, mask, w1, wsam, flags, tiny_thr, eps):
+    d, ctx_bytes, _ = _prep(x, mask, w1, wsam, flags, tiny_thr, eps)
+    return ctx_bytes
+
+
+def _grad_numel(x, w1, wsam):
+    hidden, Cc, k = w1.shape[0], x.shape[1], wsam.shape[-1]
+    return hidden * Cc + hidden + Cc * hidden + Cc + 3 * k * k + 1
+
+
+def _cbam_fwd_meta(x, mask, w1, b1, w2, b2, wsam, beta, flags, tiny_thr, eps):
+    return torch.empty_like(x, memory_format=torch.contiguous_format), x.new_empty(_ctx_bytes_of(x, mask, w1, wsam, flags, tiny_thr, eps), dtype=torch.uint8)
+
+
+def _cbam_bwd_meta(grad_out, x, mask, w1, b1, w2, b2, wsam, beta, ctx, flags, tiny_thr, eps, need_mask_grad):
+    dmask = torch.empty_like(mask, memory_format=torch.contiguous_format) if (mask is not None and need_mask_grad) else None
+    return torch.empty_like(x, memory_format=torch.contiguous_format), dmask, x.new_empty(_grad_numel(x, w1, wsam), dtype=torch.float32)
+
+
+def _cbam_gates_fwd_meta(x, mask, w1, b1, w2, b2, wsam, flags, tiny_thr, eps):
+    B, Cc, H, W = x.shape
+    return (x.new_empty((B, Cc), dtype=torch.float32), x.new_empty((B, 1, H, W), dtype=torch.float32),
+            x.new_empty(_ctx_bytes_of(x, mask, w1, wsam, flags, tiny_thr, eps), dtype=torch.uint8))
+
+
+def _cbam_gates_bwd_meta(grad_s, grad_a, x, mask, w1, b1, w2, b2, wsam, ctx, flags, tiny_thr, eps, need_mask_grad):
+    dmask = torch.empty_like(mask, memory_format=torch.contiguous_format) if (mask is not None and need_mask_grad) else None
+    return torch.empty_like(x, memory_format=torch.contiguous_format), dmask, x.new_empty(_grad_numel(x, w1, wsam), dtype=torch.float32)
+
+
+def _mask_downsample_meta(src, stride, method, thresh, close3x3, out_float):
+    dt = torch.float32 if out_float else torch.uint8
+    if stride <= 1:
+        return src.new_empty(src.shape, dtype=dt)
+    H, W = src.shape[-2:]
+    return src.new_empty((*src.shape[:-2], -(-H // stride), -(-W // stride)), dtype=dt)
+
+
+def _masks_multi_meta(src, method, thresh, close3x3, out_float):
+    B, H, W = src.shape
+    dt = torch.float32 if out_float else torch.uint8
+    return tuple(src.new_empty((B, H // s, W // s), dtype=dt) for s in (8, 16, 32))
+
+
 _LIBIMPL = torch.library.Library("mga", "IMPL")
+for _name, _fn in (("cbam_fwd", _cbam_fwd_meta), ("cbam_bwd", _cbam_bwd_meta), ("cbam_gates_fwd", _cbam_gates_fwd_meta),
+                   ("cbam_gates_bwd", _cbam_gates_bwd_meta), ("mask_downsample", _mask_downsample_meta), ("masks_multi", _masks_multi_meta)):
+    _LIBIMPL.impl(_name, _fn, "Meta")
 _LIBIMPL.impl("cbam_gates_fwd", _cbam_gates_fwd_cuda, "CUDA")
 _LIBIMPL.impl("cbam_gates_bwd", _cbam_gates_bwd_cuda, "CUDA")
 _LIBIMPL.impl("cbam_fwd", _cbam_fwd_cuda, "CUDA")
@@ -232,7 +281,7 @@ _LIBIMPL.impl("masks_multi", _masks_multi_cuda, "CUDA")
 class _CbamFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, mask, w1, b1, w2, b2, wsam, beta, flags, tiny_thr, eps):
-        if not x.is_cuda:
+        if x.device.type not in ("cuda", "meta"):
             raise RuntimeError("mga_yolo_b200: the mask-guided CBAM path runs on CUDA tensors only (no CPU fallback)")
         out, saved = torch.ops.mga.cbam_fwd(x, mask, w1, b1, w2, b2, wsam, beta, flags, tiny_thr, eps)
         ctx.save_for_backward(x, mask, w1, b1, w2, b2, wsam, beta, saved)
@@ -261,7 +310,7 @@ class _CbamGatesFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, mask, w1, b1, w2, b2, wsam, flags, tiny_thr, eps):
-        if not x.is_cuda:
+        if x.device.type not in ("cuda", "meta"):
             raise RuntimeError("mga_yolo_b200: the mask-guided CBAM path runs on CUDA tensors only (no CPU fallback)")
         s, a, saved = torch.ops.mga.cbam_gates_fwd(x, mask, w1, b1, w2, b2, wsam, flags, tiny_thr, eps)
         ctx.save_for_backward(x, mask, w1, b1, w2, b2, wsam, saved)

@@ -251,3 +251,152 @@ def test_launch_plan_is_a_function_of_the_sample_shape_only():
     assert ops.plan((2, 64, 10, 10))["path"] == "per_phase"       # W % 4 != 0
     assert ops.plan((2, 64, 80, 80), flags=_lib.FORCE_SPLIT)["path"] == "per_phase"
     assert ops.plan((2, 64, 80, 80), flags=_lib.FORCE_SPLIT, backward=True)["launches"] == 7  # 5 + reduce2 + partial sums
+
+
+def test_masks_follow_deep_copies_and_are_consumed_once():
+    """ModelEMA's deepcopy must see the masks set through the manager, and a forward without a fresh
+    set_masks() must not silently reuse the previous batch's masks."""
+    from mga_yolo_b200 import MGAHookManager
+
+    net = _ToyModel()
+    mgr = MGAHookManager(net, target_layers=("1", "2", "3")).register()
+    ema = copy.deepcopy(net)
+    assert ema.mga_cbam_masks is not net.mga_cbam_masks and ema.mga_cbam_masks.state is net.mga_cbam_masks.state
+    hook = next(iter(ema.model[1]._forward_hooks.values()))
+    assert hook.slot is ema.mga_cbam_masks
+    masks = [torch.zeros(2, 1, 16, 16), torch.zeros(2, 1, 8, 8), torch.zeros(2, 1, 4, 4)]
+    mgr.set_masks(masks)
+    assert ema.mga_cbam_masks.mask_for("1", torch.zeros(2, 16, 16, 16)) is masks[0]  # the copy's slot serves the same batch
+    assert ema.mga_cbam_masks.mask_for("2", torch.zeros(2, 24, 8, 8)) is masks[1]
+    assert ema.mga_cbam_masks.mask_for("3", torch.zeros(2, 32, 4, 4)) is masks[2]
+    assert mgr.slot.mask_for("1", torch.zeros(2, 16, 16, 16)) is None               # consumed by that forward
+    mgr.set_masks(masks, persistent=True)
+    for _ in range(2):
+        for lvl, c, s in (("1", 16, 16), ("2", 24, 8), ("3", 32, 4)):
+            assert mgr.slot.mask_for(lvl, torch.zeros(2, c, s, s)) is not None
+    mgr.set_masks(masks)
+    with pytest.raises(RuntimeError, match="stale or mismatched"):
+        mgr.slot.mask_for("1", torch.zeros(3, 16, 16, 16))  # another batch size: never a silent reuse
+    mgr.set_masks(torch.ones(2, 16, 16), model=ema)  # explicit addressing of another model object's slot
+    assert ema.mga_cbam_masks.state.full is not None
+    again = pickle.loads(pickle.dumps(net))
+    assert again.mga_cbam_masks.state is not net.mga_cbam_masks.state and again.mga_cbam_masks.state.full is None
+    with pytest.raises(AttributeError):
+        MGAHookManager.slot_of(_ToyModel())
+
+
+def test_meta_kernels_propagate_shapes_without_a_gpu():
+    """Meta kernels for torch.ops.mga.* (meta tensors / FakeTensorMode see the ops)."""
+    from mga_yolo_b200 import MaskGuidedCBAM
+
+    blk = MaskGuidedCBAM(64).to("meta")
+    x = torch.empty(2, 64, 20, 20, device="meta", dtype=torch.bfloat16, requires_grad=True)
+    mk = torch.empty(2, 1, 20, 20, device="meta")
+    out = blk([x, mk])
+    assert out.device.type == "meta" and out.shape == x.shape and out.dtype == torch.bfloat16
+    out.sum().backward()
+    assert x.grad.shape == x.shape and blk.cam_mlp[0].weight.grad.shape == (4, 64) and blk.beta.grad.shape == ()
+    u8 = torch.empty(3, 640, 640, dtype=torch.uint8, device="meta")
+    assert torch.ops.mga.mask_downsample(u8, 8, 0, 0.0, False, True).shape == (3, 80, 80)
+    assert [t.shape[-1] for t in torch.ops.mga.masks_multi(u8, 2, 0.0, True, False)] == [80, 40, 20]
+
+
+def test_shape_probe_is_the_only_cpu_answer():
+    from mga_yolo_b200 import MaskGuidedCBAM
+    from mga_yolo_b200.module import in_shape_probe, shape_probe
+
+    m = MaskGuidedCBAM(16)
+    x = torch.randn(1, 16, 8, 8)
+    with shape_probe():
+        assert in_shape_probe()
+        y = m([x, torch.randn(1, 1, 8, 8)])
+        assert y.shape == x.shape and y.dtype == x.dtype and not y.any()  # shapes only: nothing is computed on the CPU
+    assert not in_shape_probe()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(x)
+
+
+def test_flat_grad_reducer_survives_zero_grad_set_to_none():
+    """optimizer.zero_grad() (set_to_none=True) detaches .grad from the flat buffer; all_reduce() must re-bind."""
+    from mga_yolo_b200 import FlatGradReducer
+
+    lin = nn.Linear(4, 3)
+    red = FlatGradReducer(lin.parameters())
+    lin.zero_grad(set_to_none=True)
+    assert lin.weight.grad is None
+    lin(torch.ones(2, 4)).sum().backward()  # fresh .grad tensors outside the flat buffer
+    assert lin.weight.grad.data_ptr() != red.flat.data_ptr()
+    want = torch.cat([lin.weight.grad.flatten(), lin.bias.grad.flatten()]).clone()
+    red.all_reduce()  # no process group: binds + returns
+    assert torch.equal(red.flat, want) and lin.weight.grad.data_ptr() == red.flat.data_ptr()
+    lin.zero_grad(set_to_none=True)
+    lin.weight.grad = torch.ones_like(lin.weight)  # bias got no gradient this step -> contributes zero
+    red.all_reduce()
+    assert torch.equal(red.flat, torch.cat([torch.ones(12), torch.zeros(3)]))
+
+
+REF = Path("/root/reference")
+
+
+def _import_reference():
+    import os
+
+    os.environ.setdefault("YOLO_CONFIG_DIR", "/tmp/ulcfg")
+    sys.dont_write_bytecode = True  # /root/reference is read-only
+    if str(REF) not in sys.path:
+        sys.path.insert(0, str(REF))
+    from mga_yolo.external.ultralytics.ultralytics import YOLO  # noqa: F401  (import order matters, SURVEY 8c)
+    from mga_yolo.model.model import MGAModel
+
+    return MGAModel
+
+
+@pytest.mark.skipif(not (REF / "configs/models/yolov8_cbam.yaml").exists(), reason="reference checkout not present (GPU box)")
+@pytest.mark.timeout(600)
+def test_install_builds_the_reference_model_from_its_yaml():
+    """VERDICT r1 item 2 / ADVICE high: after install(), MGAModel(yolov8n_cbam.yaml) must construct -- DetectionModel.__init__
+    runs a CPU stride probe (ultralytics/nn/tasks.py:418-426) that passes through the block."""
+    import mga_yolo_b200 as mb
+
+    MGAModel = _import_reference()
+    try:
+        done = mb.install(strict=True)
+        assert any(n.endswith("nn.tasks") for n in done)
+        model = MGAModel(str(REF / "configs/models/yolov8n_cbam.yaml"), nc=1, verbose=False)
+        blocks = [m for m in model.model if isinstance(m, mb.MaskCBAM)]
+        assert [b.C for b in blocks] == [64, 128, 256] and [m.i for m in blocks] == [23, 25, 27]
+        assert model.stride.tolist() == [8.0, 16.0, 32.0]
+        ref_keys = {"beta", "cam_mlp.0.weight", "cam_mlp.0.bias", "cam_mlp.2.weight", "cam_mlp.2.bias", "sam_conv.weight"}
+        assert {k.split(".", 2)[2] for k in model.state_dict() if k.startswith("model.23.")} == ref_keys
+        with pytest.raises(RuntimeError, match="no CPU fallback"):  # outside the builder's probe a CPU forward is an error
+            model(torch.zeros(1, 3, 64, 64))
+        meta = copy.deepcopy(model).to("meta")  # whole-graph shape propagation through the Meta kernels
+        out = meta(torch.empty(1, 3, 64, 64, device="meta"))
+        assert set(out) == {"det", "seg"} and [t.shape[-1] for t in out["det"]] == [8, 4, 2]
+    finally:
+        mb.uninstall()
+    from mga_yolo.external.ultralytics.ultralytics.nn import tasks
+
+    assert tasks.MaskCBAM.__module__.startswith("mga_yolo.") and not getattr(tasks.DetectionModel.__init__, "_mga_shape_probe", False)
+
+
+@pytest.mark.skipif(not (REF / "configs/models/yolov8_cbam.yaml").exists(), reason="reference checkout not present (GPU box)")
+@pytest.mark.timeout(600)
+def test_hook_manager_on_the_vendored_detection_model():
+    """Layers 15/18/21 of stock yolov8n.yaml are the P3/P4/P5 neck outputs with 64/128/256 channels."""
+    import mga_yolo_b200 as mb
+
+    _import_reference()
+    from mga_yolo.external.ultralytics.ultralytics.nn.tasks import DetectionModel
+
+    det = DetectionModel("yolov8n.yaml", nc=1, verbose=False)
+    mgr = mb.MGAHookManager(det, target_layers=("15", "18", "21"))
+    assert [mgr.blocks[k].C for k in ("15", "18", "21")] == [64, 128, 256]
+    mgr.register()
+    ema = copy.deepcopy(det)
+    assert next(iter(ema.model[15]._forward_hooks.values())).block is ema.mga_cbam["15"]
+    assert any(k.startswith("mga_cbam.21.") for k in det.state_dict())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        det(torch.zeros(1, 3, 64, 64))
+    mgr.remove()
+    assert len(det(torch.zeros(1, 3, 64, 64))) == 3
