@@ -286,7 +286,7 @@ def gpu_arm(args, rank, world, local_rank):
 
     def flags_of(scf, split=False):
         f = _lib.SAMCAM_ADD if scf == "add" else 0
-        return f | (_lib.FORCE_SPLIT if (args.force_split or split) else 0) | (_lib.USE_FUSED if args.use_fused else 0) | (_lib.USE_FLOW if args.use_flow else 0)
+        return f | (_lib.FORCE_SPLIT if (args.force_split or split) else 0)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -717,8 +717,6 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer end-to-end measurement")
     ap.add_argument("--force-split", action="store_true", help="never use the cluster-resident fused kernels")
-    ap.add_argument("--use-flow", action="store_true", help="wavefront-ordered dataflow kernels (one launch per direction)")
-    ap.add_argument("--use-fused", action="store_true", help="opt in to the experimental cluster-resident fused forward kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

@@ -45,9 +45,7 @@ enum {
     MGA_GATE_CLAMP = 1 << 2,       /* eval-mode ProbMaskGater: clamp mask to [0,1] first (probmaskgater.py:77) */
     MGA_SAMCAM_ADD = 1 << 4,       /* sam_cam_fusion = add (build-side mode, parity unpinned); default multiply = reference */
     MGA_PYRAMID_MULTIPLY = 1 << 6, /* mga_pyramid_fusion = multiply (build-side mode); default add = reference alpha-skip */
-    MGA_FORCE_SPLIT = 1 << 8,      /* never take the cluster-resident fused forward kernel */
-    MGA_USE_FUSED = 1 << 9,        /* opt in to the cluster-resident fused forward kernel (experimental) */
-    MGA_USE_FLOW = 1 << 11,        /* one wavefront-ordered dataflow kernel per direction instead of one kernel per phase */
+    MGA_FORCE_SPLIT = 1 << 8,      /* one kernel per phase instead of the cluster-per-sample kernels (bits 9 and 11 are retired) */
     MGA_GATES_ONLY = 1 << 10,      /* internal: compute / differentiate the two gates s(B,C), a(B,HW) only (concat fusion modes) */
     MGA_NO_SAVE = 1 << 12          /* inference (model.eval() + no_grad, predictor.py:7-24): the forward may skip the saved-for-backward
                                       planes; ctx is then NOT valid for mga_cbam_backward (s and a are still written) */

@@ -16,7 +16,8 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
-LIB = PKG / os.environ.get("MGA_LIBNAME", "libmga_cbam.so")
+LIB = PKG / "libmga_cbam.so"
+LIB_TUNING = PKG / "libmga_cbam_tuning.so"  # same sources + -DMGA_TUNING: MGA_CL_* environment knobs and the phase timeline (tools/, geometry tests)
 SOURCES = ("mga_cbam.cu", "mask_ops.cu")
 ARCH = ("-gencode", "arch=compute_100a,code=sm_100a")
 
@@ -28,24 +29,27 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: the CUDA library cannot be built (there is no CPU fallback)")
 
 
-def _stale() -> bool:
-    if not LIB.exists():
+def _stale(lib: Path = LIB) -> bool:
+    if not lib.exists():
         return True
-    t = LIB.stat().st_mtime
+    t = lib.stat().st_mtime
     deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h")) + [Path(__file__)]
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not _stale():
-        return LIB
+def build(force: bool = False, verbose: bool = False, tuning: bool = False) -> Path:
+    lib = LIB_TUNING if tuning else LIB
+    if not force and not _stale(lib):
+        return lib
     nvcc = _nvcc()
-    objdir = PKG / "build"
-    objdir.mkdir(exist_ok=True)
+    objdir = PKG / "build" / ("tuning" if tuning else "product")
+    objdir.mkdir(parents=True, exist_ok=True)
     common = [nvcc, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", str(INCLUDE), "-I", str(CSRC)]
     if verbose:
         common += ["-Xptxas", "-v"]
-    common += [f"-D{d}" for d in os.environ.get("MGA_DEFINES", "").split() if d]
+    if tuning:
+        common += ["-DMGA_TUNING"]
+        common += [f"-D{d}" for d in os.environ.get("MGA_DEFINES", "").split() if d]
 
     def compile_one(src: str) -> Path:
         obj = objdir / (src + ".o")
@@ -59,13 +63,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIB.with_suffix(".so.tmp")
+    tmp = lib.with_suffix(".so.tmp")
     r = subprocess.run([nvcc, *ARCH, "-shared", "-o", str(tmp), *map(str, objs), "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    os.replace(tmp, LIB)
-    return LIB
+    os.replace(tmp, lib)
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, tuning="--tuning" in sys.argv))

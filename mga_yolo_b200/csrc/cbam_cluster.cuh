@@ -29,7 +29,6 @@
 #include <cooperative_groups.h>
 
 #include "cbam_conv.cuh"
-#include "cbam_fused.cuh"  // load_mask_any / store_mask_any / stamp
 #include "common.cuh"
 
 namespace mga {

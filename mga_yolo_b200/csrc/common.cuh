@@ -248,9 +248,50 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0,
                  : "memory");
 }
 
+
+// ---------------------------------------------------------------- small helpers shared by the cluster and per-phase kernels
+constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
+
+// In-kernel phase timeline (tools/timeline.py): compiled in only with -DMGA_TUNING; thread 0 of each CTA stamps %globaltimer.
+#ifdef MGA_TUNING
+__device__ unsigned long long* g_timeline = nullptr;
+__device__ __forceinline__ void stamp(int k) {
+    if (g_timeline != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_timeline[(size_t)blockIdx.x * 16 + k] = t;
+        if (k == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_timeline[(size_t)blockIdx.x * 16 + 15] = smid;
+        }
+    }
+}
+#else
+__device__ __forceinline__ void stamp(int) {}
+#endif
+
+__device__ __forceinline__ float load_mask_any(const void* mask, int mdt, size_t i) {
+    if (mdt == MGA_F32) return __ldg(static_cast<const float*>(mask) + i);
+    if (mdt == MGA_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(mask)[i]);
+    return __half2float(static_cast<const __half*>(mask)[i]);
+}
+__device__ __forceinline__ void store_mask_any(void* mask, int mdt, size_t i, float v) {
+    if (mdt == MGA_F32) static_cast<float*>(mask)[i] = v;
+    else if (mdt == MGA_BF16) static_cast<__nv_bfloat16*>(mask)[i] = __float2bfloat16_rn(v);
+    else static_cast<__half*>(mask)[i] = __float2half_rn(v);
+}
+
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- block coordinates as data
 // Every phase is written as a __device__ body that takes its block coordinates as an argument, so the same code runs
-// either as its own kernel (coordinates = blockIdx) or as one role of the wavefront-ordered dataflow kernels (cbam_flow.cuh).
+// as its own kernel (coordinates = blockIdx); the indirection lets tools re-drive a phase with synthetic coordinates.
 struct Blk {
     int x, y, z, gx;  // blockIdx.x/y/z and gridDim.x of the equivalent stand-alone launch
 };

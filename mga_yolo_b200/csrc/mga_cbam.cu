@@ -4,13 +4,13 @@
 #include <cstring>
 #include <type_traits>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "cbam_bwd.cuh"
 #include "cbam_cluster.cuh"
 #include "cbam_conv.cuh"
-#include "cbam_flow.cuh"
-#include "cbam_fused.cuh"
 #include "cbam_fwd.cuh"
 #include "common.cuh"
 
@@ -30,27 +30,31 @@ int fail(int code, const char* fmt, ...) {
 // Every kernel launch of the library goes through a LaunchScope: it bumps the launch counter
 // (bench.py's "gpu_launches") and, when profiling is switched on, brackets the launch with
 // CUDA events on the launching stream so bench.py can report the dominant kernel's duration.
+// Forward and autograd's per-device backward threads launch concurrently: the counter is atomic, the record list is
+// guarded by a mutex (records are addressed by index, never by reference, so growth of the vector is harmless).
 struct ProfRec { const char* name; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof;
-static bool g_prof_on = false;
-static unsigned long long g_launches = 0;
+static std::mutex g_prof_mu;
+static std::atomic<bool> g_prof_on{false};
+static std::atomic<unsigned long long> g_launches{0};
 
 struct LaunchScope {
     cudaStream_t st;
-    int rec = -1;
+    cudaEvent_t end = nullptr;
     LaunchScope(const char* name, cudaStream_t s) : st(s) {
-        ++g_launches;
-        if (g_prof_on) {
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (g_prof_on.load(std::memory_order_relaxed)) {
             ProfRec r{name, nullptr, nullptr};
             cudaEventCreate(&r.a);
             cudaEventCreate(&r.b);
             cudaEventRecord(r.a, st);
+            end = r.b;
+            std::lock_guard<std::mutex> lk(g_prof_mu);
             g_prof.push_back(r);
-            rec = (int)g_prof.size() - 1;
         }
     }
     ~LaunchScope() {
-        if (rec >= 0) cudaEventRecord(g_prof[rec].b, st);
+        if (end) cudaEventRecord(end, st);
     }
 };
 #define MGA_LAUNCH(name, st, ...) do { LaunchScope _ls(name, st); __VA_ARGS__; } while (0)
@@ -228,99 +232,16 @@ static int pick_vec(const Shape& s, int dtype, std::initializer_list<const void*
     return v;
 }
 
-// ------------------------------------------------------------------ cluster-resident fused path: geometry + launch
-static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
-
-// Smallest cluster size whose per-CTA slice (+ work buffers) fits in shared memory.  false -> use the split path.
-static bool fused_geometry(const Shape& sh, int esize, bool bwd, FusedGeom* out) {
-    const int vec = 16 / esize;
-    if (sh.S % vec) return false;
-    const int U = sh.S / vec, C = sh.C, pad = kMaxK / 2;  // the fused conv always runs 7x7 with zero-padded weights
-    for (int CS = 1; CS <= 16; CS *= 2) {
-        FusedGeom g{};
-        g.CS = CS;
-        g.nUmax = (U + CS - 1) / CS;
-        if (g.nUmax > 256) continue;
-        if (CS > 1 && (CS - 1) * g.nUmax >= U + g.nUmax) continue;
-        g.rsU = g.nUmax | 1;
-        g.UT = std::min(8, pow2ceil((g.nUmax + 31) / 32));
-        g.CG = kFW / g.UT;
-        g.NJ = C < kFB ? std::max(1, kFB / C) : 1;
-        g.NG = std::min(4, C);
-        g.rowsPerGroup = (C + g.NG - 1) / g.NG;
-        const int nPmax = g.nUmax * vec;
-        g.tileRows = (nPmax + sh.W - 2) / sh.W + 1 + 2 * pad;
-        const int TW = sh.W + 2 * pad;
-        size_t off = 128;  // mbarriers (unused by the cp.async load path)
-        g.off_misc = (int)off;
-        off += 1024;
-        g.off_chan = (int)off;
-        const size_t chan_f = bwd ? ((size_t)(12 + g.UT) * C + 4 * sh.hidden + 16) : ((size_t)7 * C + 2 * sh.hidden);
-        off += align256(chan_f * 4);
-        g.off_pix = (int)off;
-        off += align256((size_t)(bwd ? 3 : 1) * nPmax * 4);
-        g.off_tile = (int)off;
-        g.plane_floats = g.tileRows * TW;
-        // scratch aliases the pmax/pavg planes: pool partials [NJ][4][C], optionally the staged DSMEM gather [CS][4][C]
-        size_t scratch_f = std::max<size_t>((size_t)2 * g.plane_floats, (size_t)4 * g.NJ * C);
-        if ((size_t)4 * C * CS <= 4096) scratch_f = std::max<size_t>(scratch_f, (size_t)4 * C * CS);
-        g.scratch_floats = (int)scratch_f;
-        off += align256(((size_t)g.plane_floats + scratch_f) * 4);
-        g.off_xs = (int)off;
-        off += (size_t)C * g.rsU * 16;
-        if (off > (size_t)kSmemLimit) continue;
-        g.smem_bytes = (int)off;
-        *out = g;
-        return true;
-    }
-    return false;
-}
-
-template <typename K, typename... Args>
-static int launch_cluster(const char* name, K kernel, const FusedGeom& gm, int nClusters, cudaStream_t st, Args... args) {
-    static thread_local const void* configured[16] = {};
-    bool done = false;
-    for (const void* c : configured) done |= (c == (const void*)kernel);
-    if (!done) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) return fail(MGA_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
-        for (auto& c : configured)
-            if (!c) { c = (const void*)kernel; break; }
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(nClusters * gm.CS));
-    cfg.blockDim = dim3(kFB);
-    cfg.dynamicSmemBytes = (size_t)gm.smem_bytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)gm.CS;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e;
-    {
-        LaunchScope ls(name, st);
-        e = cudaLaunchKernelEx(&cfg, kernel, args...);
-    }
-    if (e != cudaSuccess) return fail(MGA_ERR_CUDA, "%s: launch (cluster %d, %d B smem): %s", name, gm.CS, gm.smem_bytes, cudaGetErrorString(e));
-    return MGA_OK;
-}
-
-template <typename T>
-static int forward_fused(const Shape& sh, const FusedGeom& gm, const T* x, const void* mask, int mask_dtype, const mga_cbam_params& p, T* out,
-                         Ctx ctx, cudaStream_t st) {
-    return launch_cluster("fused_fwd", fused_fwd_kernel<T>, gm, sh.B, st, x, mask, mask_dtype, out, sh, p, ctx, gm);
-}
-
-
 // ------------------------------------------------------------------ cluster-per-sample path (cbam_cluster.cuh): geometry + launch
+// Tuning knobs (MGA_CL_* environment variables) exist only in -DMGA_TUNING builds (tools/); the product library has none.
+#ifdef MGA_TUNING
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return (e && *e) ? atoi(e) : dflt;
 }
+#else
+static constexpr int env_int(const char*, int dflt) { return dflt; }
+#endif
 
 // Smallest cluster whose per-CTA share of the sample (x, plus g in backward) is <= ~224 KB: with 2 CTAs per SM that keeps
 // ~60 MB of feature map in flight on the whole GPU, well inside the 126 MB L2, so the later passes are L2 hits.
@@ -393,15 +314,19 @@ static bool cl_geometry(const Shape& sh, int esize, bool bwd, ClGeom* out) {
 
 template <typename Kern, typename... Args>
 static int launch_cl(const char* name, Kern kernel, const ClGeom& gm, int nClusters, cudaStream_t st, Args... args) {
-    static thread_local const void* configured[16] = {};
+    // function attributes and the occupancy answer are per-DEVICE state: both caches are keyed by (device, kernel)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(MGA_ERR_CUDA, "%s: cudaGetDevice failed", name);
+    struct Cfg { const void* k; int dev; };
+    static thread_local Cfg configured[64] = {};
     bool done = false;
-    for (const void* c : configured) done |= (c == (const void*)kernel);
+    for (const Cfg& c : configured) done |= (c.k == (const void*)kernel && c.dev == dev);
     if (!done) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return fail(MGA_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
         for (auto& c : configured)
-            if (!c) { c = (const void*)kernel; break; }
+            if (!c.k) { c = Cfg{(const void*)kernel, dev}; break; }  // table full: the attributes are simply set again next time
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(nClusters * gm.CS));
@@ -424,15 +349,15 @@ static int launch_cl(const char* name, Kern kernel, const ClGeom& gm, int nClust
     cudaError_t e;
     {
         // can at least one cluster of this size / shared-memory footprint be resident?  (cached; 0 -> the caller takes the per-phase path)
-        struct Occ { const void* k; int cs, smem, n; };
-        static thread_local Occ cache[32] = {};
+        struct Occ { const void* k; int dev, cs, smem, n; };
+        static thread_local Occ cache[64] = {};
         int n = -1;
         for (const Occ& c : cache)
-            if (c.k == (const void*)kernel && c.cs == gm.CS && c.smem == gm.smem_bytes) n = c.n;
+            if (c.k == (const void*)kernel && c.dev == dev && c.cs == gm.CS && c.smem == gm.smem_bytes) n = c.n;
         if (n < 0) {
             if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
             for (Occ& c : cache)
-                if (!c.k) { c = Occ{(const void*)kernel, gm.CS, gm.smem_bytes, n}; break; }
+                if (!c.k) { c = Occ{(const void*)kernel, dev, gm.CS, gm.smem_bytes, n}; break; }
         }
         if (n <= 0) return MGA_ERR_UNSUPPORTED;
     }
@@ -442,73 +367,6 @@ static int launch_cl(const char* name, Kern kernel, const ClGeom& gm, int nClust
     }
     if (e != cudaSuccess) return fail(MGA_ERR_CUDA, "%s: launch (cluster %d, %d B smem): %s", name, gm.CS, gm.smem_bytes, cudaGetErrorString(e));
     return MGA_OK;
-}
-
-// ------------------------------------------------------------------ wavefront-ordered dataflow forward (one launch)
-// Steps between two dependent phases of the same sample.  A phase takes a few microseconds (it is latency bound), a step
-// (= one sample's worth of CTAs of every role) far less, so the lag is sized to ~5 us of streaming: when a role's CTAs
-// are dispatched their dependency has normally completed and nobody spins.  ~7.5 MB of feature map per lag keeps the
-// in-flight window (5-6 lags) well inside the 126 MB L2.  MGA_FLOW_LAG overrides (tuning).
-static int flow_lag(const Shape& s, int esize) {
-    if (const char* e = getenv("MGA_FLOW_LAG")) { const int v = atoi(e); if (v > 0) return v; }
-    const double sample_bytes = (double)s.C * s.S * esize;
-    const int lag = (int)(7.5e6 / sample_bytes + 0.999);
-    return std::min(std::max(lag, 2), 32);
-}
-
-static size_t flow_ctl_bytes(const Shape& s) { return align256(((size_t)kFlowMaxRoles * s.B + 16) * sizeof(unsigned)); }
-
-template <typename T>
-static bool flow_fwd_supported(const Shape& sh) {
-    constexpr int VEC = 16 / sizeof(T);
-    if (sh.S % VEC || sh.W % 4) return false;
-    const int U = sh.S / VEC;
-    const int tpp = pool_tpp(U, VEC);
-    return sh.C % (kBlock / tpp) == 0;  // a pooling CTA must not straddle two samples
-}
-
-template <typename T>
-static int forward_flow(const Shape& sh, const T* x, const void* mask, int mask_dtype, const mga_cbam_params& p, T* out, Ctx ctx, FwdScratch fs,
-                        void* ctl, cudaStream_t st) {
-    constexpr int VEC = 16 / sizeof(T);
-    const int U = sh.S / VEC;
-    const int cls = plane_class(U);
-    const TileCfg tc = pick_tiles(sh, U, VEC);
-    const int tpp = pool_tpp(U, VEC);
-    const int nMaskTiles = (sh.S + kMaskTile - 1) / kMaskTile;
-    ConvGeom cg = conv_geom(sh.W);
-    cg.use_tma = 0;  // planes are produced inside the same kernel: staged with L2-coherent loads
-    FlowSched sc{};
-    sc.nRoles = kFwdRoles;
-    sc.cnt[kFwdMask] = sh.has_mask() ? nMaskTiles : 0;
-    sc.cnt[kFwdPool] = sh.C / (kBlock / tpp);
-    sc.cnt[kFwdMlp] = 1;
-    sc.cnt[kFwdReduce] = (U + tc.lpt * tc.upt - 1) / (tc.lpt * tc.upt);
-    sc.cnt[kFwdConv] = (sh.H + cg.RB - 1) / cg.RB;
-    sc.cnt[kFwdRescale] = (sh.C * U + kRescaleUnits - 1) / kRescaleUnits;
-    sc.pre[0] = 0;
-    for (int r = 0; r < kFwdRoles; ++r) {
-        sc.lag[r] = flow_lag(sh, (int)sizeof(T)) * r;
-        sc.dep[r] = r - 1;
-        sc.pre[r + 1] = sc.pre[r] + sc.cnt[r];
-    }
-    sc.per_step = sc.pre[kFwdRoles];
-    sc.steps = sh.B + sc.lag[kFwdRoles - 1];
-    sc.done = static_cast<unsigned*>(ctl);
-    sc.err = reinterpret_cast<int*>(sc.done + (size_t)kFlowMaxRoles * sh.B);
-    cudaMemsetAsync(ctl, 0, flow_ctl_bytes(sh), st);
-    const size_t smem = std::max((size_t)(2 * sh.C + 2 * sh.hidden), (size_t)3 * cg.planeT + (size_t)3 * cg.nStrips * 4 + 3 * kMaxK * kMaxK) * sizeof(float);
-    const unsigned grid = (unsigned)sc.steps * (unsigned)sc.per_step;
-#define MGA_FLOW(CLS)                                                                                                                  \
-    do {                                                                                                                               \
-        allow_big_smem(flow_fwd_kernel<T, CLS>, smem);                                                                                 \
-        MGA_LAUNCH("flow_fwd", st, (flow_fwd_kernel<T, CLS><<<grid, kBlock, smem, st>>>(x, mask, mask_dtype, out, sh, p, ctx, fs, cg, sc, nMaskTiles))); \
-    } while (0)
-    if (cls == 0) MGA_FLOW(0);
-    else if (cls == 1) MGA_FLOW(1);
-    else MGA_FLOW(2);
-#undef MGA_FLOW
-    return check_launch("mga_cbam_forward(flow)");
 }
 
 // ------------------------------------------------------------------ forward
@@ -563,16 +421,8 @@ static int forward_split(const Shape& sh, const T* x, const void* mask, int mask
 
 template <typename T>
 static int forward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, const void* mask, const mga_cbam_params& p, void* out,
-                     Ctx ctx, FwdScratch fs, void* flow_ctl, cudaStream_t st) {
+                     Ctx ctx, FwdScratch fs, cudaStream_t st) {
     const int vec = pick_vec(sh, d->dtype, {x, out});
-    // Cluster-resident fused forward: only when asked for (MGA_USE_FUSED).  Measured r1: alone it beats the split forward on
-    // small samples (29 us vs 44 us at B64 x C256 x 20x20) but its 227 KB CTAs evict the other levels' kernels from 128 SMs,
-    // so the three-level step got slower (0.404 vs 0.395 ms) -- not the default.  Never a function of B.
-    FusedGeom gm;
-    if (vec > 1 && (d->flags & MGA_USE_FUSED) && !(d->flags & (MGA_FORCE_SPLIT | MGA_GATES_ONLY)) && fused_geometry(sh, (int)sizeof(T), false, &gm))
-        return forward_fused<T>(sh, gm, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, st);
-    if (vec > 1 && (d->flags & MGA_USE_FLOW) && !(d->flags & (MGA_FORCE_SPLIT | MGA_GATES_ONLY)) && flow_fwd_supported<T>(sh))
-        return forward_flow<T>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, flow_ctl, st);
     ClGeom cgm;
     if (vec > 1 && !(d->flags & MGA_FORCE_SPLIT) && cl_geometry(sh, (int)sizeof(T), false, &cgm)) {
         const int rc = launch_cl("cl_fwd", cl_fwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), mask, d->mask_dtype, static_cast<T*>(out), sh, p, ctx);
@@ -674,23 +524,34 @@ extern "C" {
 int mga_abi_version(void) { return MGA_ABI_VERSION; }
 const char* mga_last_error(void) { return g_err; }
 
-unsigned long long mga_launch_count(void) { return g_launches; }
+unsigned long long mga_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-/* debug: device buffer of 16 uint64 per CTA that the fused kernels stamp with %globaltimer per phase (NULL = off) */
+/* debug (tools/timeline.py): device buffer of 16 uint64 per CTA that the cluster kernels stamp with %globaltimer per phase (NULL = off).
+   Only -DMGA_TUNING builds carry the stamps; the product library answers MGA_ERR_UNSUPPORTED. */
 int mga_debug_timeline(void* device_buffer) {
+#ifdef MGA_TUNING
     unsigned long long* p = static_cast<unsigned long long*>(device_buffer);
     const cudaError_t e = cudaMemcpyToSymbol(g_timeline, &p, sizeof(p));
     return e == cudaSuccess ? MGA_OK : fail(MGA_ERR_CUDA, "mga_debug_timeline: %s", cudaGetErrorString(e));
+#else
+    (void)device_buffer;
+    return fail(MGA_ERR_UNSUPPORTED, "mga_debug_timeline: library built without -DMGA_TUNING");
+#endif
 }
 
 int mga_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     g_prof.clear();
-    g_prof_on = on != 0;
+    g_prof_on.store(on != 0);
     return MGA_OK;
 }
-int mga_profile_count(void) { return (int)g_prof.size(); }
+int mga_profile_count(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    return (int)g_prof.size();
+}
 int mga_profile_read(int i, const char** name, float* ms) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     if (i < 0 || i >= (int)g_prof.size() || !name || !ms) return fail(MGA_ERR_ARG, "bad profile record index");
     *name = g_prof[i].name;
     const cudaError_t e = cudaEventElapsedTime(ms, g_prof[i].a, g_prof[i].b);
@@ -707,7 +568,7 @@ int mga_cbam_plan(const mga_cbam_desc* d, int direction, mga_cbam_plan_info* inf
     ClGeom g{};
     std::memset(info, 0, sizeof(*info));
     const bool vec_ok = sh.S % (16 / esize) == 0;  // (pointer alignment is checked at call time)
-    if (vec_ok && !(d->flags & (MGA_FORCE_SPLIT | MGA_USE_FUSED | MGA_USE_FLOW)) && cl_geometry(sh, esize, bwd, &g)) {
+    if (vec_ok && !(d->flags & MGA_FORCE_SPLIT) && cl_geometry(sh, esize, bwd, &g)) {
         info->path = 1;
         info->cluster_size = g.CS;
         info->rows_per_cta = g.rowsPer;
@@ -733,7 +594,7 @@ int mga_cbam_workspace(const mga_cbam_desc* d, size_t* ctx_bytes, size_t* scratc
     FwdScratch f;
     BwdScratch b;
     if (ctx_bytes) *ctx_bytes = carve_ctx(sh, nullptr, &c);
-    if (scratch_bytes) *scratch_bytes = std::max(carve_fwd(sh, nullptr, &f), carve_bwd(sh, nullptr, &b)) + flow_ctl_bytes(sh);
+    if (scratch_bytes) *scratch_bytes = std::max(carve_fwd(sh, nullptr, &f), carve_bwd(sh, nullptr, &b));
     return MGA_OK;
 }
 
@@ -747,14 +608,12 @@ int mga_cbam_forward(const mga_cbam_desc* d, const void* x, const void* mask, co
     Ctx ctx;
     FwdScratch fs;
     carve_ctx(sh, ctx_buf, &ctx);
-    const size_t fwd_bytes = carve_fwd(sh, scratch, &fs);
-    BwdScratch btmp;
-    void* flow_ctl = static_cast<char*>(scratch) + std::max(fwd_bytes, carve_bwd(sh, nullptr, &btmp));  // tail of the scratch buffer
+    carve_fwd(sh, scratch, &fs);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (d->dtype) {
-        case MGA_F32: return forward_t<float>(sh, d, x, mask, *p, out, ctx, fs, flow_ctl, st);
-        case MGA_BF16: return forward_t<__nv_bfloat16>(sh, d, x, mask, *p, out, ctx, fs, flow_ctl, st);
-        default: return forward_t<__half>(sh, d, x, mask, *p, out, ctx, fs, flow_ctl, st);
+        case MGA_F32: return forward_t<float>(sh, d, x, mask, *p, out, ctx, fs, st);
+        case MGA_BF16: return forward_t<__nv_bfloat16>(sh, d, x, mask, *p, out, ctx, fs, st);
+        default: return forward_t<__half>(sh, d, x, mask, *p, out, ctx, fs, st);
     }
 }
 

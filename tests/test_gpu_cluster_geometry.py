@@ -44,8 +44,9 @@ CASES += [
 def test_forced_cluster_sizes_match_oracle(case):
     B, C, H, W, dt, scf, pyr, csf, csb = case[:9]
     variant = case[9] if len(case) > 9 else "default"
-    env = dict(os.environ, MGA_CL_CS_F=str(csf), MGA_CL_CS_B=str(csb), MGA_CL_DEBUG="1", PYTHONPATH=str(ROOT))
-    for k in ("MGA_FORCE_SPLIT", "MGA_USE_FUSED", "MGA_USE_FLOW", "MGA_CL"):
+    # forcing a cluster size is a tuning knob: only the -DMGA_TUNING build of the library (same kernels) reads MGA_CL_*
+    env = dict(os.environ, MGA_CL_CS_F=str(csf), MGA_CL_CS_B=str(csb), MGA_CL_DEBUG="1", PYTHONPATH=str(ROOT), MGA_LIBNAME="libmga_cbam_tuning.so")
+    for k in ("MGA_FORCE_SPLIT", "MGA_CL"):
         env.pop(k, None)
     r = subprocess.run([sys.executable, "-m", "tests._cluster_case", str(B), str(C), str(H), str(W), dt, scf, pyr, variant], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=300)
