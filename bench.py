@@ -19,10 +19,16 @@ Numbers on the JSON line
   roofline       dominant kernel: algorithmic bytes of that kernel / its CUDA-event duration,
                  measured in an instrumented pass right after the timed region (per-kernel events
                  cannot be recorded inside a CUDA graph).
-  cpu_baseline   the oracle port of the reference algorithm (torch CPU ops + autograd, all host
-                 threads) on a reduced batch of the same workload.
-Multi-GPU: one process per GPU (torchrun), batch sharded = every rank runs the full per-GPU
-batch (weak scaling); the only collective is one NCCL all-reduce of the flat weight-gradient buffer.
+  cpu_baseline   the reference's own MaskCBAM class (oracle/_ref, laid out by oracle/build_ref.py;
+                 kind "reference") -- or, when oracle/_ref is absent, the oracle port (kind "port") --
+                 on the host cores, bounded sample of the same workload.
+  gpu_eager_baseline  the reference class .cuda() (eager PyTorch kernels) on the same B200, same tensors:
+                 the like-for-like GPU comparator of SURVEY.md section 8d.
+  workloads      the other single-GPU BASELINE configs (cfg3 = configs[2] shapes, cfg5 = configs[4]
+                 shapes), same step, same timing rules, fewer timed steps.
+Multi-GPU: one process per GPU (torchrun).  --scaling weak (default): every rank runs the full per-GPU
+batch; --scaling strong: the workload's GLOBAL batch is sharded (BASELINE configs[2]: 256 -> 128/64/32).
+The only collective is one NCCL all-reduce of the flat weight-gradient buffer.
 """
 from __future__ import annotations
 
@@ -141,37 +147,73 @@ class ClockSampler(threading.Thread):
                 "samples": len(win), "power_w_max": round(max(s[4] for s in win), 1)}
 
 
-# --------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_port_step(levels, B, dtype, sam_cam, threads):
-    """Build closures running the oracle port of the reference algorithm on CPU tensors."""
-    from oracle import cbam_oracle as co
+# --------------------------------------------------------------------------- parameters / CPU arm
+def make_params(Cc, r=16, k=7, beta=0.0):
+    """Deterministic parameter values: the block's own default init (== the reference's init order, masked_cbam.py:53-64)
+    under torch.manual_seed(C).  Returned in state_dict order of the flat gradient buffer: w1, b1, w2, b2, wsam, beta."""
+    from mga_yolo_b200 import MaskGuidedCBAM
 
+    torch.manual_seed(Cc)
+    m = MaskGuidedCBAM(Cc, r=r, spatial_k=k)
+    with torch.no_grad():
+        m.beta.fill_(beta)
+    return [t.detach().clone() for t in (m.cam_mlp[0].weight, m.cam_mlp[0].bias, m.cam_mlp[2].weight, m.cam_mlp[2].bias, m.sam_conv.weight, m.beta)]
+
+
+def reference_available():
+    try:
+        from oracle import build_ref
+        return build_ref.available()
+    except Exception:
+        return False
+
+
+def cpu_step_fn(levels, B, dtype, sam_cam, threads):
+    """fwd+bwd of the three levels on CPU tensors.  kind "reference": the reference's MaskCBAM class itself (oracle/_ref) with
+    torch autograd -- only for the reference-equivalent fusion mode; kind "port": oracle/cbam_oracle.py."""
     torch.set_num_threads(threads)
-    work = []
     gen = torch.Generator().manual_seed(0)
+    use_ref = reference_available() and sam_cam == "multiply"
+    work = []
+    if use_ref:
+        from oracle import build_ref
+
+        ref = build_ref.load()
+    else:
+        from oracle import cbam_oracle as co
     for (Cc, H, W) in levels:
         x = torch.randn(B, Cc, H, W, generator=gen).to(dtype).float()
         mk = torch.randn(B, 1, H, W, generator=gen)
         g = torch.randn(B, Cc, H, W, generator=gen)
-        p = co.default_params(Cc, seed=Cc)
-        leaves = [t.clone().requires_grad_(True) for t in (p.w1, p.b1, p.w2, p.b2, p.wsam, p.beta)]
-        work.append((x, mk, g, leaves))
+        w1, b1, w2, b2, wsam, beta = make_params(Cc)
+        if use_ref:
+            mod = ref.MaskCBAM(Cc)
+            mod.load_state_dict({"cam_mlp.0.weight": w1, "cam_mlp.0.bias": b1, "cam_mlp.2.weight": w2, "cam_mlp.2.bias": b2,
+                                 "sam_conv.weight": wsam, "beta": beta})
+            work.append((x, mk, g, mod))
+        else:
+            leaves = [t.clone().requires_grad_(True) for t in (w1, b1, w2, b2, wsam, beta)]
+            work.append((x, mk, g, leaves))
 
     def step():
-        for x, mk, g, leaves in work:
+        for x, mk, g, obj in work:
             xi = x.clone().requires_grad_(True)
             mi = mk.clone().requires_grad_(True)
-            out = co.cbam_forward_autograd(xi, mi, co.CbamParams(*leaves), sam_cam_fusion=sam_cam)
-            out.backward(g)
-            for leaf in leaves:
-                leaf.grad = None
+            if use_ref:
+                obj([xi, mi]).backward(g)
+                obj.zero_grad(set_to_none=True)
+            else:
+                out = co.cbam_forward_autograd(xi, mi, co.CbamParams(*obj), sam_cam_fusion=sam_cam)
+                out.backward(g)
+                for leaf in obj:
+                    leaf.grad = None
 
-    return step
+    return step, ("reference" if use_ref else "port")
 
 
 def time_cpu(levels, B, dtype, sam_cam, steps, warmup):
     threads = os.cpu_count() or 1
-    step = cpu_port_step(levels, B, dtype, sam_cam, threads)
+    step, kind = cpu_step_fn(levels, B, dtype, sam_cam, threads)
     for _ in range(warmup):
         step()
     ts = []
@@ -179,7 +221,7 @@ def time_cpu(levels, B, dtype, sam_cam, steps, warmup):
         t0 = time.perf_counter()
         step()
         ts.append(time.perf_counter() - t0)
-    return sum(ts) / len(ts), threads
+    return sum(ts) / len(ts), threads, kind
 
 
 # --------------------------------------------------------------------------- GPU arm (C ABI, resident inputs)
@@ -188,7 +230,6 @@ class LevelPlan:
 
     def __init__(self, lib_mod, Cc, H, W, B, dtype, flags, dev, seed, grads_flat, goff):
         from mga_yolo_b200 import _lib
-        from oracle import cbam_oracle as co  # only for deterministic parameter values (same as the CPU arm)
 
         self.lib = _lib.load()
         self._lib = _lib
@@ -200,8 +241,7 @@ class LevelPlan:
         self.out = torch.empty_like(self.x)
         self.dx = torch.empty_like(self.x)
         self.dmask = torch.empty_like(self.mask)
-        p = co.default_params(Cc, seed=Cc)
-        self.params = [t.to(dev).contiguous() for t in (p.w1, p.b1, p.w2, p.b2, p.wsam, p.beta)]
+        self.params = [t.to(dev).contiguous() for t in make_params(Cc)]
         hidden = self.params[0].shape[0]
         dt_code = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}[dtype]
         self.desc = _lib.Desc(B, Cc, H, W, hidden, 7, dt_code, _lib.F32, flags | _lib.HAS_MASK | _lib.SIGMOID_MASK, 1e-4, 1e-6)
@@ -270,108 +310,92 @@ def run_step_streams(plans, main, sides):
             main.wait_stream(s)
 
 
-def gpu_arm(args, rank, world, local_rank):
+def measure(args, lib, dev, world, levels, B, dtype, flags, steps, warmup, one_stream=False, instrument=True):
+    """Time `steps` fwd+bwd steps of one workload (CUDA events on the launching stream, max over ranks) and, in an
+    instrumented pass right after, every kernel of the step (events around each launch, one stream)."""
     import torch.distributed as dist
 
     from mga_yolo_b200 import _lib
 
-    lib = _lib.load()
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    levels, B, dtname, desc_txt = WORKLOADS[args.workload]
-    if args.batch:
-        B = args.batch
-    dtype = DT[dtname]
-    esize = torch.empty((), dtype=dtype).element_size()
+    sets = build_plans(levels, B, dtype, flags, dev, nsets=2)
+    stream = torch.cuda.current_stream(dev)
+    sptr = stream.cuda_stream
+    sides = [torch.cuda.Stream(dev) for _ in levels[1:]] if not (args.one_stream or one_stream) else []
 
-    def flags_of(scf, split=False):
-        f = _lib.SAMCAM_ADD if scf == "add" else 0
-        return f | (_lib.FORCE_SPLIT if (args.force_split or split) else 0)
+    def step_on(plans, main):
+        if sides:
+            run_step_streams(plans, main, sides)
+        else:
+            run_step(plans, main.cuda_stream)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    alg_bytes = algorithmic_bytes(levels, B, esize)
-    results = {}
+    # warm-up (un-graphed) also gives launches per step
+    torch.cuda.synchronize(dev)
+    n0 = lib.mga_launch_count()
+    run_step(sets[0][0], sptr)
+    launches_per_step = lib.mga_launch_count() - n0
+    run_step(sets[1][0], sptr)
+    torch.cuda.synchronize(dev)
+    graphs = None
+    if not args.no_graph:
+        try:
+            graphs = []
+            for plans, _flat in sets:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    step_on(plans, torch.cuda.current_stream(dev))
+                graphs.append(g)
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] CUDA graph capture failed ({e}); timing direct launches", file=sys.stderr)
+            graphs = None
 
-    def measure(scf, steps, warmup, split=False):
-        sets = build_plans(levels, B, dtype, flags_of(scf, split), dev, nsets=2)
-        stream = torch.cuda.current_stream(dev)
-        sptr = stream.cuda_stream
-        sides = [torch.cuda.Stream(dev) for _ in levels[1:]] if not args.one_stream else []
+    pending = [None, None]  # all-reduce in flight on each buffer set
 
-        def step_on(plans, main):
-            if sides:
-                run_step_streams(plans, main, sides)
-            else:
-                run_step(plans, main.cuda_stream)
-
-        # warm-up (un-graphed) also gives launches per step
-        torch.cuda.synchronize(dev)
-        n0 = lib.mga_launch_count()
-        run_step(sets[0][0], sptr)
-        launches_per_step = lib.mga_launch_count() - n0
-        run_step(sets[1][0], sptr)
-        torch.cuda.synchronize(dev)
-        graphs = None
-        if not args.no_graph:
-            try:
-                graphs = []
-                for plans, _flat in sets:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        step_on(plans, torch.cuda.current_stream(dev))
-                    graphs.append(g)
-            except Exception as e:  # pragma: no cover
-                print(f"[bench] CUDA graph capture failed ({e}); timing direct launches", file=sys.stderr)
-                graphs = None
-
-        pending = [None, None]  # all-reduce in flight on each buffer set
-
-        def one(i):
-            if pending[i & 1] is not None:  # this set's previous gradients must have been reduced before they are overwritten
-                pending[i & 1].wait()
-                pending[i & 1] = None
-            if graphs is not None:
-                graphs[i & 1].replay()
-            else:
-                step_on(sets[i & 1][0], stream)
-            if world > 1:
-                # the only collective: the flat weight-gradient buffer; asynchronous (NCCL's stream waits for this step's kernels,
-                # the next step's kernels -- on the other buffer set -- do not wait for NCCL), like DDP's bucket overlap
-                pending[i & 1] = dist.all_reduce(sets[i & 1][1], async_op=True)
-
-        def drain():
-            for k in (0, 1):
-                if pending[k] is not None:
-                    pending[k].wait()
-                    pending[k] = None
-
-        for i in range(warmup):
-            one(i)
-        drain()
-        torch.cuda.synchronize(dev)
+    def one(i):
+        if pending[i & 1] is not None:  # this set's previous gradients must have been reduced before they are overwritten
+            pending[i & 1].wait()
+            pending[i & 1] = None
+        if graphs is not None:
+            graphs[i & 1].replay()
+        else:
+            step_on(sets[i & 1][0], stream)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_wall0 = time.time()
-        e0.record()
-        for i in range(steps):
-            one(i)
-        drain()  # every all-reduce of the timed steps is inside the timed region
-        e1.record()
-        torch.cuda.synchronize(dev)
-        t_wall1 = time.time()
-        if world > 1:
-            dist.barrier()
-        ms = e0.elapsed_time(e1) / steps
-        if world > 1:
-            tmax = torch.tensor([ms], device=dev)
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            ms = float(tmax.item())
+            # the only collective: the flat weight-gradient buffer; asynchronous (NCCL's stream waits for this step's kernels,
+            # the next step's kernels -- on the other buffer set -- do not wait for NCCL), like DDP's bucket overlap
+            pending[i & 1] = dist.all_reduce(sets[i & 1][1], async_op=True)
 
-        # instrumented pass: per-kernel CUDA events (same buffers, direct launches, one stream); every record is tagged
-        # with the level whose call produced it
+    def drain():
+        for k in (0, 1):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
+
+    for i in range(warmup):
+        one(i)
+    drain()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(steps):
+        one(i)
+    drain()  # every all-reduce of the timed steps is inside the timed region
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t_wall1 = time.time()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+
+    klist = []
+    if instrument:
+        # per-kernel CUDA events (same buffers, direct launches, one stream); every record is tagged with the level whose call produced it
         lib.mga_profile_enable(1)
         reps = 5
         tags = []
@@ -398,34 +422,12 @@ def gpu_arm(args, rank, world, local_rank):
         lib.mga_profile_enable(0)
         klist = [{"kernel": nm, "li": li, "phase": phase, "ms": sum(per_kernel[(phase, li, nm)]) / len(per_kernel[(phase, li, nm)])}
                  for (phase, li, nm) in order_keys]
-        return {"ms": ms, "launches_per_step": int(launches_per_step), "graph": graphs is not None, "kernels": klist,
-                "streams": 1 + len(sides),
-                "wall": (t_wall0, t_wall1), "sets": sets}
+    return {"ms": ms, "launches_per_step": int(launches_per_step), "graph": graphs is not None, "kernels": klist,
+            "streams": 1 + len(sides), "wall": (t_wall0, t_wall1), "sets": sets}
 
-    main = measure(args.sam_cam_fusion, args.steps, args.warmup)
-    t0w, t1w = main["wall"]
-    # keep the GPU busy long enough for the clock sampler when the timed region is short
-    if t1w - t0w < 1.0:
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        tb = time.time()
-        while time.time() - tb < 1.0:
-            for _ in range(20):
-                run_step(main["sets"][0][0], stream)
-            torch.cuda.synchronize(dev)
-        t1w = time.time()
-    other = "add" if args.sam_cam_fusion == "multiply" else "multiply"
-    variant = measure(other, max(10, args.steps // 2), max(3, args.warmup)) if not args.no_variant else None
-    # the other launch path of the library (one kernel per phase), same step, same timing rules
-    variant_split = measure(args.sam_cam_fusion, max(10, args.steps // 2), max(3, args.warmup), split=True) \
-        if not (args.no_variant or args.force_split) else None
 
-    # ---- roofline of the dominant kernel
-    peaks_path = ROOT / "MEASURED_PEAKS.json"
-    if peaks_path.exists():
-        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
-    else:
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (of fallback)"
-    klist = main["kernels"]
+def annotate_kernels(klist, levels, B, esize, peak):
+    """Algorithmic bytes / GB/s per kernel record; returns the dominant (longest) one."""
     best = None
     for k in klist:
         Cc, H, W = levels[k["li"]]
@@ -436,13 +438,75 @@ def gpu_arm(args, rank, world, local_rank):
             continue
         k["alg_bytes"] = fn(N, BS, esize)
         k["gbps"] = k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9
+        k["frac"] = k["gbps"] / peak
         if best is None or k["ms"] > best["ms"]:
             best = k
+    return best
+
+
+def gpu_arm(args, rank, world, local_rank):
+    from mga_yolo_b200 import _lib
+
+    lib = _lib.load()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    levels, Bglobal, dtname, desc_txt = WORKLOADS[args.workload]
+    if args.batch:
+        Bglobal = args.batch
+    strong = args.scaling == "strong"
+    if strong and Bglobal % world:
+        raise SystemExit(f"--scaling strong: the global batch {Bglobal} does not divide over {world} ranks")
+    B = Bglobal // world if strong else Bglobal
+    dtype = DT[dtname]
+    esize = torch.empty((), dtype=dtype).element_size()
+
+    def flags_of(scf, split=False):
+        f = _lib.SAMCAM_ADD if scf == "add" else 0
+        return f | (_lib.FORCE_SPLIT if (args.force_split or split) else 0)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    alg_bytes = algorithmic_bytes(levels, B, esize)
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (of fallback)"
+
+    main = measure(args, lib, dev, world, levels, B, dtype, flags_of(args.sam_cam_fusion), args.steps, args.warmup)
+    t0w, t1w = main["wall"]
+    # keep the GPU busy long enough for the clock sampler when the timed region is short
+    if t1w - t0w < 1.0:
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        tb = time.time()
+        while time.time() - tb < 1.0:
+            for _ in range(20):
+                run_step(main["sets"][0][0], stream)
+            torch.cuda.synchronize(dev)
+        t1w = time.time()
+    main["sets"] = None
+    short = (max(10, args.steps // 2), max(3, args.warmup))
+    other = "add" if args.sam_cam_fusion == "multiply" else "multiply"
+    variant = None if args.no_variant else measure(args, lib, dev, world, levels, B, dtype, flags_of(other), *short, instrument=False)
+    # the other launch path of the library (one kernel per phase), same step, same timing rules
+    variant_split = None if (args.no_variant or args.force_split) else \
+        measure(args, lib, dev, world, levels, B, dtype, flags_of(args.sam_cam_fusion, split=True), *short, instrument=False)
+    # the same step issued on ONE stream (the order an nn.Module caller gets), graph replay
+    one_stream = None if (args.no_variant or args.one_stream) else \
+        measure(args, lib, dev, world, levels, B, dtype, flags_of(args.sam_cam_fusion), *short, one_stream=True, instrument=False)
+    for v in (variant, variant_split, one_stream):
+        if v is not None:
+            v["sets"] = None
+    torch.cuda.empty_cache()
+
+    # ---- roofline of the dominant kernel
+    klist = main["kernels"]
+    best = annotate_kernels(klist, levels, B, esize, peak)
     roofline = None
     traffic = None
     tpath = ROOT / "profiles" / "traffic.json"
     if best and tpath.exists():  # dram bytes per launch from the committed ncu --set full capture of the same kernel/shape
-        traffic = json.loads(tpath.read_text()).get(f"{best['kernel']}[{best['level']}]") if args.workload == "cfg2" else None
+        traffic = json.loads(tpath.read_text()).get(f"{best['kernel']}[{best['level']}]") if (args.workload == "cfg2" and not strong and not args.batch) else None
     if best:
         roofline = {"bound": "hbm", "kernel": f"{best['kernel']}[{best['level']}]", "achieved": round(best["gbps"], 1), "peak": peak,
                     "unit": "GB/s", "frac": round(best["gbps"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
@@ -451,33 +515,33 @@ def gpu_arm(args, rank, world, local_rank):
                     "step_frac_of_8TBps_nominal": round(alg_bytes / (main["ms"] * 1e-3) / 1e9 / 8000.0, 4)}
 
     # ---- e2e: public module API, host buffers
-    e2e = None if args.no_e2e else e2e_module(args, dev, levels, B, dtype, world, alg_bytes)
+    e2e = None if args.no_e2e else e2e_module(args, dev, local_rank, levels, B, dtype, world, alg_bytes)
 
     sampler.stop()
     clocks = sampler.summary(t0w, t1w)
     value = world * alg_bytes / (main["ms"] * 1e-3) / 1e9
+    nparams = sum(LevelPlan.n_params(c) for c, _, _ in levels)
     line = {
         "metric": "mga_cbam_fwd_bwd_algorithmic_GBps", "value": round(value, 1), "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(main["ms"], 5), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": {"float32": "f32", "bfloat16": "bf16", "float16": "f16"}[dtname],
-        "data": "synthetic (x, grad_out ~ N(0,1); mask logits ~ N(0,1); reference-default parameter init, seed = C)",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": {"float32": "f32", "bfloat16": "bf16", "float16": "f16"}[dtname],
+        "data": "synthetic (x, grad_out ~ N(0,1); mask logits ~ N(0,1); the block's reference-order default parameter init under torch.manual_seed(C))",
         "images_per_sec": round(world * B / (main["ms"] * 1e-3), 1),
         "config": {"workload": desc_txt, "levels_CHW": levels, "batch_per_gpu": B, "global_batch": B * world,
-                   "sam_cam_fusion": args.sam_cam_fusion, "mga_pyramid_fusion": "add", "parallelism": f"dp{world} (batch sharded; all-reduce of {sum(LevelPlan.n_params(c) for c,_,_ in levels)} fp32 weight grads)",
-                   "l2": "two rotating input/output sets per level (2 x 0.73 GB touched per pair of steps) >> 126 MB L2",
+                   "sam_cam_fusion": args.sam_cam_fusion, "mga_pyramid_fusion": "add",
+                   "parallelism": f"dp{world} (batch sharded, {args.scaling} scaling; all-reduce of {nparams} fp32 weight grads)",
+                   "l2": "two rotating input/output sets per level (>= 0.73 GB touched per pair of steps) >> 126 MB L2",
                    "cuda_graph": main["graph"], "streams": main["streams"], "algorithmic_bytes_per_step": alg_bytes,
-                   "launch_path": "one kernel per phase (MGA_FORCE_SPLIT)" if args.force_split else "cluster-per-sample fused kernels (cl_fwd / cl_bwd) + bwd_wgrad; shapes the cluster path does not take fall back to one kernel per phase",
+                   "launch_path": "one kernel per phase (MGA_FORCE_SPLIT)" if args.force_split else "cluster-per-sample kernels (cl_fwd / cl_bwd) + bwd_wgrad; shapes the cluster path does not take fall back to one kernel per phase",
                    "step_order": "forward of all levels (one stream per level), join, backward of all levels, join"},
         "gpu_launches": main["launches_per_step"] * args.steps,
         "launches_per_step": main["launches_per_step"],
         "roofline": roofline,
-        "kernels": [{"kernel": k["kernel"], "level": k["level"], "ms": round(k["ms"], 5), "gbps": round(k.get("gbps", 0.0), 1)} for k in klist],
+        "kernels": [{"kernel": k["kernel"], "level": k["level"], "ms": round(k["ms"], 5), "gbps": round(k.get("gbps", 0.0), 1),
+                     "frac": round(k.get("frac", 0.0), 4)} for k in klist],
         "e2e": e2e,
         "clocks": clocks,
     }
-    if rank == 0 and world == 1 and not args.no_cpu and args.workload == "cfg2":
-        line["mask_pipeline"] = mask_pipeline(dev, B, 640, peak)
-        line["inference_b1"] = inference_b1(dev, levels, dtype, os.cpu_count() or 1)
     if variant is not None:
         line["variants"] = {other: {"ms_per_step": round(variant["ms"], 5), "value": round(world * alg_bytes / (variant["ms"] * 1e-3) / 1e9, 1),
                                     "images_per_sec": round(world * B / (variant["ms"] * 1e-3), 1),
@@ -487,25 +551,134 @@ def gpu_arm(args, rank, world, local_rank):
             "ms_per_step": round(variant_split["ms"], 5), "value": round(world * alg_bytes / (variant_split["ms"] * 1e-3) / 1e9, 1),
             "launches_per_step": variant_split["launches_per_step"],
             "note": "MGA_FORCE_SPLIT: 12 kernels per level and direction; HBM traffic 10N instead of 5N"}
+    if one_stream is not None:
+        line.setdefault("variants", {})["one_stream"] = {
+            "ms_per_step": round(one_stream["ms"], 5), "value": round(world * alg_bytes / (one_stream["ms"] * 1e-3) / 1e9, 1),
+            "note": "the same step issued on ONE stream (fwd P3,P4,P5 then bwd P5,P4,P3), CUDA graph replay: what a training loop's module calls give"}
     if args.sam_cam_fusion == "add":
         line["config"]["note"] = "oracle: in-repo PyTorch composition; reference parity unpinned"
-    if rank == 0 and world == 1 and not args.no_cpu:
+    solo = rank == 0 and world == 1 and not args.batch
+    if solo and not args.no_cpu and args.workload == "cfg2":
+        line["mask_pipeline"] = mask_pipeline(dev, B, 640, peak)
+        line["inference_b1"] = inference_b1(dev, levels, dtype, os.cpu_count() or 1)
+    if solo and not args.no_workloads and args.workload == "cfg2":
+        # the other BASELINE configs that fit one GPU: same step, same rules, fewer timed steps
+        wl = {}
+        for name in ("cfg3", "cfg5"):
+            lv, Bw, dn, txt = WORKLOADS[name]
+            dtw = DT[dn]
+            ew = torch.empty((), dtype=dtw).element_size()
+            r = measure(args, lib, dev, world, lv, Bw, dtw, flags_of(args.sam_cam_fusion), 10, 3)
+            r["sets"] = None
+            torch.cuda.empty_cache()
+            ab = algorithmic_bytes(lv, Bw, ew)
+            bw = annotate_kernels(r["kernels"], lv, Bw, ew, peak)
+            wl[name] = {"workload": txt, "levels_CHW": lv, "batch": Bw, "dtype": dn, "ms_per_step": round(r["ms"], 5), "steps": 10, "warmup": 3,
+                        "value": round(ab / (r["ms"] * 1e-3) / 1e9, 1), "unit": "GB/s", "images_per_sec": round(Bw / (r["ms"] * 1e-3), 1),
+                        "step_frac": round(ab / (r["ms"] * 1e-3) / 1e9 / peak, 4), "launches_per_step": r["launches_per_step"],
+                        "algorithmic_bytes_per_step": ab,
+                        "dominant_kernel": None if bw is None else {"kernel": f"{bw['kernel']}[{bw['level']}]", "ms": round(bw["ms"], 5),
+                                                                     "achieved": round(bw["gbps"], 1), "frac": round(bw["frac"], 4)},
+                        "kernels": [{"kernel": k["kernel"], "level": k["level"], "ms": round(k["ms"], 5), "frac": round(k.get("frac", 0.0), 4)} for k in r["kernels"]]}
+        line["workloads"] = wl
+    if solo and not args.no_cpu:
+        line["gpu_eager_baseline"] = gpu_eager_baseline(dev, levels, B, dtype, alg_bytes, args.sam_cam_fusion)
         cb = 16 if args.workload == "cfg2" else 8
-        sec, threads = time_cpu(levels, cb, dtype, args.sam_cam_fusion, steps=3, warmup=1)
+        sec, threads, kind = time_cpu(levels, cb, dtype, args.sam_cam_fusion, steps=3, warmup=1)
         cbytes = algorithmic_bytes(levels, cb, esize)
-        line["cpu_baseline"] = {"value": round(cbytes / sec / 1e9, 3), "unit": "GB/s", "cores": threads, "kind": "port",
-                                "sample": f"same workload at batch {cb} (3 timed steps after 1 warm-up, {sec*1e3:.1f} ms/step); oracle/cbam_oracle.py forward + torch autograd backward",
+        line["cpu_baseline"] = {"value": round(cbytes / sec / 1e9, 3), "unit": "GB/s", "cores": threads, "kind": kind,
+                                "sample": f"same workload at batch {cb} (3 timed steps after 1 warm-up, {sec*1e3:.1f} ms/step); "
+                                          + ("the reference's MaskCBAM class (oracle/_ref) forward + torch autograd backward on CPU tensors" if kind == "reference"
+                                             else "oracle/cbam_oracle.py forward + torch autograd backward"),
                                 "images_per_sec": round(cb / sec, 1)}
     return line
 
 
-def e2e_module(args, dev, levels, B, dtype, world, alg_bytes):
-    """Public API path: pinned host inputs -> H2D -> MaskGuidedCBAM forward -> autograd backward -> grads D2H."""
+def gpu_eager_baseline(dev, levels, B, dtype, alg_bytes, sam_cam):
+    """SURVEY.md section 8d's like-for-like comparator: the reference's MaskCBAM class (oracle/_ref) moved to the same B200 and run
+    with eager PyTorch kernels (forward + autograd backward) on tensors of the same shapes.  ~200 ATen launches per level and direction."""
+    if not reference_available() or sam_cam != "multiply":
+        return {"unavailable": "oracle/_ref not built" if sam_cam == "multiply" else "the reference has no sam_cam_fusion=add"}
+    from oracle import build_ref
+
+    ref = build_ref.load()
+    work = []
+    gen = torch.Generator(device=dev).manual_seed(11)
+    for (Cc, H, W) in levels:
+        mod = ref.MaskCBAM(Cc)
+        w1, b1, w2, b2, wsam, beta = make_params(Cc)
+        mod.load_state_dict({"cam_mlp.0.weight": w1, "cam_mlp.0.bias": b1, "cam_mlp.2.weight": w2, "cam_mlp.2.bias": b2, "sam_conv.weight": wsam, "beta": beta})
+        mod = mod.to(dev)
+        x = torch.randn(B, Cc, H, W, generator=gen, device=dev).to(dtype)
+        mk = torch.randn(B, 1, H, W, generator=gen, device=dev).to(dtype)
+        g = torch.randn(B, Cc, H, W, generator=gen, device=dev).to(dtype)
+        if dtype != torch.float32:
+            mod = mod.to(dtype)  # module.bfloat16(): the reference's low-precision mode (SURVEY 8c)
+        work.append((mod, x, mk, g))
+
+    def step():
+        for mod, x, mk, g in work:
+            xi = x.detach().requires_grad_(True)
+            mi = mk.detach().requires_grad_(True)
+            mod([xi, mi]).backward(g)
+            mod.zero_grad(set_to_none=True)
+
+    try:
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+    except Exception as e:  # pragma: no cover  (e.g. out of memory at a large workload)
+        return {"unavailable": repr(e)[:200]}
+    finally:
+        work.clear()
+        torch.cuda.empty_cache()
+    return {"ms_per_step": round(ms, 4), "value": round(alg_bytes / (ms * 1e-3) / 1e9, 1), "unit": "GB/s", "images_per_sec": round(B / (ms * 1e-3), 1),
+            "steps": reps, "kind": "reference class on cuda:0, eager PyTorch (ATen/cuDNN kernels), same shapes and dtype, inputs resident in HBM"}
+
+
+def bind_to_gpu_numa(local_rank):
+    """Best effort: run this process on the CPUs of the NUMA node the GPU hangs off, BEFORE the pinned host buffers are
+    allocated and first touched, so each rank's staging memory is local to its PCIe root (8 ranks x 0.7 GB/step otherwise share
+    one socket's memory system).  Returns the node or None."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        devid = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/numa_node"
+        node = int(Path(path).read_text().strip())
+        if node < 0:
+            return None
+        cpus = Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        allowed = ids & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
+def e2e_module(args, dev, local_rank, levels, B, dtype, world, alg_bytes):
+    """Public API path with HOST buffers in and out: pinned host x / mask / grad_out -> H2D -> MaskGuidedCBAM forward ->
+    autograd backward -> out, dx, dmask and the flat weight gradients -> D2H into pinned host memory.  Everything a caller of the
+    reference's CPU path holds in host memory after a step is in host memory here too."""
     import torch.distributed as dist
 
     from mga_yolo_b200 import FlatGradReducer, MaskGuidedCBAM
 
-    mods, host, devb = [], [], []
+    numa = bind_to_gpu_numa(local_rank)
+    mods, host, devb, hres = [], [], [], []
     gen = torch.Generator().manual_seed(5)
     for (Cc, H, W) in levels:
         torch.manual_seed(Cc)
@@ -516,22 +689,26 @@ def e2e_module(args, dev, levels, B, dtype, world, alg_bytes):
         hg = torch.randn(B, Cc, H, W, generator=gen).to(dtype).pin_memory()
         host.append((hx, hm, hg))
         devb.append((torch.empty_like(hx, device=dev), torch.empty_like(hm, device=dev), torch.empty_like(hg, device=dev)))
+        hres.append((torch.empty_like(hx).pin_memory(), torch.empty_like(hx).pin_memory(), torch.empty_like(hm).pin_memory()))  # out, dx, dmask
     reducer = FlatGradReducer([p for m in mods for p in m.parameters()])
     hgrad = torch.empty(reducer.numel, dtype=torch.float32).pin_memory()
     h2d = sum(t.numel() * t.element_size() for trip in host for t in trip)
-    d2h = hgrad.numel() * 4
+    d2h_full = hgrad.numel() * 4 + sum(t.numel() * t.element_size() for trip in hres for t in trip)
 
     # Input pipeline of a training loop: the host->device copies run on their own stream, level by level; the compute stream
-    # waits for the copy of ITS level only, so the copies of the later levels (and of the next step) overlap the kernels.
-    # Each device buffer is rewritten only after the kernels that read it have finished (ev_done).
+    # waits for the copy of ITS level only, so the copies of the later levels (and of the next step) overlap the kernels; the
+    # results leave on a third stream (PCIe is full duplex).  Each device buffer is rewritten only after its readers finished.
     main_s = torch.cuda.current_stream(dev)
     copy_s = torch.cuda.Stream(dev)
+    back_s = torch.cuda.Stream(dev)
     ev_copied = [torch.cuda.Event() for _ in levels]
     ev_done = [torch.cuda.Event() for _ in levels]
-    for e in ev_done:
+    ev_back = [torch.cuda.Event() for _ in levels]
+    for e in ev_done + ev_back:
         e.record(main_s)
+    keep = [None] * len(levels)  # results of the previous step stay alive until their D2H copy has been issued
 
-    def step():
+    def step(full):
         with torch.cuda.stream(copy_s):
             for li, ((hx, hm, hg), (dx_, dm_, dg_)) in enumerate(zip(host, devb)):
                 copy_s.wait_event(ev_done[li])
@@ -545,37 +722,62 @@ def e2e_module(args, dev, levels, B, dtype, world, alg_bytes):
             min_ = dm_.requires_grad_(True)
             out = m([xin, min_])
             torch.autograd.backward(out, dg_, inputs=[xin, min_, *m.parameters()])
+            gx, gm = xin.grad, min_.grad
             xin.grad = None
             min_.grad = None
             dx_.requires_grad_(False)
             dm_.requires_grad_(False)
             ev_done[li].record(main_s)
+            if full:
+                ho, hdx, hdm = hres[li]
+                back_s.wait_event(ev_done[li])
+                with torch.cuda.stream(back_s):
+                    ho.copy_(out.detach(), non_blocking=True)
+                    hdx.copy_(gx, non_blocking=True)
+                    hdm.copy_(gm, non_blocking=True)
+                    for t in (out, gx, gm):
+                        t.record_stream(back_s)
+                    ev_back[li].record(back_s)
+            keep[li] = (out, gx, gm)
         if world > 1:
             reducer.all_reduce()
         hgrad.copy_(reducer.flat, non_blocking=True)
 
-    steps = max(5, min(args.steps, 20))
-    for _ in range(3):
-        reducer.zero()
-        step()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        reducer.zero()
-        step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / steps
-    if world > 1:
-        tmax = torch.tensor([ms], device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
-    return {"value": round(world * alg_bytes / (ms * 1e-3) / 1e9, 2), "unit": "GB/s", "ms_per_step": round(ms, 4), "steps": steps,
-            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "images_per_sec": round(world * B / (ms * 1e-3), 1),
-            "api": "mga_yolo_b200.MaskGuidedCBAM forward + torch.autograd backward, pinned host x/mask/grad_out in (copy stream, overlapped with the kernels of the previous level), flat weight grads out"}
+    def timed(full):
+        steps = max(5, min(args.steps, 20))
+        for _ in range(3):
+            reducer.zero()
+            step(full)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            reducer.zero()
+            step(full)
+        for e in ev_back:
+            main_s.wait_event(e)  # the closing event is after the last result has reached host memory
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            tmax = torch.tensor([ms], device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ms = float(tmax.item())
+        return ms, steps
+
+    ms_full, steps = timed(True)
+    ms_grads, _ = timed(False)
+    return {"value": round(world * alg_bytes / (ms_full * 1e-3) / 1e9, 2), "unit": "GB/s", "ms_per_step": round(ms_full, 4), "steps": steps,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full, "images_per_sec": round(world * B / (ms_full * 1e-3), 1),
+            "numa_node_of_pinned_buffers": numa,
+            "api": "mga_yolo_b200.MaskGuidedCBAM forward + torch.autograd backward; pinned host x/mask/grad_out in (copy stream, overlapped with the kernels "
+                   "of the previous level); out, dx, dmask and the flat weight grads back to pinned host memory (second copy stream, full duplex)",
+            "result_stays_on_device": {"value": round(world * alg_bytes / (ms_grads * 1e-3) / 1e9, 2), "ms_per_step": round(ms_grads, 4),
+                                       "d2h_bytes_per_step": hgrad.numel() * 4,
+                                       "note": "same step when only the weight gradients return to the host (out feeds Detect and dx the neck's backward on the device, "
+                                               "as inside the reference's training step)"}}
 
 
 def mask_pipeline(dev, B, imgsz, peak):
@@ -607,18 +809,28 @@ def mask_pipeline(dev, B, imgsz, peak):
     ms_one = timed(lambda m: MaskUtils.masks_multi(m))
     ms_per = timed(lambda m: [MaskUtils.downsample_mask(m, s) for s in (8, 16, 32)])
     host = bufs[0][:8].cpu().numpy()
+    kind, fn = "port", mo.downsample_mask
+    if reference_available():
+        try:  # the reference's own MaskUtils (three cv2 calls per sample in the dataloader workers, dataset.py:95-103)
+            from oracle import build_ref
+
+            kind, fn = "reference", build_ref.load().MaskUtils.downsample_mask
+            fn(host[0], 8)
+        except Exception:
+            kind, fn = "port", mo.downsample_mask
     t0 = time.perf_counter()
     for b in range(host.shape[0]):
         for s in (8, 16, 32):
-            mo.downsample_mask(host[b], s)
+            fn(host[b], s)
     cpu_s = (time.perf_counter() - t0) / host.shape[0]
     return {"workload": f"{B} binary masks {imgsz}x{imgsz} uint8 -> strides 8/16/32, default method (block max + 3x3 close)",
             "one_pass_ms": round(ms_one, 5), "per_stride_ms": round(ms_per, 5), "masks_per_sec": round(B / (ms_one * 1e-3), 1),
             "roofline": {"bound": "hbm", "achieved": round(alg / (ms_one * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(alg / (ms_one * 1e-3) / 1e9 / peak, 4), "alg_bytes_per_launch": alg,
                          "note": "one CTA per image: 64 CTAs on 148 SMs, launch-latency bound at this batch"},
-            "cpu_baseline": {"masks_per_sec": round(1.0 / cpu_s, 1), "cores": 1, "kind": "port",
-                             "sample": "8 masks, oracle/mask_oracle.py (numpy restatement of cv2.resize / morphologyEx)"}}
+            "cpu_baseline": {"masks_per_sec": round(1.0 / cpu_s, 1), "cores": 1, "kind": kind,
+                             "sample": "8 masks x 3 strides, " + ("the reference's MaskUtils.downsample_mask (cv2) from oracle/_ref" if kind == "reference"
+                                                                  else "oracle/mask_oracle.py (numpy restatement of cv2.resize / morphologyEx)")}}
 
 
 def inference_b1(dev, levels, dtype, threads):
@@ -661,7 +873,7 @@ def inference_b1(dev, levels, dtype, threads):
     torch.cuda.synchronize(dev)
     ms_eager = (time.perf_counter() - t0) / 50 * 1e3
     torch.set_num_threads(threads)
-    ps = [co.default_params(Cc, seed=Cc) for (Cc, _, _) in levels]
+    ps = [co.CbamParams(*make_params(Cc)) for (Cc, _, _) in levels]
     with torch.no_grad():
         for _ in range(2):
             [co.cbam_forward(x.float(), k, p)[0] for x, k, p in zip(xs, ms, ps)]
@@ -675,29 +887,36 @@ def inference_b1(dev, levels, dtype, threads):
 
 
 def reference_arm(args, rank):
-    """CPU arm: the oracle port of the reference's algorithm on the host cores, bounded sample."""
+    """CPU arm: the reference's own MaskCBAM class (oracle/_ref; the oracle port when that is absent or for the `add` mode,
+    which the reference does not have) on the host cores with all host threads.  cfg2 runs the FULL batch 64 and honours
+    --steps / --warmup (same config, same steps as the GPU arm); the larger workloads run a bounded batch-8 sample."""
     if rank != 0:
         return None
     levels, B, dtname, desc_txt = WORKLOADS[args.workload]
     dtype = DT[dtname]
     esize = torch.empty((), dtype=dtype).element_size()
-    cb = 16 if args.workload == "cfg2" else 8
-    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 3))
-    sec, threads = time_cpu(levels, cb, dtype, args.sam_cam_fusion, steps=steps, warmup=warmup)
+    cb = args.batch or (B if args.workload == "cfg2" else 8)
+    steps, warmup = args.steps, args.warmup
+    if args.workload != "cfg2":
+        steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 3))
+    sec, threads, kind = time_cpu(levels, cb, dtype, args.sam_cam_fusion, steps=steps, warmup=warmup)
     cbytes = algorithmic_bytes(levels, cb, esize)
     val = round(cbytes / sec / 1e9, 3)
-    sample = f"batch {cb} of the workload per step ({steps} timed steps after {warmup} warm-up), all host threads"
+    sample = f"batch {cb} of the workload per step ({steps} timed steps after {warmup} warm-up), all {threads} host threads"
     return {
         "impl": "reference", "metric": "mga_cbam_fwd_bwd_algorithmic_GBps", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (same generator as the GPU arm)",
+        "steps": steps, "warmup": warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": {"float32": "f32", "bfloat16": "bf16", "float16": "f16"}[dtname],
+        "data": "synthetic (same distributions and parameter values as the GPU arm)",
         "images_per_sec": round(cb / sec, 1),
-        "config": {"workload": desc_txt, "levels_CHW": levels, "batch_per_gpu": B, "sam_cam_fusion": args.sam_cam_fusion,
-                   "mga_pyramid_fusion": "add", "sample_batch": cb},
-        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": desc_txt, "levels_CHW": levels, "batch_per_gpu": cb, "global_batch": cb, "sam_cam_fusion": args.sam_cam_fusion,
+                   "mga_pyramid_fusion": "add"},
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the reference is pure Python/PyTorch and cannot travel to the GPU box; this is oracle/cbam_oracle.py (pinned against reference-generated goldens) with torch autograd backward",
+        "note": ("the reference's unmodified MaskCBAM class (mga_yolo/nn/modules/masked_cbam.py, laid out under oracle/_ref by oracle/build_ref.py) "
+                 "forward + torch autograd backward on CPU tensors") if kind == "reference" else
+                "oracle/cbam_oracle.py (pinned against reference-generated goldens) with torch autograd backward",
     }
 
 
@@ -716,6 +935,9 @@ def main():
     ap.add_argument("--no-variant", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer end-to-end measurement")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the cfg3 / cfg5 block of the default (cfg2) run")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank runs the workload's full batch; strong: the workload's batch is the GLOBAL batch, sharded over the ranks")
     ap.add_argument("--force-split", action="store_true", help="never use the cluster-resident fused kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -86,6 +86,7 @@ struct ClGeom {
     int smem_bytes;
     int stage_w;   // 1: the cam_mlp weight matrices are staged in shared memory (decided on the host: only when the second resident CTA per SM survives)
     int prefetch;  // 1: bulk L2 prefetch of the sample at kernel start, so the HBM stream overlaps the latency-bound prologue
+    int use_tma;   // backward: 1 = the padded [pmax, pavg, m] tile arrives by tensor-map TMA (host made the maps), 0 = plain loads
 };
 
 // the two weight matrices of the shared MLP may be staged in shared memory (16-byte cp.async copies) when they are small
@@ -119,7 +120,7 @@ __host__ __device__ inline ClFwdOff cl_fwd_off(int C, int Hd, const ClGeom& g) {
 }
 
 struct ClBwdOff {
-    int wsm, red, s, chA, chG, amx, cM, dz, eloc, qloc, binloc, dha, dhm, q, epart, qpart, binpart, gxpart;
+    int wsm, red, bar, s, chA, chG, amx, cM, dz, eloc, qloc, binloc, dha, dhm, q, epart, qpart, binpart, gxpart;
     int aloc, ae, mloc, idx, pmx, d0, d1s, d2, dpre, cat, tp, dwp, binw, stage, mlpw, total;
 };
 __host__ __device__ inline ClBwdOff cl_bwd_off(int C, int Hd, const ClGeom& g) {
@@ -128,6 +129,7 @@ __host__ __device__ inline ClBwdOff cl_bwd_off(int C, int Hd, const ClGeom& g) {
     auto take = [&p](int n) { const int r = p; p += (n + 3) & ~3; return r; };
     o.wsm = take(3 * kMaxK * kMaxK);
     o.red = take(64);  // 32 doubles
+    o.bar = take(4);   // two mbarriers: [0] context planes (bulk copies), [1] the [pmax, pavg, m] tile (tensor-map TMA)
     o.s = take(C);
     o.chA = take(4 * g.G * g.CG);  // group-major (A, B, q, cA)
     o.chG = take(g.G * g.CG);      // group-major cG
@@ -140,14 +142,21 @@ __host__ __device__ inline ClBwdOff cl_bwd_off(int C, int Hd, const ClGeom& g) {
     const int padP = g.LPT * g.K * 8;  // T1 footprint in pixels (>= nPmax), zero padded
     o.aloc = take(g.nPmax); o.ae = take(padP); o.mloc = take(g.nPmax); o.idx = take(g.nPmax); o.pmx = take(g.nPmax);
     o.d0 = take(g.nPmax); o.d1s = take(padP); o.d2 = take(g.nPmax);
+    p = (p + 31) & ~31;  // 128-byte alignment: TMA destinations
     o.dpre = take(g.planeT);
-    o.cat = take(3 * g.planeT);
-    int tpn = (g.slots > g.G ? g.slots : g.G) * g.nPmax;
-    if (tpn < 21 * 12 * kMaxK) tpn = 21 * 12 * kMaxK;
-    o.tp = take(tpn);          // T partials of the channel slots, then the dW team partials, then the R partials of the G channel groups
-    o.dwp = o.tp;
+    // One region, three tenants with disjoint lifetimes:
+    //   phase 1      : tp (T partials of the channel slots) | stage (per-channel thread partials)
+    //   phase 2      : cat = the [pmax, pavg, m] tile (lands asynchronously after the T merge) | dwp (dW team partials)
+    //   phase 3 / 5  : stage again (Q partials) / tp again (R partials of the G channel groups)
+    const int tpn = (((g.slots > g.G ? g.slots : g.G) * g.nPmax) + 3) & ~3;
+    const int stagen = (C * (g.LPT | 1) + 3) & ~3;
+    const int dwpn = 21 * 12 * kMaxK;
+    const int a = tpn + stagen, b = 3 * g.planeT + dwpn;
+    o.tp = take(a > b ? a : b);
+    o.stage = o.tp + tpn;
+    o.cat = o.tp;
+    o.dwp = o.cat + 3 * g.planeT;
     o.binw = take((g.NT / 32) * C);
-    o.stage = take(C * (g.LPT | 1));
     o.mlpw = g.stage_w ? take(2 * C * Hd) : -1;  // cam_mlp weights [W1 | W2] staged with cp.async
     o.total = p;
     return o;
@@ -759,7 +768,8 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
 template <typename T>
 __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* __restrict__ x, const T* __restrict__ g, const void* __restrict__ mask,
                                                                   int mdt, T* __restrict__ dx, void* __restrict__ dmask, Shape sh,
-                                                                  mga_cbam_params prm, Ctx ctx, BwdScratch bs, ClGeom gm) {
+                                                                  mga_cbam_params prm, Ctx ctx, BwdScratch bs, const __grid_constant__ PlaneMaps maps,
+                                                                  ClGeom gm) {
     constexpr int VEC = 16 / sizeof(T);
     constexpr int K = (VEC == 4) ? kClKB : kClKB16;
     constexpr int NT = kClNTB, NW = NT / 32;
@@ -869,36 +879,36 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
         s_s[c] = s;
         s_q[c] = multiply ? s : 1.0f;
     }
-    for (int q0 = 0; q0 < gm.LPT * K * VEC; q0 += 4 * NT) {  // four pixels per thread: all loads first
-        float av[4], mv[4], pv[4];
-        int iv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int p = q0 + j * NT + tid;
-            av[j] = 0.0f; mv[j] = 0.0f; pv[j] = 0.0f; iv[j] = 0;
-            if (p < nP) {
-                av[j] = ctx.a[bS + p0 + p];
-                if (has_mask) mv[j] = ctx.m[bS + p0 + p];
-                iv[j] = ctx.idx[bS + p0 + p];
-                pv[j] = ctx.pmax[bS + p0 + p];
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int p = q0 + j * NT + tid;
-            if (p < gm.LPT * K * VEC) {
-                const bool in = p < nP;
-                ae[p] = in ? (multiply ? av[j] : 1.0f) : 0.0f;
-                d1s[p] = 0.0f;
-                if (in) { aloc[p] = av[j]; mloc[p] = mv[j]; idxl[p] = iv[j]; pmx[p] = pv[j]; }
-            }
+    // Saved planes of the CTA's own pixels (a, idx, pmax [, m]): contiguous nP * 4 bytes each -> asynchronous bulk copies
+    // (cp.async.bulk, SASS UBLKCP) issued by one thread and counted on an mbarrier; no registers, no scoreboard.  In multiply
+    // mode the zero-padded T1 copy `ae` of a is a second bulk copy; the padding and the constant planes are plain stores.
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(csm + o.bar);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+        if (nP > 0) {
+            const uint32_t nb = (uint32_t)nP * 4u;
+            mbar_expect_tx(&bars[0], nb * (3u + (has_mask ? 1u : 0u) + (multiply ? 1u : 0u)));
+            bulk_g2s(aloc, ctx.a + bS + p0, nb, &bars[0]);
+            bulk_g2s(idxl, ctx.idx + bS + p0, nb, &bars[0]);
+            bulk_g2s(pmx, ctx.pmax + bS + p0, nb, &bars[0]);
+            if (has_mask) bulk_g2s(mloc, ctx.m + bS + p0, nb, &bars[0]);
+            if (multiply) bulk_g2s(ae, ctx.a + bS + p0, nb, &bars[0]);
         }
     }
     {
-        const float* const planes[3] = {ctx.pmax + bS, ctx.pavg + bS, has_mask ? ctx.m + bS : nullptr};
-        cl_stage_three<NT>(cat, planeT, planes, y0 - kMaxK / 2, gm.tileRows, H, W, TWp);
+        const int padP = gm.LPT * K * VEC;
+        for (int p = tid; p < padP; p += NT) {
+            d1s[p] = 0.0f;
+            if (p >= nP) ae[p] = 0.0f;
+            else if (!multiply) ae[p] = 1.0f;
+        }
+        if (!has_mask)
+            for (int p = tid; p < nP; p += NT) mloc[p] = 0.0f;
     }
     __syncthreads();
+    if (nP > 0) mbar_wait(&bars[0], 0);
 
     // ---- phase 1 (T1) over (x,g): T_p = sum_c g x q_c (per pixel), E_c = sum_p g x (a | 1) (per channel), sum g x
     stamp(1);
@@ -969,6 +979,23 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
 
     // ---- phase 2: dpre halo through DSMEM; dcat = conv7x7^T(dpre); dWsam partials
     stamp(3);
+    // the T partials are dead (every thread of the CTA is past the merge): their storage takes the padded [pmax, pavg, m]
+    // tile of rows [y0-3, y0+rowsPer+3) x columns [-4, W+4) -- one tensor-map box per plane (SASS UTMALDG), out-of-image
+    // elements zero-filled by the TMA unit (= the convolution's padding); it lands while the dpre halo / conv^T run.
+    const bool tile_tma = gm.use_tma && rows > 0;
+    if (tile_tma) {
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of the old tenant before async-proxy writes
+            const int np = has_mask ? 3 : 2;
+            mbar_expect_tx(&bars[1], (uint32_t)(np * gm.tileRows * TWp * 4));
+            for (int pl = 0; pl < np; ++pl) tma_load_3d(cat + pl * planeT, &maps.m[pl], -4, y0 - kMaxK / 2, b, &bars[1]);
+        }
+        if (!has_mask)
+            for (int i = tid; i < planeT; i += NT) cat[2 * planeT + i] = 0.0f;
+    } else if (rows > 0) {
+        const float* const planes[3] = {ctx.pmax + bS, ctx.pavg + bS, has_mask ? ctx.m + bS : nullptr};
+        cl_stage_three<NT>(cat, planeT, planes, y0 - kMaxK / 2, gm.tileRows, H, W, TWp);
+    }
     if (nP > 0) cl_fetch_halo<NT>(cluster, dpre, 1, gm, y0, rows, H, W);
     __syncthreads();
     {
@@ -986,6 +1013,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
                 *reinterpret_cast<float4*>(dst + s * 4) = make_float4(acc[0] * sc, acc[1] * sc, acc[2] * sc, acc[3] * sc);
             }
         }
+        if (tile_tma) mbar_wait(&bars[1], 0);
         // conv2d_weight: a team of 12 threads owns one (plane, kernel row) pair, the 7 column taps live in registers
         constexpr int kTeam = 12;
         const int team = tid / kTeam, tl = tid - team * kTeam;

@@ -133,13 +133,13 @@ static EncodeTiledFn tensor_map_encoder() {
     }();
     return fn;
 }
-// box (W + 8, RB + 6, 1) over a (B,H,W) fp32 plane; zero fill outside the image.  false -> stage with plain loads instead.
-static bool make_plane_maps(PlaneMaps* out, const float* const (&planes)[3], const Shape& sh, const ConvGeom& cg) {
+// box (boxW, boxH, 1) over a (B,H,W) fp32 plane; zero fill outside the image.  false -> stage with plain loads instead.
+static bool make_plane_maps_box(PlaneMaps* out, const float* const (&planes)[3], const Shape& sh, int boxW, int boxH) {
     EncodeTiledFn enc = tensor_map_encoder();
-    if (!enc || !cg.use_tma) return false;
+    if (!enc || boxW > 256 || boxH > 256 || (boxW * 4) % 16) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)sh.W, (cuuint64_t)sh.H, (cuuint64_t)sh.B};
     const cuuint64_t strides[2] = {(cuuint64_t)sh.W * 4, (cuuint64_t)sh.S * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)cg.TWp, (cuuint32_t)cg.rowsT, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     for (int pl = 0; pl < 3; ++pl) {
         if (planes[pl] == nullptr) { std::memset(&out->m[pl], 0, sizeof(CUtensorMap)); continue; }
@@ -150,6 +150,9 @@ static bool make_plane_maps(PlaneMaps* out, const float* const (&planes)[3], con
         if (r != CUDA_SUCCESS) return false;
     }
     return true;
+}
+static bool make_plane_maps(PlaneMaps* out, const float* const (&planes)[3], const Shape& sh, const ConvGeom& cg) {
+    return cg.use_tma && make_plane_maps_box(out, planes, sh, cg.TWp, cg.rowsT);
 }
 
 template <typename K>
@@ -498,8 +501,12 @@ static int backward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, co
     const int vec = pick_vec(sh, d->dtype, {x, g, dx});
     ClGeom cgm;
     if (vec > 1 && !(d->flags & MGA_FORCE_SPLIT) && cl_geometry(sh, (int)sizeof(T), true, &cgm)) {
+        PlaneMaps maps;
+        const float* const planes[3] = {ctx.pmax, ctx.pavg, sh.has_mask() ? ctx.m : nullptr};
+        cgm.use_tma = make_plane_maps_box(&maps, planes, sh, cgm.TWp, cgm.tileRows) ? 1 : 0;
+        if (!cgm.use_tma) std::memset(&maps, 0, sizeof(maps));
         const int rc = launch_cl("cl_bwd", cl_bwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), static_cast<const T*>(g), mask, d->mask_dtype,
-                                 static_cast<T*>(dx), dmask, sh, p, ctx, bs);
+                                 static_cast<T*>(dx), dmask, sh, p, ctx, bs, maps);
         if (rc != MGA_OK && rc != MGA_ERR_UNSUPPORTED) return rc;
         if (rc == MGA_OK) {
         const int nw = 2 * sh.C * sh.hidden + sh.C + sh.hidden;
