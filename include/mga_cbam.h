@@ -47,6 +47,7 @@ enum {
     MGA_PYRAMID_MULTIPLY = 1 << 6, /* mga_pyramid_fusion = multiply (build-side mode); default add = reference alpha-skip */
     MGA_FORCE_SPLIT = 1 << 8,      /* one kernel per phase instead of the cluster-per-sample kernels (bits 9 and 11 are retired) */
     MGA_GATES_ONLY = 1 << 10,      /* internal: compute / differentiate the two gates s(B,C), a(B,HW) only (concat fusion modes) */
+    MGA_NO_PERSIST = 1 << 14,      /* tuning library only: skip the persistent shared-memory-resident experiment even when MGA_PF=1 */
     MGA_NO_SAVE = 1 << 12          /* inference (model.eval() + no_grad, predictor.py:7-24): the forward may skip the saved-for-backward
                                       planes; ctx is then NOT valid for mga_cbam_backward (s and a are still written) */
 };

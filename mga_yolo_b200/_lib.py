@@ -16,7 +16,7 @@ ABI_VERSION = 1
 # enums of include/mga_cbam.h
 F32, BF16, F16, U8 = 0, 1, 2, 3
 HAS_MASK, SIGMOID_MASK, GATE_CLAMP = 1 << 0, 1 << 1, 1 << 2
-SAMCAM_ADD, PYRAMID_MULTIPLY, FORCE_SPLIT, GATES_ONLY, NO_SAVE = 1 << 4, 1 << 6, 1 << 8, 1 << 10, 1 << 12
+SAMCAM_ADD, PYRAMID_MULTIPLY, FORCE_SPLIT, GATES_ONLY, NO_SAVE, NO_PERSIST = 1 << 4, 1 << 6, 1 << 8, 1 << 10, 1 << 12, 1 << 14
 DS_NEAREST, DS_AREA, DS_MAXPOOL, DS_AVGPOOL, DS_AREA_RAW = 0, 1, 2, 3, 4
 
 EXPORTS = (

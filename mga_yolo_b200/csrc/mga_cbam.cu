@@ -13,6 +13,9 @@
 #include "cbam_conv.cuh"
 #include "cbam_fwd.cuh"
 #include "common.cuh"
+#ifdef MGA_TUNING
+#include "cbam_persist.cuh"  // experiment (profiles/r2_persistent_experiment.md): tuning library only, opt-in with MGA_PF=1
+#endif
 
 namespace mga {
 
@@ -115,7 +118,7 @@ static size_t carve_ctx(const Shape& s, void* base, Ctx* c) {
 
 static int tiles_of(const Shape& s, int vec) { return (s.S / vec + 31) / 32; }
 static int conv_ctas(const Shape& s) {
-    const int generic = std::max(((s.W + kConvTW - 1) / kConvTW) * ((s.H + kConvTH - 1) / kConvTH) * s.B, 16 * s.B);  // 16: cluster path
+    const int generic = std::max(((s.W + kConvTW - 1) / kConvTW) * ((s.H + kConvTH - 1) / kConvTH) * s.B, 64 * s.B);  // cluster path: <= 16 CTAs per sample, persistent path: <= 64
     if (s.W % 4) return generic;
     const ConvGeom cg = conv_geom(s.W);
     return std::max(generic, ((s.H + cg.RB - 1) / cg.RB) * s.B);
@@ -160,8 +163,22 @@ static void allow_big_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-static size_t carve_fwd(const Shape& s, void* base, FwdScratch* f) {
+// exchange slots and team counters of the persistent kernels (cbam_persist.cuh); first in the scratch so that forward and backward agree
+struct PfScratch { unsigned* ctr; float* xchg; int xstride; };
+#ifdef MGA_TUNING
+static void carve_pf(const Shape& s, Carver& k, PfScratch* p) {
+    p->xstride = 4 * (4 * s.C + 8);  // a team's buffer is [4C+1][TS rounded up to 4] floats: fits TS slots for every TS >= 1
+    p->ctr = k.take<unsigned>((size_t)kPfMaxLv * kPfMaxCtas);
+    p->xchg = k.take<float>((size_t)kPfMaxCtas * p->xstride);
+}
+#else
+static void carve_pf(const Shape&, Carver&, PfScratch* p) { p->ctr = nullptr; p->xchg = nullptr; p->xstride = 0; }  // (the persistent experiment is not in the product library)
+#endif
+
+static size_t carve_fwd(const Shape& s, void* base, FwdScratch* f, PfScratch* pf = nullptr) {
     Carver k{static_cast<char*>(base)};
+    PfScratch tmp;
+    carve_pf(s, k, pf ? pf : &tmp);
     const size_t BC = (size_t)s.B * s.C;
     f->sxm = k.take<float>(BC);
     f->sx = k.take<float>(BC);
@@ -171,8 +188,10 @@ static size_t carve_fwd(const Shape& s, void* base, FwdScratch* f) {
     return k.off;
 }
 
-static size_t carve_bwd(const Shape& s, void* base, BwdScratch* b) {
+static size_t carve_bwd(const Shape& s, void* base, BwdScratch* b, PfScratch* pf = nullptr) {
     Carver k{static_cast<char*>(base)};
+    PfScratch tmp;
+    carve_pf(s, k, pf ? pf : &tmp);
     const size_t BS = (size_t)s.B * s.S, BC = (size_t)s.B * s.C, BH = (size_t)s.B * s.hidden;
     const size_t nT = tiles_of(s, 1);  // scalar tiling is the largest tile count
     b->T = k.take<float>(BS);
@@ -372,6 +391,234 @@ static int launch_cl(const char* name, Kern kernel, const ClGeom& gm, int nClust
     return MGA_OK;
 }
 
+
+#ifdef MGA_TUNING
+// ------------------------------------------------------------------ persistent shared-memory-resident path (cbam_persist.cuh): geometry + launch
+struct PfCall {  // one pyramid level of a (multi-level) call, host side
+    Shape sh;
+    int dtype, mdt;
+    const void* x; const void* mask; void* out;
+    const void* g; void* dx; void* dmask;
+    mga_cbam_params prm;
+    Ctx ctx;
+    BwdScratch bs;
+    PfScratch ps;
+};
+
+static int pf_gcd(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+
+// per-level geometry for `TSwant` CTAs per sample (0: the fewest whose slice is <= kPfSliceBytes).  false -> not a persistent shape.
+static bool pf_level_geom(const Shape& sh, int esize, bool bwd, int TSwant, PfLevel* lv) {
+    const int vec = 16 / esize, NT = bwd ? kPfNTB : kPfNTF;
+    if (sh.gates_only() || sh.C % kPfNCH || sh.C < 16 || sh.C / kPfNCH > 256 || sh.W % 4 || sh.S % vec) return false;
+    int rowq = 1;
+    while ((rowq * sh.W) % vec) ++rowq;
+    const long rowBytes = (long)sh.C * sh.W * esize;
+    int rowsPer;
+    if (TSwant > 0) {
+        rowsPer = ((sh.H + TSwant - 1) / TSwant + rowq - 1) / rowq * rowq;
+    } else {
+        rowsPer = (int)(kPfSliceBytes / rowBytes) / rowq * rowq;
+        if (rowsPer < rowq) return false;
+        const int TS0 = (sh.H + rowsPer - 1) / rowsPer;
+        rowsPer = ((sh.H + TS0 - 1) / TS0 + rowq - 1) / rowq * rowq;  // same team, balanced rows
+    }
+    if (rowsPer < 1 || (long)rowsPer * rowBytes > kPfSliceBytes) return false;
+    const int TS = (sh.H + rowsPer - 1) / rowsPer;
+    if (TS > 64 || (TSwant > 0 && TS != TSwant)) return false;
+    const int nP = rowsPer * sh.W, nU = nP / vec;
+    if (nU > NT || nU < 1) return false;
+    const int nsplit = nP <= 256 ? 1 : 2;
+    if (nP % nsplit) return false;
+    const int nPbox = nP / nsplit;
+    if (nPbox > 256 || nPbox % vec) return false;
+    lv->sh = sh;
+    lv->TS = TS;
+    lv->rowsPer = rowsPer;
+    lv->nP = nP;
+    lv->nU = nU;
+    lv->nsplit = nsplit;
+    lv->nPbox = nPbox;
+    lv->CCH = sh.C / kPfNCH;
+    lv->chunkBytes = lv->CCH * nP * esize;
+    // pooling: CPL = 2 channels per lane share the mask-plane loads; ~5 units per lane and channel, every thread busy
+    const int cpl = (sh.C % 2 == 0 && lv->CCH % 2 == 0) ? 2 : 1;
+    int lpc = 1;
+    while (lpc < 32 && (lpc * 5 < nU || sh.C * lpc < NT * cpl)) lpc <<= 1;
+    lv->LPC = lpc;
+    lv->CPL = cpl;
+    // channel max/mean: a warp task = UL units x (32/UL) channel ranges, WS warps per unit group; choose the most even split over the warps
+    const int NW = NT / 32;
+    int bestUL = 8, bestWS = 1;
+    double bestCost = 1e30;
+    for (int ul = 8; ul <= 32; ul <<= 1) {
+        const int nUG = (nU + ul - 1) / ul, cq = 32 / ul;
+        for (int ws = 1; ws <= 16; ++ws) {
+            if (ws * 3 * nP * 4 > 12 * 1024 || ws * cq > sh.C) break;
+            const int tasks = nUG * ws, rounds = (tasks + NW - 1) / NW;
+            const double cost = rounds * ((double)((sh.C + cq * ws - 1) / (cq * ws)) + 6.0) + 0.5 * ws;  // channels per lane + merge overhead
+            if (cost < bestCost) { bestCost = cost; bestUL = ul; bestWS = ws; }
+        }
+    }
+    lv->UL = bestUL;
+    lv->WS = bestWS;
+    int G = std::max(1, std::min(NT / nU, lv->CCH));  // rescale: channel groups; must divide the channels of a chunk
+    while (lv->CCH % G) --G;
+    lv->G = G;
+    lv->TWp = sh.W + 8;
+    lv->planeT = ((rowsPer + kMaxK - 1) * lv->TWp + 31) & ~31;
+    return true;
+}
+
+static PfFwdOff pf_fwd_off(const PfLevel* lv, int n) {
+    int C = 0, Hd = 0, nP = 0, mrawF = 0, Rf = 0;
+    for (int i = 0; i < n; ++i) {
+        C = std::max(C, lv[i].sh.C); Hd = std::max(Hd, lv[i].sh.hidden); nP = std::max(nP, lv[i].nP);
+        mrawF = std::max(mrawF, (lv[i].rowsPer + kMaxK - 1) * lv[i].sh.W);
+        const int stage = 4 * lv[i].sh.C * (lv[i].LPC | 1) + 8;
+        const int tilemg = 3 * lv[i].planeT + std::max(lv[i].WS, 1) * 3 * lv[i].nP;
+        Rf = std::max(Rf, std::max(stage, tilemg));
+    }
+    PfFwdOff o;
+    int p = 0;
+    auto take = [&p](int n) { const int r = p; p += (n + 3) & ~3; return r; };
+    o.bar = take(2 * (kPfNCH + 1) + 2);
+    o.red = take(64);
+    o.wk = take(3 * kMaxK * kMaxK);
+    o.avg = take(C); o.mx = take(C); o.ha = take(Hd); o.hm = take(Hd);
+    o.q2 = take(2 * C); o.AB4 = take(4 * C); o.pst = take(4 * C);
+    o.mloc = take(nP); o.mb = take(nP); o.aloc = take(nP);
+    o.mraw = take(mrawF);
+    p = (p + 31) & ~31;
+    o.R = take(Rf);
+    o.total = p;
+    return o;
+}
+
+// x (or g) of one level as a 2-D tensor: dim0 = the S pixels of a plane, dim1 = the B*C planes; box = (nPbox, CCH)
+static bool pf_make_map(CUtensorMap* out, const void* base, const Shape& sh, int dtype, const PfLevel& lv) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    const int esize = dtype == MGA_F32 ? 4 : 2;
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) || ((size_t)sh.S * esize) % 16) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)sh.S, (cuuint64_t)sh.B * sh.C};
+    const cuuint64_t strides[1] = {(cuuint64_t)sh.S * esize};
+    const cuuint32_t box[2] = {(cuuint32_t)lv.nPbox, (cuuint32_t)lv.CCH};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = dtype == MGA_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (dtype == MGA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    return enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct PfPlan { PfParams P; int smem; int NT; };
+
+// Geometry of a call of n levels (same element type): team sizes, items, shared-memory layout.  false -> some level does not fit.
+static bool pf_plan(const PfCall* calls, int n, bool bwd, PfPlan* plan) {
+    static const int enabled = env_int("MGA_PF", 0);  // opt-in
+    static const int max_st = env_int("MGA_PF_MAXST", 64);
+    if (!enabled || n < 1 || n > kPfMaxLv) return false;
+    PfParams& P = plan->P;
+    std::memset(&P, 0, sizeof(P));
+    const int esize = calls[0].dtype == MGA_F32 ? 4 : 2;
+    int ST = 1;
+    for (int i = 0; i < n; ++i) {
+        if (calls[i].dtype != calls[0].dtype) return false;
+        if (!pf_level_geom(calls[i].sh, esize, bwd, 0, &P.lv[i])) return false;
+        ST = std::max(ST, P.lv[i].TS);
+    }
+    for (int i = 0; i < n; ++i) {  // every team size must divide the super-team: grow the smaller teams to the next divisor
+        int ts = P.lv[i].TS;
+        while (ts <= ST && (ST % ts || !pf_level_geom(calls[i].sh, esize, bwd, ts, &P.lv[i]))) ++ts;
+        if (ts > ST) return false;
+    }
+    if (ST > max_st) return false;
+    P.n_levels = n;
+    P.ST = ST;
+    int xbytes = 0, items = 0;
+    for (int i = 0; i < n; ++i) {
+        PfLevel& lv = P.lv[i];
+        lv.spi = ST / lv.TS;
+        lv.first_item = items;
+        lv.n_items = (lv.sh.B + lv.spi - 1) / lv.spi;
+        items += lv.n_items;
+        xbytes = std::max(xbytes, lv.sh.C * lv.nP * esize);
+    }
+    P.total_items = items;
+    P.xbytes = (xbytes + 127) & ~127;
+    plan->NT = bwd ? kPfNTB : kPfNTF;
+    static const int stagger = env_int("MGA_PF_STAGGER_NS", 8000);
+    P.stagger_ns = stagger;
+    P.fo = pf_fwd_off(P.lv, n);
+    plan->smem = P.xbytes + 4 * P.fo.total;
+    return plan->smem <= kClTwoCtaSmem;
+}
+
+template <typename Kern>
+static int pf_launch(const char* name, Kern kernel, PfPlan& plan, const PfMaps& maps, cudaStream_t st) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(MGA_ERR_CUDA, "%s: cudaGetDevice failed", name);
+    struct Cfg { const void* k; int dev, smem, ctas; };
+    static thread_local Cfg cache[32] = {};
+    int ctas = -1;
+    for (const Cfg& c : cache)
+        if (c.k == (const void*)kernel && c.dev == dev && c.smem == plan.smem) ctas = c.ctas;
+    if (ctas < 0) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        int occ = 0, sms = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, plan.NT, (size_t)plan.smem);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) { cudaGetLastError(); return MGA_ERR_UNSUPPORTED; }
+        ctas = std::min(occ * sms, kPfMaxCtas);
+        for (Cfg& c : cache)
+            if (!c.k) { c = Cfg{(const void*)kernel, dev, plan.smem, ctas}; break; }
+    }
+    PfParams& P = plan.P;
+    P.nST = std::min(ctas / P.ST, P.total_items);
+    if (P.nST < 1) return MGA_ERR_UNSUPPORTED;
+    // team counters start at zero: one memset node per launch (all levels' counters live in level 0's scratch)
+    if (cudaMemsetAsync(P.lv[0].ctr, 0, sizeof(unsigned) * kPfMaxLv * kPfMaxCtas, st) != cudaSuccess) return fail(MGA_ERR_CUDA, "%s: memset failed", name);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(P.nST * P.ST));
+    cfg.blockDim = dim3((unsigned)plan.NT);
+    cfg.dynamicSmemBytes = (size_t)plan.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // every CTA of the grid is co-resident: the team barriers cannot deadlock
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    {
+        LaunchScope ls(name, st);
+        e = cudaLaunchKernelEx(&cfg, kernel, P, maps);
+    }
+    if (e != cudaSuccess) return fail(MGA_ERR_CUDA, "%s: launch (%d CTAs, %d B smem): %s", name, P.nST * P.ST, plan.smem, cudaGetErrorString(e));
+    return MGA_OK;
+}
+
+// MGA_ERR_UNSUPPORTED: not a persistent shape (the caller takes the cluster / per-phase path)
+static int pf_forward(const PfCall* calls, int n, cudaStream_t st) {
+    PfPlan plan;
+    if (!pf_plan(calls, n, false, &plan)) return MGA_ERR_UNSUPPORTED;
+    PfMaps maps;
+    for (int i = 0; i < n; ++i) {
+        PfLevel& lv = plan.P.lv[i];
+        const PfCall& c = calls[i];
+        if ((reinterpret_cast<uintptr_t>(c.out) & 15) || !pf_make_map(&maps.x[i], c.x, c.sh, c.dtype, lv)) return MGA_ERR_UNSUPPORTED;
+        if (c.sh.has_mask() && ((reinterpret_cast<uintptr_t>(c.mask) & 15) || (c.sh.W * (c.mdt == MGA_F32 ? 4 : 2)) % 16)) return MGA_ERR_UNSUPPORTED;  // bulk copies of mask rows
+        lv.x = c.x; lv.mask = c.mask; lv.out = c.out; lv.mdt = c.mdt;
+        lv.prm = c.prm; lv.ctx = c.ctx;
+        lv.xchg = c.ps.xchg; lv.xstride = c.ps.xstride;
+        lv.ctr = calls[0].ps.ctr + (size_t)i * kPfMaxCtas;
+    }
+    switch (calls[0].dtype) {
+        case MGA_F32: return pf_launch("pf_fwd", pf_fwd_kernel<float>, plan, maps, st);
+        case MGA_BF16: return pf_launch("pf_fwd", pf_fwd_kernel<__nv_bfloat16>, plan, maps, st);
+        default: return pf_launch("pf_fwd", pf_fwd_kernel<__half>, plan, maps, st);
+    }
+}
+
+#endif  // MGA_TUNING
+
 // ------------------------------------------------------------------ forward
 template <typename T, int VEC>
 static int forward_split(const Shape& sh, const T* x, const void* mask, int mask_dtype, const mga_cbam_params& p, T* out, Ctx ctx,
@@ -424,8 +671,18 @@ static int forward_split(const Shape& sh, const T* x, const void* mask, int mask
 
 template <typename T>
 static int forward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, const void* mask, const mga_cbam_params& p, void* out,
-                     Ctx ctx, FwdScratch fs, cudaStream_t st) {
+                     Ctx ctx, FwdScratch fs, const PfScratch& ps, cudaStream_t st) {
     const int vec = pick_vec(sh, d->dtype, {x, out});
+#ifdef MGA_TUNING
+    if (vec > 1 && !(d->flags & (MGA_FORCE_SPLIT | MGA_NO_PERSIST))) {
+        PfCall c{};
+        c.sh = sh; c.dtype = d->dtype; c.mdt = d->mask_dtype; c.x = x; c.mask = mask; c.out = out; c.prm = p; c.ctx = ctx; c.ps = ps;
+        const int rc = pf_forward(&c, 1, st);
+        if (rc != MGA_ERR_UNSUPPORTED) return rc;
+    }
+#else
+    (void)ps;
+#endif
     ClGeom cgm;
     if (vec > 1 && !(d->flags & MGA_FORCE_SPLIT) && cl_geometry(sh, (int)sizeof(T), false, &cgm)) {
         const int rc = launch_cl("cl_fwd", cl_fwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), mask, d->mask_dtype, static_cast<T*>(out), sh, p, ctx);
@@ -614,13 +871,14 @@ int mga_cbam_forward(const mga_cbam_desc* d, const void* x, const void* mask, co
     if (sh.has_mask() && !mask) return fail(MGA_ERR_ARG, "MGA_HAS_MASK set but mask is null");
     Ctx ctx;
     FwdScratch fs;
+    PfScratch ps;
     carve_ctx(sh, ctx_buf, &ctx);
-    carve_fwd(sh, scratch, &fs);
+    carve_fwd(sh, scratch, &fs, &ps);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (d->dtype) {
-        case MGA_F32: return forward_t<float>(sh, d, x, mask, *p, out, ctx, fs, st);
-        case MGA_BF16: return forward_t<__nv_bfloat16>(sh, d, x, mask, *p, out, ctx, fs, st);
-        default: return forward_t<__half>(sh, d, x, mask, *p, out, ctx, fs, st);
+        case MGA_F32: return forward_t<float>(sh, d, x, mask, *p, out, ctx, fs, ps, st);
+        case MGA_BF16: return forward_t<__nv_bfloat16>(sh, d, x, mask, *p, out, ctx, fs, ps, st);
+        default: return forward_t<__half>(sh, d, x, mask, *p, out, ctx, fs, ps, st);
     }
 }
 

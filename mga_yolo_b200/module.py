@@ -160,6 +160,8 @@ class MaskGuidedCBAM(nn.Module):
             f |= _lib.PYRAMID_MULTIPLY
         if os.getenv("MGA_FORCE_SPLIT", ""):  # one kernel per phase instead of the cluster-per-sample kernels
             f |= _lib.FORCE_SPLIT
+        if os.getenv("MGA_NO_PERSIST", ""):  # cluster-per-sample kernels instead of the persistent shared-memory-resident ones
+            f |= _lib.NO_PERSIST
         return f
 
     def forward(self, x: Union[torch.Tensor, Sequence[torch.Tensor]]) -> torch.Tensor:
