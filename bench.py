@@ -581,6 +581,22 @@ def gpu_arm(args, rank, world, local_rank):
                                                                      "achieved": round(bw["gbps"], 1), "frac": round(bw["frac"], 4)},
                         "kernels": [{"kernel": k["kernel"], "level": k["level"], "ms": round(k["ms"], 5), "frac": round(k.get("frac", 0.0), 4)} for k in r["kernels"]]}
         line["workloads"] = wl
+    if args.workload == "cfg2" and not args.batch and not strong and not args.no_workloads and 256 % world == 0:
+        # BASELINE configs[2] as it is stated: YOLOv8s bf16, GLOBAL batch 256 sharded over the ranks (strong scaling: 256 / N samples
+        # per GPU), module-only fwd+bwd + the weight-gradient all-reduce; every rank takes part, rank 0 reports
+        lv, Bg, dn, txt = WORKLOADS["cfg3"]
+        dtw = DT[dn]
+        ew = torch.empty((), dtype=dtw).element_size()
+        Bs = Bg // world
+        r = measure(args, lib, dev, world, lv, Bs, dtw, flags_of(args.sam_cam_fusion), 10, 3, instrument=False)
+        r["sets"] = None
+        torch.cuda.empty_cache()
+        ab = algorithmic_bytes(lv, Bs, ew)
+        line["strong_scaling_cfg3"] = {
+            "workload": txt + f": global batch {Bg} sharded over {world} GPU(s)", "global_batch": Bg, "batch_per_gpu": Bs, "dtype": dn,
+            "ms_per_step": round(r["ms"], 5), "steps": 10, "warmup": 3, "value": round(world * ab / (r["ms"] * 1e-3) / 1e9, 1), "unit": "GB/s",
+            "images_per_sec": round(Bg / (r["ms"] * 1e-3), 1), "per_gpu_step_frac": round(ab / (r["ms"] * 1e-3) / 1e9 / peak, 4),
+            "scaling": "strong", "timing": "CUDA events, max over ranks, all-reduce inside the timed region"}
     if solo and not args.no_cpu:
         line["gpu_eager_baseline"] = gpu_eager_baseline(dev, levels, B, dtype, alg_bytes, args.sam_cam_fusion)
         cb = 16 if args.workload == "cfg2" else 8

@@ -154,6 +154,12 @@ int mga_mask_downsample(const uint8_t* src, void* dst, void* tmp, int32_t B, int
 int mga_masks_multi(const uint8_t* src, void* dst8, void* dst16, void* dst32, int32_t B, int32_t H, int32_t W, int32_t method,
                     float thresh, int32_t close3x3, int32_t out_dtype, void* stream);
 
+/* Same results in two stages when the caller provides tmp (2 * B * (H/8) * (W/8) bytes): stage 1 reads the masks with one thread per
+ * 8x8 block over the whole batch (enough CTAs to pull them at HBM speed), stage 2 derives the three strides per image from the block
+ * counts.  tmp == NULL is mga_masks_multi. */
+int mga_masks_multi_ws(const uint8_t* src, void* dst8, void* dst16, void* dst32, void* tmp, int32_t B, int32_t H, int32_t W,
+                       int32_t method, float thresh, int32_t close3x3, int32_t out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

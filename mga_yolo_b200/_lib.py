@@ -21,7 +21,7 @@ DS_NEAREST, DS_AREA, DS_MAXPOOL, DS_AVGPOOL, DS_AREA_RAW = 0, 1, 2, 3, 4
 
 EXPORTS = (
     "mga_abi_version", "mga_last_error", "mga_cbam_workspace", "mga_cbam_forward", "mga_cbam_backward",
-    "mga_cbam_ctx_view", "mga_mask_downsample", "mga_masks_multi", "mga_cbam_plan", "mga_cbam_gates_forward", "mga_cbam_gates_backward", "mga_launch_count", "mga_profile_enable", "mga_profile_count",
+    "mga_cbam_ctx_view", "mga_mask_downsample", "mga_masks_multi", "mga_masks_multi_ws", "mga_cbam_plan", "mga_cbam_gates_forward", "mga_cbam_gates_backward", "mga_launch_count", "mga_profile_enable", "mga_profile_count",
     "mga_profile_read",
 )
 
@@ -83,6 +83,9 @@ def load() -> C.CDLL:
     lib.mga_masks_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                     C.c_int32, C.c_int32, C.c_void_p]
     lib.mga_masks_multi.restype = C.c_int
+    lib.mga_masks_multi_ws.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_float, C.c_int32, C.c_int32, C.c_void_p]
+    lib.mga_masks_multi_ws.restype = C.c_int
     lib.mga_cbam_plan.argtypes = [C.POINTER(Desc), C.c_int, C.POINTER(PlanInfo)]
     lib.mga_cbam_plan.restype = C.c_int
     lib.mga_launch_count.restype = C.c_ulonglong

@@ -142,8 +142,31 @@ __device__ __forceinline__ void multi_morph(const uint8_t* src, uint8_t* dst, in
     }
 }
 
+// Stage 1 of the two-stage form (mga_masks_multi_ws): one THREAD per 8x8 block over the whole batch -- the only pass over the masks,
+// with enough CTAs to pull them at HBM speed (one CTA per image leaves 84 of 148 SMs idle at batch 64).  cnt8 / tl8: (B, H/8 * W/8) bytes.
+__global__ void __launch_bounds__(256) masks_count8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ cnt8, uint8_t* __restrict__ tl8,
+                                                           int B, int H, int W) {
+    const int w8 = W / 8, n8 = (H / 8) * w8;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * n8) return;
+    const int b = (int)(i / n8), j = (int)(i - (size_t)b * n8);
+    const int by = j / w8, bx = j - by * w8;
+    const uint8_t* p = src + (size_t)b * H * W + (size_t)(by * 8) * W + bx * 8;
+    int cnt = 0;
+    unsigned first = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(p + (size_t)r * W));
+        cnt += __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u);
+        if (r == 0) first = v.x & 0xffu;
+    }
+    cnt8[i] = (uint8_t)cnt;
+    tl8[i] = (uint8_t)(first != 0);
+}
+
 __global__ void __launch_bounds__(kMultiThreads) masks_multi_kernel(const uint8_t* __restrict__ src, void* __restrict__ d8, void* __restrict__ d16,
-                                                                   void* __restrict__ d32, MultiArgs a) {
+                                                                   void* __restrict__ d32, MultiArgs a, const uint8_t* __restrict__ pre_cnt8,
+                                                                   const uint8_t* __restrict__ pre_tl8) {
     extern __shared__ __align__(16) uint8_t msm[];
     const int b = blockIdx.x;
     const int h8 = a.H / 8, w8 = a.W / 8, n8 = h8 * w8;
@@ -156,6 +179,12 @@ __global__ void __launch_bounds__(kMultiThreads) masks_multi_kernel(const uint8_
     uint8_t* wa = reinterpret_cast<uint8_t*>(c32 + n32);  // work planes for the close: [n8] x 2
     uint8_t* wb = wa + n8;
     const uint8_t* sp = src + (size_t)b * a.H * a.W;
+    if (pre_cnt8 != nullptr) {  // two-stage form: the 8x8 block counts were made by masks_count8_kernel
+        for (int i = threadIdx.x; i < n8; i += kMultiThreads) {
+            c8[i] = pre_cnt8[(size_t)b * n8 + i];
+            t8[i] = pre_tl8[(size_t)b * n8 + i];
+        }
+    } else
     for (int i = threadIdx.x; i < n8; i += kMultiThreads) {
         const int by = i / w8, bx = i - by * w8;
         const uint8_t* p = sp + (size_t)(by * 8) * a.W + bx * 8;
@@ -271,8 +300,15 @@ extern "C" int mga_mask_downsample(const uint8_t* src, void* dst, void* tmp, int
     return MGA_OK;
 }
 
+extern "C" int mga_masks_multi_ws(const uint8_t* src, void* dst8, void* dst16, void* dst32, void* tmp, int32_t B, int32_t H, int32_t W,
+                                  int32_t method, float thresh, int32_t close3x3, int32_t out_dtype, void* stream);
 extern "C" int mga_masks_multi(const uint8_t* src, void* dst8, void* dst16, void* dst32, int32_t B, int32_t H, int32_t W, int32_t method,
                                float thresh, int32_t close3x3, int32_t out_dtype, void* stream) {
+    return mga_masks_multi_ws(src, dst8, dst16, dst32, nullptr, B, H, W, method, thresh, close3x3, out_dtype, stream);
+}
+
+extern "C" int mga_masks_multi_ws(const uint8_t* src, void* dst8, void* dst16, void* dst32, void* tmp, int32_t B, int32_t H, int32_t W,
+                                  int32_t method, float thresh, int32_t close3x3, int32_t out_dtype, void* stream) {
     auto bad = [&](int code, const char* msg) { return fail(code, "mga_masks_multi: %s", msg); };
     if (!src || !dst8 || !dst16 || !dst32) return bad(MGA_ERR_ARG, "null pointer argument");
     if (B <= 0 || H <= 0 || W <= 0) return bad(MGA_ERR_ARG, "bad mask shape");
@@ -291,7 +327,14 @@ extern "C" int mga_masks_multi(const uint8_t* src, void* dst8, void* dst16, void
         cudaFuncSetAttribute(masks_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         configured = true;
     }
-    masks_multi_kernel<<<B, kMultiThreads, smem, static_cast<cudaStream_t>(stream)>>>(src, dst8, dst16, dst32, a);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* cnt8 = static_cast<uint8_t*>(tmp);
+    uint8_t* tl8 = cnt8 ? cnt8 + (size_t)B * n8 : nullptr;
+    if (cnt8) {
+        const size_t total = (size_t)B * n8;
+        masks_count8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, cnt8, tl8, B, H, W);
+    }
+    masks_multi_kernel<<<B, kMultiThreads, smem, st>>>(src, dst8, dst16, dst32, a, cnt8, tl8);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bad(MGA_ERR_CUDA, cudaGetErrorString(e));
     return MGA_OK;

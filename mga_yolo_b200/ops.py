@@ -165,8 +165,10 @@ def _masks_multi_cuda(src, method, thresh, close3x3, out_float):
     dt = torch.float32 if out_float else torch.uint8
     with torch.cuda.device(src.device):
         outs = [torch.empty((B, H // s, W // s), dtype=dt, device=src.device) for s in (8, 16, 32)]
-        rc = lib.mga_masks_multi(s3.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), B, H, W, method, float(thresh),
-                                 int(close3x3), _lib.F32 if out_float else _lib.U8, _stream(src))
+        # two stages from 8 images on: one thread per 8x8 block reads the masks (grid over the whole batch), then one CTA per image
+        tmp = torch.empty(2 * B * (H // 8) * (W // 8), dtype=torch.uint8, device=src.device) if B >= 8 else None
+        rc = lib.mga_masks_multi_ws(s3.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), None if tmp is None else tmp.data_ptr(),
+                                    B, H, W, method, float(thresh), int(close3x3), _lib.F32 if out_float else _lib.U8, _stream(src))
     _lib.check(rc, "mga_masks_multi")
     return tuple(outs)
 

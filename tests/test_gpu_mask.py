@@ -60,8 +60,9 @@ def test_batched_full_size_vs_oracle(hw, monkeypatch):
     assert [tuple(m.shape) for m in multi] == [(B, 1, -(-H // s), -(-W // s)) for s in (8, 16, 32)]
 
 
+@pytest.mark.parametrize("B", [3, 9])  # 9: the two-stage form (whole-batch 8x8 block counts, then one CTA per image) of mga_masks_multi_ws
 @pytest.mark.parametrize("hw", [(640, 640), (1280, 1280), (608, 352), (32, 64)])
-def test_one_pass_multi_stride_is_bit_identical_to_per_stride(hw, monkeypatch):
+def test_one_pass_multi_stride_is_bit_identical_to_per_stride(hw, B, monkeypatch):
     """torch.ops.mga.masks_multi (one read of the masks -> strides 8/16/32) against the per-stride op, which is pinned to the
     reference's cv2 outputs above, and against the numpy oracle; every method / bridge / output type of the dataset loop
     (mga_yolo/data/dataset.py:95-103)."""
@@ -70,7 +71,6 @@ def test_one_pass_multi_stride_is_bit_identical_to_per_stride(hw, monkeypatch):
     dev = torch.device("cuda:0")
     H, W = hw
     rng = np.random.default_rng(H + W)
-    B = 3
     src = (rng.random((B, H, W)) > 0.55).astype(np.uint8)
     src[0, : H // 2] = 0
     src[1] &= (rng.random((H, W)) > 0.8)
