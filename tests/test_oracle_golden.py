@@ -102,3 +102,82 @@ def test_oracle_matches_reference_on_full_size_neck_shapes(tag):
     assert rel_err(gr["dmask"], t(z["dmask_f64"])) <= 1e-11
     for k in PARAM_KEYS:
         assert rel_err(gr[k], t(z["d." + k + "_f64"])) <= 1e-10, k
+
+
+# ---------------------------------------------------------------- MaskECA, MGAMaskHead tail, ProbMaskGater (train mode)
+ECA_CASES = ("basic", "beta", "edge", "nomask", "raw3d")
+
+
+@pytest.mark.parametrize("tag", ECA_CASES)
+@pytest.mark.parametrize("dtype,suffix,tol", [(torch.float64, "_f64", 1e-12), (torch.float32, "", 2e-6)])
+def test_eca_oracle_matches_reference(tag, dtype, suffix, tol):
+    from oracle import eca_oracle as eo
+
+    z = np.load(GOLDEN / f"eca_{tag}.npz")
+    C, use_sig = (int(v) for v in z["cfg"])
+    assert z["w1d"].shape[-1] == eo.eca_kernel_size(C)
+    x = t(z["x"], dtype)
+    mask = t(z["mask"], dtype) if bool(z["has_mask"]) else None
+    out, sv = eo.eca_forward(x, mask, t(z["w1d"], dtype).reshape(-1), t(z["beta"], dtype), use_sigmoid_mask=bool(use_sig))
+    gr = eo.eca_backward(t(z["g"], dtype), sv)
+    assert rel_err(out, t(z["out" + suffix])) <= tol
+    assert rel_err(gr["dx"], t(z["dx" + suffix])) <= tol
+    if mask is not None:
+        assert gr["dmask"].shape == z["dmask" + suffix].shape
+        assert rel_err(gr["dmask"], t(z["dmask" + suffix])) <= tol
+    for k in ("conv1d.weight", "beta"):
+        assert rel_err(gr[k], t(z["d." + k + "_f64"])) <= max(tol, 2e-5 if dtype == torch.float32 else 0.0), k
+
+
+@pytest.mark.parametrize("tag", ["p3", "odd"])
+@pytest.mark.parametrize("dtype,suffix,tol", [(torch.float64, "_f64", 1e-12), (torch.float32, "", 2e-6)])
+def test_head_tail_oracle_matches_reference(tag, dtype, suffix, tol):
+    from oracle import next_oracle as no
+
+    z = np.load(GOLDEN / f"head_{tag}.npz")
+    feat, w, b, g = (t(z[k], dtype) for k in ("feat", "w", "b", "g"))
+    out = no.head_tail_forward(feat, w, b)
+    dfeat, dw, db = no.head_tail_backward(feat, w, g)
+    assert rel_err(out, t(z["out" + suffix])) <= tol
+    assert rel_err(dfeat, t(z["dfeat" + suffix])) <= tol
+    assert rel_err(dw, t(z["dw_f64"])) <= max(tol, 2e-5 if dtype == torch.float32 else 0.0)
+    assert rel_err(db, t(z["db_f64"])) <= max(tol, 2e-5 if dtype == torch.float32 else 0.0)
+
+
+@pytest.mark.parametrize("tag", ["gumbel", "gumbel_pmin", "hard_st"])
+def test_gate_oracle_matches_reference_given_its_uniform_draws(tag):
+    from oracle import next_oracle as no
+
+    z = np.load(GOLDEN / f"gate_{tag}.npz")
+    tau, p_min, thr = (float(v) for v in z["cfg"])
+    assert int(z["n_u"]) == 2
+    out, saved = no.gate_forward(t(z["p"]), t(z["u0"]), t(z["u1"]), mode=str(z["mode"]), tau=tau, p_min=p_min, threshold=thr)
+    assert rel_err(out, t(z["out"])) <= 2e-6
+    dp = no.gate_backward(t(z["g"]), saved, tau=tau, p_min=p_min)
+    assert rel_err(dp, t(z["dp"])) <= 2e-5
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors of Philox4x32-10."""
+    from oracle import next_oracle as no
+
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = no.philox4x32(ctr, key)
+        assert tuple(int(v) for v in got) == want
+    u1, u2 = no.gate_uniforms(1000, seed=1234, offset=7)
+    assert u1.dtype == np.float32 and (u1 > 0).all() and (u1 <= 1).all() and abs(float(u1.mean()) - 0.5) < 0.05 and abs(float(u2.mean()) - 0.5) < 0.05
+
+
+def test_collate_oracle_matches_reference_rule():
+    """dataset.py:149-169: F.pad(t, (0, pad_w, 0, pad_h), 0) then stack."""
+    import torch.nn.functional as F
+
+    from oracle import next_oracle as no
+
+    rng = np.random.default_rng(0)
+    per = [rng.random((1, h, w)).astype(np.float32) for h, w in ((10, 8), (7, 12), (10, 12))]
+    want = torch.stack([F.pad(torch.from_numpy(a), (0, 12 - a.shape[2], 0, 10 - a.shape[1]), value=0.0) for a in per], 0).numpy()
+    assert np.array_equal(no.collate_masks([a[0] for a in per]), want)
