@@ -160,6 +160,42 @@ int mga_masks_multi(const uint8_t* src, void* dst8, void* dst16, void* dst32, in
 int mga_masks_multi_ws(const uint8_t* src, void* dst8, void* dst16, void* dst32, void* tmp, int32_t B, int32_t H, int32_t W,
                        int32_t method, float thresh, int32_t close3x3, int32_t out_dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Components either side of the block
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* MaskECA (mga_yolo/nn/modules/masked_eca.py:139-193): out = x * (1 + softplus(beta) * (sigmoid(conv1d_k(masked_avg(x, mask))) - 0.5)).
+ * The descriptor is mga_cbam_desc with `hidden` = the odd conv1d kernel size k (masked_eca.py:43-52, <= 15) and `ksize` ignored;
+ * flags: MGA_HAS_MASK, MGA_SIGMOID_MASK.  w1d = conv1d.weight (k floats), beta ().  Gradients are written, not accumulated. */
+int mga_eca_workspace(const mga_cbam_desc* d, size_t* ctx_bytes, size_t* scratch_bytes);
+int mga_eca_forward(const mga_cbam_desc* d, const void* x, const void* mask, const float* w1d, const float* beta, void* out, void* ctx,
+                    void* scratch, void* stream);
+int mga_eca_backward(const mga_cbam_desc* d, const void* x, const void* mask, const void* grad_out, const float* w1d, const void* ctx,
+                     void* grad_x, void* grad_mask, float* grad_w1d, float* grad_beta, void* scratch, void* stream);
+
+/* MGAMaskHead tail (mga_yolo/nn/modules/segmentation.py:94,107-110): logits (B,1,H,W) fp32 = Conv2d(C, 1, 3, padding 1, bias)(feat),
+ * feat (B,C,H,W) of `dtype`, weight (1,C,3,3) and bias (1) fp32, C <= 256.  Backward: grad_feat (dtype of feat), grad_weight, grad_bias. */
+int mga_head_tail_forward(const void* feat, const float* weight, const float* bias, float* logits, int32_t B, int32_t C, int32_t H, int32_t W,
+                          int32_t dtype, void* stream);
+int mga_head_tail_backward(const void* feat, const float* weight, const float* grad_logits, void* grad_feat, float* grad_weight, float* grad_bias,
+                           int32_t B, int32_t C, int32_t H, int32_t W, int32_t dtype, void* stream);
+
+/* ProbMaskGater in train mode (mga_yolo/nn/modules/probmaskgater.py:59-95).  mode: 0 gumbel, 1 hard_st, 2 bernoulli_detach.
+ * p: n raw gate inputs (clamped to [0,1], floored at p_min inside); out: the gate; soft: the soft gate saved for backward (modes 0/1).
+ * NOISE CONTRACT: when `noise` is NULL, element i draws Philox4x32-10 (Salmon et al. 2011) with key = (seed & 0xffffffff, seed >> 32)
+ * and counter = (i & 0xffffffff, i >> 32, offset & 0xffffffff, offset >> 32); u1 = (r0 + 0.5) * 2^-32, u2 = (r1 + 0.5) * 2^-32 (fp32).
+ * gumbel / hard_st use logistic noise -log(-log u1) + log(-log u2) (u clamped to [1e-6, 1-1e-6]); bernoulli_detach is [u1 < p].
+ * The caller advances `offset` by one per call (the reference re-seeds a generator with seed + call counter, probmaskgater.py:43-49).
+ * When `noise` is not NULL it holds the uniforms (u1: noise[0..n), u2: noise[n..2n)) -- how the parity tests feed the reference's own
+ * draws.  noise_out (2n floats, may be NULL) receives the uniforms that were used. */
+int mga_gate_sample_forward(const float* p, const float* noise, float* out, float* soft, float* noise_out, size_t n, int32_t mode, float tau,
+                            float p_min, float threshold, uint64_t seed, uint64_t offset, void* stream);
+int mga_gate_sample_backward(const float* grad_out, const float* p, const float* soft, float* grad_p, size_t n, float tau, float p_min, void* stream);
+
+/* Zero-pad + stack of per-sample masks of ONE pyramid stride (mga_yolo/data/dataset.py:149-169): items is a DEVICE array of B records
+ * { const void* src; int32_t h, w; } (16 bytes each), src uint8 or float32 (h,w) maps; dst (B,1,H,W) float32 with H >= h_i, W >= w_i. */
+int mga_collate_masks(const void* items_dev, float* dst, int32_t B, int32_t H, int32_t W, int32_t src_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

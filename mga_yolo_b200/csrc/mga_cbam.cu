@@ -952,3 +952,5 @@ int mga_cbam_ctx_view(const mga_cbam_desc* d, const void* ctx_buf, int which, co
 }
 
 }  // extern "C"
+
+#include "next_ops.cuh"  // MaskECA, MGAMaskHead tail, ProbMaskGater sampling, collate

@@ -74,6 +74,12 @@ class MaskUtils:
         return _lib.DS_MAXPOOL, 0.0, bridge, False
 
     @staticmethod
+    def collate_masks(per_sample: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Zero-pad to the largest (h, w) of the batch and stack: (B,1,H,W) float32, one pyramid stride per call -- the
+        `masks_multi` branch of MGADataset.collate_fn (mga_yolo/data/dataset.py:149-169) on device tensors (uint8 or float32)."""
+        return torch.ops.mga.collate_masks(list(per_sample))
+
+    @staticmethod
     def masks_multi(bin_masks: torch.Tensor, strides: Sequence[int] = (8, 16, 32), prob: bool = False) -> list:
         """Batch form of MGADataset.__getitem__'s loop (mga_yolo/data/dataset.py:95-103):
         (B,H,W) uint8 -> [ (B,1,Hs,Ws) for s in strides ].  Letterboxed sizes (H, W multiples of 32) with the default

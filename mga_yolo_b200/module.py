@@ -67,32 +67,32 @@ class MaskGate(nn.Module):
     """Mask pre-gate used when the MGA_PROB_MODE environment switch is on
     (probmaskgater.py:27-98).  The deterministic branch (eval mode, or mode
     'deterministic') is only a clamp to [0,1] and is fused into the CUDA kernels; the
-    sampling branches run here as a few elementwise torch ops on the (B,1,H,W) map."""
+    sampling branches are ONE CUDA kernel (Philox noise + logistic-gumbel sigmoid / straight-through / Bernoulli) with a closed-form backward."""
 
     def __init__(self, mode: str = "gumbel", tau: float = 1.0, p_min: float = 0.0, threshold: float = 0.5):
         super().__init__()
         if tau <= 0:
             raise ValueError("tau must be > 0")
         self.mode, self.tau, self.p_min, self.threshold = mode, float(tau), float(p_min), float(threshold)
+        self.seed: Optional[int] = None  # Philox key of this gate's noise stream (set on first use)
+        self.calls = 0                   # stream offset: one per sampled forward
 
     def is_deterministic(self) -> bool:
         return (not self.training) or self.mode == "deterministic" or self.mode not in _GATE_MODES
 
     def sample(self, mask: torch.Tensor) -> torch.Tensor:
-        p = (mask if mask.dim() == 4 else mask.unsqueeze(1)).float().clamp(0.0, 1.0)
-        if self.p_min > 0:
-            p = p.clamp_min(self.p_min)
-        if self.mode == "bernoulli_detach":
-            return torch.bernoulli(p.detach())
-        lo, hi = 1e-6, 1.0 - 1e-6
-        u1 = torch.rand_like(p).clamp_(lo, hi)
-        u2 = torch.rand_like(p).clamp_(lo, hi)
-        noise = torch.log(-torch.log(u2)) - torch.log(-torch.log(u1))  # difference of two Gumbels = logistic
-        pc = p.clamp(lo, hi)
-        soft = torch.sigmoid((torch.log(pc) - torch.log1p(-pc) + noise) / self.tau)
-        if self.mode == "hard_st":
-            return (soft > self.threshold).float() + (soft - soft.detach())
-        return soft
+        """Train-mode gate (probmaskgater.py:73-95) by the CUDA sampling kernel.  Noise contract (include/mga_cbam.h): Philox4x32-10
+        keyed by `self.seed` with the call counter as the stream offset -- the reference draws from torch's global generator with
+        seed=None (masked_cbam.py:74-78), so its samples are not reproducible either; parity is on the distribution and, with the
+        reference's own uniforms fed through `noise`, on the values (tests/test_gpu_next.py)."""
+        from . import next_ops
+
+        p = mask if mask.dim() == 4 else mask.unsqueeze(1)
+        if self.seed is None:  # fresh stream per module instance, drawn once from torch's generator (so torch.manual_seed governs it)
+            self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        out = next_ops.gate_sample(p.float(), self.mode, tau=self.tau, p_min=self.p_min, threshold=self.threshold, seed=self.seed, offset=self.calls)
+        self.calls += 1
+        return out
 
 
 class MaskGuidedCBAM(nn.Module):

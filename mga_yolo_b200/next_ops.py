@@ -1,0 +1,288 @@
+"""Torch-facing operators of the components either side of the block:
+
+    torch.ops.mga.eca_fwd / eca_bwd                   MaskECA                 (mga_yolo/nn/modules/masked_eca.py:139-193)
+    torch.ops.mga.head_tail_fwd / head_tail_bwd       MGAMaskHead.head        (mga_yolo/nn/modules/segmentation.py:94,107-110)
+    torch.ops.mga.gate_sample / gate_sample_bwd       ProbMaskGater, training (mga_yolo/nn/modules/probmaskgater.py:59-95)
+    torch.ops.mga.collate_masks                       masks_multi collate     (mga_yolo/data/dataset.py:149-169)
+
+CUDA dispatch key (the kernels of csrc/next_ops.cuh through the C ABI) and Meta key (shapes only): CPU tensors fail in the dispatcher.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from functools import lru_cache
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ops import _DT, _LIBDEF, _LIBIMPL, _stream
+
+GATE_MODES = {"gumbel": 0, "hard_st": 1, "bernoulli_detach": 2}
+
+_LIBDEF.define("eca_fwd(Tensor x, Tensor? mask, Tensor w1d, Tensor beta, int flags, float tiny_thr, float eps) -> (Tensor, Tensor)")
+_LIBDEF.define("eca_bwd(Tensor grad_out, Tensor x, Tensor? mask, Tensor w1d, Tensor ctx, int flags, float tiny_thr, float eps, bool need_mask_grad)"
+               " -> (Tensor, Tensor?, Tensor, Tensor)")
+_LIBDEF.define("head_tail_fwd(Tensor feat, Tensor weight, Tensor bias) -> Tensor")
+_LIBDEF.define("head_tail_bwd(Tensor grad_logits, Tensor feat, Tensor weight) -> (Tensor, Tensor, Tensor)")
+_LIBDEF.define("gate_sample(Tensor p, Tensor? noise, int mode, float tau, float p_min, float threshold, int seed, int offset) -> (Tensor, Tensor)")
+_LIBDEF.define("gate_sample_bwd(Tensor grad_out, Tensor p, Tensor soft, float tau, float p_min) -> Tensor")
+_LIBDEF.define("collate_masks(Tensor[] maps) -> Tensor")
+
+
+@lru_cache(maxsize=256)
+def _eca_desc(B, Cc, H, W, k, dt, mdt, flags, tiny, eps):
+    d = _lib.Desc(B, Cc, H, W, k, 1, dt, mdt, flags, tiny, eps)
+    cb, sb = C.c_size_t(0), C.c_size_t(0)
+    _lib.check(_lib.load().mga_eca_workspace(C.byref(d), C.byref(cb), C.byref(sb)), "mga_eca_workspace")
+    return d, int(cb.value), int(sb.value)
+
+
+def _eca_prep(x, mask, w1d, flags, tiny, eps):
+    if x.dim() != 4 or x.dtype not in _DT:
+        raise RuntimeError(f"feature map must be (B,C,H,W) float32 / bfloat16 / float16, got {tuple(x.shape)} {x.dtype}")
+    B, Cc, H, W = x.shape
+    mdt = _lib.F32
+    if mask is not None:
+        if mask.dtype not in _DT:
+            raise RuntimeError(f"unsupported mask dtype {mask.dtype}")
+        if mask.numel() != B * H * W or tuple(mask.shape[-2:]) != (H, W):
+            raise RuntimeError(f"mask {tuple(mask.shape)} does not match feature map {tuple(x.shape)}")  # masked_eca.py:149 expand fails too
+        mdt = _DT[mask.dtype]
+        flags |= _lib.HAS_MASK
+    else:
+        flags &= ~_lib.HAS_MASK
+    return _eca_desc(B, Cc, H, W, int(w1d.numel()), _DT[x.dtype], mdt, flags, float(tiny), float(eps))
+
+
+def _f32c(t):
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+def _eca_fwd_cuda(x, mask, w1d, beta, flags, tiny_thr, eps):
+    lib = _lib.load()
+    x = x.contiguous()
+    mask = None if mask is None else mask.contiguous()
+    d, ctx_bytes, scratch_bytes = _eca_prep(x, mask, w1d, flags, tiny_thr, eps)
+    w, b = _f32c(w1d.reshape(-1)), _f32c(beta)
+    with torch.cuda.device(x.device):
+        out = torch.empty_like(x)
+        ctx = torch.empty(ctx_bytes, dtype=torch.uint8, device=x.device)
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=x.device)
+        rc = lib.mga_eca_forward(C.byref(d), x.data_ptr(), None if mask is None else mask.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(),
+                                 ctx.data_ptr(), scratch.data_ptr(), _stream(x))
+    _lib.check(rc, "mga_eca_forward")
+    return out, ctx
+
+
+def _eca_bwd_cuda(grad_out, x, mask, w1d, ctx, flags, tiny_thr, eps, need_mask_grad):
+    lib = _lib.load()
+    x = x.contiguous()
+    grad_out = grad_out.contiguous().to(x.dtype)
+    mask = None if mask is None else mask.contiguous()
+    d, _, scratch_bytes = _eca_prep(x, mask, w1d, flags, tiny_thr, eps)
+    w = _f32c(w1d.reshape(-1))
+    with torch.cuda.device(x.device):
+        dx = torch.empty_like(x)
+        dmask = torch.empty_like(mask) if (mask is not None and need_mask_grad) else None
+        dw = torch.empty(w.numel(), dtype=torch.float32, device=x.device)
+        dbeta = torch.empty((), dtype=torch.float32, device=x.device)
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=x.device)
+        rc = lib.mga_eca_backward(C.byref(d), x.data_ptr(), None if mask is None else mask.data_ptr(), grad_out.data_ptr(), w.data_ptr(),
+                                  ctx.data_ptr(), dx.data_ptr(), None if dmask is None else dmask.data_ptr(), dw.data_ptr(), dbeta.data_ptr(),
+                                  scratch.data_ptr(), _stream(x))
+    _lib.check(rc, "mga_eca_backward")
+    return dx, dmask, dw, dbeta
+
+
+def _head_tail_fwd_cuda(feat, weight, bias):
+    lib = _lib.load()
+    if feat.dim() != 4 or feat.dtype not in _DT:
+        raise RuntimeError(f"hidden feature must be (B,C,H,W) float32 / bfloat16 / float16, got {tuple(feat.shape)} {feat.dtype}")
+    feat = feat.contiguous()
+    B, Cc, H, W = feat.shape
+    if tuple(weight.shape) != (1, Cc, 3, 3):
+        raise RuntimeError(f"head weight must be (1,{Cc},3,3), got {tuple(weight.shape)}")
+    w, b = _f32c(weight), _f32c(bias)
+    with torch.cuda.device(feat.device):
+        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=feat.device)
+        rc = lib.mga_head_tail_forward(feat.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), B, Cc, H, W, _DT[feat.dtype], _stream(feat))
+    _lib.check(rc, "mga_head_tail_forward")
+    return out
+
+
+def _head_tail_bwd_cuda(grad_logits, feat, weight):
+    lib = _lib.load()
+    feat = feat.contiguous()
+    B, Cc, H, W = feat.shape
+    g, w = _f32c(grad_logits), _f32c(weight)
+    with torch.cuda.device(feat.device):
+        dfeat = torch.empty_like(feat)
+        dw = torch.empty((1, Cc, 3, 3), dtype=torch.float32, device=feat.device)
+        db = torch.empty((1,), dtype=torch.float32, device=feat.device)
+        rc = lib.mga_head_tail_backward(feat.data_ptr(), w.data_ptr(), g.data_ptr(), dfeat.data_ptr(), dw.data_ptr(), db.data_ptr(), B, Cc, H, W,
+                                        _DT[feat.dtype], _stream(feat))
+    _lib.check(rc, "mga_head_tail_backward")
+    return dfeat, dw, db
+
+
+def _gate_sample_cuda(p, noise, mode, tau, p_min, threshold, seed, offset):
+    lib = _lib.load()
+    p = _f32c(p)
+    n = p.numel()
+    if noise is not None:
+        noise = _f32c(noise)
+        if noise.numel() != 2 * n:
+            raise RuntimeError("noise must hold two uniforms per element: shape (2, *p.shape)")
+    with torch.cuda.device(p.device):
+        out = torch.empty_like(p)
+        soft = torch.empty_like(p)
+        rc = lib.mga_gate_sample_forward(p.data_ptr(), None if noise is None else noise.data_ptr(), out.data_ptr(), soft.data_ptr(), None, n, int(mode),
+                                         float(tau), float(p_min), float(threshold), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), _stream(p))
+    _lib.check(rc, "mga_gate_sample_forward")
+    return out, soft
+
+
+def _gate_sample_bwd_cuda(grad_out, p, soft, tau, p_min):
+    lib = _lib.load()
+    g, p = _f32c(grad_out), _f32c(p)
+    with torch.cuda.device(p.device):
+        dp = torch.empty_like(p)
+        rc = lib.mga_gate_sample_backward(g.data_ptr(), p.data_ptr(), soft.data_ptr(), dp.data_ptr(), p.numel(), float(tau), float(p_min), _stream(p))
+    _lib.check(rc, "mga_gate_sample_backward")
+    return dp
+
+
+def _collate_cuda(maps: List[torch.Tensor]):
+    lib = _lib.load()
+    if not maps:
+        raise RuntimeError("collate_masks needs at least one map")
+    dev = maps[0].device
+    dt = maps[0].dtype
+    if dt not in (torch.uint8, torch.float32) or any(m.dtype != dt or m.device != dev for m in maps):
+        raise RuntimeError("collate_masks takes uint8 or float32 maps of one dtype on one device")
+    maps = [m.reshape(m.shape[-2], m.shape[-1]).contiguous() for m in maps]
+    H, W = max(m.shape[0] for m in maps), max(m.shape[1] for m in maps)
+    rec = np.zeros(len(maps), dtype=np.dtype([("src", np.uint64), ("h", np.int32), ("w", np.int32)]))
+    for i, m in enumerate(maps):
+        rec[i] = (m.data_ptr(), m.shape[0], m.shape[1])
+    with torch.cuda.device(dev):
+        items = torch.from_numpy(rec.view(np.uint8)).to(dev, non_blocking=False)
+        out = torch.empty((len(maps), 1, H, W), dtype=torch.float32, device=dev)
+        rc = lib.mga_collate_masks(items.data_ptr(), out.data_ptr(), len(maps), H, W, _lib.F32 if dt == torch.float32 else _lib.U8, _stream(out))
+    _lib.check(rc, "mga_collate_masks")
+    return out
+
+
+# ---- Meta kernels (shapes only)
+def _eca_fwd_meta(x, mask, w1d, beta, flags, tiny_thr, eps):
+    _, ctx_bytes, _ = _eca_prep(x, mask, w1d, flags, tiny_thr, eps)
+    return torch.empty_like(x, memory_format=torch.contiguous_format), x.new_empty(ctx_bytes, dtype=torch.uint8)
+
+
+def _eca_bwd_meta(grad_out, x, mask, w1d, ctx, flags, tiny_thr, eps, need_mask_grad):
+    dmask = torch.empty_like(mask, memory_format=torch.contiguous_format) if (mask is not None and need_mask_grad) else None
+    return (torch.empty_like(x, memory_format=torch.contiguous_format), dmask, x.new_empty(w1d.numel(), dtype=torch.float32),
+            x.new_empty((), dtype=torch.float32))
+
+
+def _head_tail_fwd_meta(feat, weight, bias):
+    B, _, H, W = feat.shape
+    return feat.new_empty((B, 1, H, W), dtype=torch.float32)
+
+
+def _head_tail_bwd_meta(grad_logits, feat, weight):
+    return torch.empty_like(feat, memory_format=torch.contiguous_format), feat.new_empty(weight.shape, dtype=torch.float32), feat.new_empty((1,), dtype=torch.float32)
+
+
+def _gate_sample_meta(p, noise, mode, tau, p_min, threshold, seed, offset):
+    return p.new_empty(p.shape, dtype=torch.float32), p.new_empty(p.shape, dtype=torch.float32)
+
+
+def _gate_sample_bwd_meta(grad_out, p, soft, tau, p_min):
+    return p.new_empty(p.shape, dtype=torch.float32)
+
+
+def _collate_meta(maps):
+    H, W = max(m.shape[-2] for m in maps), max(m.shape[-1] for m in maps)
+    return maps[0].new_empty((len(maps), 1, H, W), dtype=torch.float32)
+
+
+for _name, _cuda, _meta in (("eca_fwd", _eca_fwd_cuda, _eca_fwd_meta), ("eca_bwd", _eca_bwd_cuda, _eca_bwd_meta),
+                            ("head_tail_fwd", _head_tail_fwd_cuda, _head_tail_fwd_meta), ("head_tail_bwd", _head_tail_bwd_cuda, _head_tail_bwd_meta),
+                            ("gate_sample", _gate_sample_cuda, _gate_sample_meta), ("gate_sample_bwd", _gate_sample_bwd_cuda, _gate_sample_bwd_meta),
+                            ("collate_masks", _collate_cuda, _collate_meta)):
+    _LIBIMPL.impl(_name, _cuda, "CUDA")
+    _LIBIMPL.impl(_name, _meta, "Meta")
+
+
+def _need_cuda(t, what):
+    if t.device.type not in ("cuda", "meta"):
+        raise RuntimeError(f"mga_yolo_b200: {what} runs on CUDA tensors only (no CPU fallback)")
+
+
+class _EcaFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mask, w1d, beta, flags, tiny_thr, eps):
+        _need_cuda(x, "MaskECA")
+        out, saved = torch.ops.mga.eca_fwd(x, mask, w1d, beta, flags, tiny_thr, eps)
+        ctx.save_for_backward(x, mask, w1d, saved)
+        ctx.cfg = (flags, tiny_thr, eps)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, mask, w1d, saved = ctx.saved_tensors
+        flags, tiny_thr, eps = ctx.cfg
+        need_mask = mask is not None and ctx.needs_input_grad[1]
+        dx, dmask, dw, dbeta = torch.ops.mga.eca_bwd(grad_out, x, mask, w1d, saved, flags, tiny_thr, eps, need_mask)
+        return dx, dmask, dw.view(w1d.shape), dbeta, None, None, None
+
+
+def mask_eca(x, mask, w1d, beta, *, flags: int, tiny_mask_thr: float = 1e-4, eps: float = 1e-6):
+    """out = MaskECA([x, mask]) with the given conv1d weight (1,1,k) and beta (autograd-aware)."""
+    return _EcaFn.apply(x, mask, w1d, beta, int(flags), float(tiny_mask_thr), float(eps))
+
+
+class _HeadTailFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, weight, bias):
+        _need_cuda(feat, "the MGAMaskHead tail")
+        ctx.save_for_backward(feat, weight)
+        return torch.ops.mga.head_tail_fwd(feat, weight, bias)
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        feat, weight = ctx.saved_tensors
+        dfeat, dw, db = torch.ops.mga.head_tail_bwd(grad_logits, feat, weight)
+        return dfeat, dw.to(weight.dtype), db
+
+
+def head_tail(feat, weight, bias):
+    """Mask logits (B,1,H,W) fp32 = Conv2d(hidden, 1, 3, padding=1)(feat) by the CUDA tail kernel (autograd-aware)."""
+    return _HeadTailFn.apply(feat, weight, bias)
+
+
+class _GateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, noise, mode, tau, p_min, threshold, seed, offset):
+        _need_cuda(p, "ProbMaskGater sampling")
+        out, soft = torch.ops.mga.gate_sample(p, noise, mode, tau, p_min, threshold, seed, offset)
+        ctx.save_for_backward(p, soft)
+        ctx.cfg = (mode, tau, p_min)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        p, soft = ctx.saved_tensors
+        mode, tau, p_min = ctx.cfg
+        if mode == GATE_MODES["bernoulli_detach"]:
+            return (None,) * 8
+        return (torch.ops.mga.gate_sample_bwd(grad_out, p, soft, tau, p_min).view(p.shape).to(p.dtype),) + (None,) * 7
+
+
+def gate_sample(p: torch.Tensor, mode: str, *, tau: float = 1.0, p_min: float = 0.0, threshold: float = 0.5, seed: int = 0, offset: int = 0,
+                noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Train-mode ProbMaskGater on a (B,1,H,W) map; noise contract in include/mga_cbam.h (Philox4x32-10 keyed by seed, offset)."""
+    return _GateFn.apply(p, noise, GATE_MODES[mode], float(tau), float(p_min), float(threshold), int(seed), int(offset))

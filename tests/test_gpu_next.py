@@ -1,0 +1,201 @@
+"""GPU parity of the components either side of the block, through nn.Module -> torch op -> C ABI:
+MaskECA, the MGAMaskHead 3x3 tail, train-mode ProbMaskGater sampling (Philox noise contract) and the zero-pad collate.
+Fixtures come from running the reference (oracle/gen_golden_next.py); the oracles are pinned to them in test_oracle_golden.py.
+Tolerances as for the block: fp32 1e-5 (parameter gradients against the fp64 run), 16-bit 1e-2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import eca_oracle as eo
+from oracle import next_oracle as no
+from tests._golden import GOLDEN, rel_err, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _run_eca(mod, x, mask, g):
+    x = x.clone().requires_grad_(True)
+    mask = None if mask is None else mask.clone().requires_grad_(True)
+    for p in mod.parameters():
+        p.grad = None
+    out = mod(x if mask is None else [x, mask])
+    out.backward(g)
+    return out.detach(), x.grad, None if mask is None else mask.grad, mod.conv1d.weight.grad.clone(), mod.beta.grad.clone()
+
+
+@pytest.mark.parametrize("tag", ["basic", "beta", "edge", "nomask", "raw3d"])
+def test_eca_golden_cases_match_reference(tag):
+    from mga_yolo_b200 import MaskECA
+
+    z = np.load(GOLDEN / f"eca_{tag}.npz")
+    C, use_sig = (int(v) for v in z["cfg"])
+    mod = MaskECA(C, use_sigmoid_mask=bool(use_sig))
+    mod.load_state_dict({"conv1d.weight": t(z["w1d"]), "beta": t(z["beta"])}, strict=True)
+    mod.to(DEV)
+    mask = t(z["mask"]).to(DEV) if bool(z["has_mask"]) else None
+    out, dx, dmask, dw, dbeta = _run_eca(mod, t(z["x"]).to(DEV), mask, t(z["g"]).to(DEV))
+    assert rel_err(out.cpu(), t(z["out"])) <= 1e-5
+    assert rel_err(dx.cpu(), t(z["dx"])) <= 1e-5
+    if mask is not None:
+        assert dmask.shape == mask.shape and rel_err(dmask.cpu(), t(z["dmask"])) <= 1e-5
+    assert rel_err(dw.cpu(), t(z["d.conv1d.weight_f64"])) <= 2e-5
+    assert rel_err(dbeta.cpu(), t(z["d.beta_f64"])) <= 2e-5
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 80, 80), (2, 256, 20, 20), (2, 96, 17, 13), (1, 8, 8, 8)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_eca_matches_oracle_at_neck_shapes(shape, dtype):
+    from mga_yolo_b200 import MaskECA
+
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B, C, H, W, generator=gen).to(dtype)
+    mask = torch.randn(B, 1, H, W, generator=gen)
+    mask[0] = -20.0
+    g = torch.randn(B, C, H, W, generator=gen).to(dtype)
+    torch.manual_seed(C)
+    mod = MaskECA(C)
+    with torch.no_grad():
+        mod.beta.fill_(0.3)
+    w1d, beta = mod.conv1d.weight.detach().clone().double().reshape(-1), mod.beta.detach().clone().double()
+    mod.to(DEV)
+    out, dx, dmask, dw, dbeta = _run_eca(mod, x.to(DEV), mask.to(DEV), g.to(DEV))
+    ref_out, sv = eo.eca_forward(x.double(), mask.double(), w1d, beta)
+    ref = eo.eca_backward(g.double(), sv)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert out.dtype == dtype and rel_err(out.float().cpu(), ref_out) <= tol
+    assert rel_err(dx.float().cpu(), ref["dx"]) <= tol
+    assert rel_err(dmask.cpu(), ref["dmask"]) <= (1e-5 if dtype == torch.float32 else 1e-2)
+    ptol = 5e-5 if dtype == torch.float32 else 1e-2
+    assert rel_err(dw.cpu(), ref["conv1d.weight"]) <= ptol
+    assert rel_err(dbeta.cpu(), ref["beta"]) <= max(ptol, 4e-5)
+
+
+def test_eca_module_contract():
+    from mga_yolo_b200 import MaskECA
+    from mga_yolo_b200.eca import eca_kernel_size
+
+    mod = MaskECA(128).to(DEV)
+    assert set(mod.state_dict()) == {"conv1d.weight", "beta"} and mod.conv1d.weight.shape[-1] == eca_kernel_size(128) == eo.eca_kernel_size(128)
+    assert abs(float(mod.alpha.detach()) - 0.6931471805599453) < 1e-6
+    x = torch.randn(2, 128, 8, 8, device=DEV)
+    assert mod(x).shape == x.shape and mod([x, torch.randn(2, 8, 8, device=DEV)]).shape == x.shape  # Tensor / [feat, 3-D mask]
+    with pytest.raises(RuntimeError):
+        mod(x.cpu())
+    with pytest.raises(RuntimeError):
+        mod([x, torch.randn(2, 1, 4, 4, device=DEV)])
+
+
+@pytest.mark.parametrize("tag", ["p3", "odd"])
+def test_head_tail_matches_reference(tag):
+    from mga_yolo_b200 import next_ops
+
+    z = np.load(GOLDEN / f"head_{tag}.npz")
+    feat = t(z["feat"]).to(DEV).requires_grad_(True)
+    w = t(z["w"]).to(DEV).requires_grad_(True)
+    b = t(z["b"]).to(DEV).requires_grad_(True)
+    out = next_ops.head_tail(feat, w, b)
+    out.backward(t(z["g"]).to(DEV))
+    assert rel_err(out.detach().cpu(), t(z["out"])) <= 1e-5
+    assert rel_err(feat.grad.cpu(), t(z["dfeat"])) <= 1e-5
+    assert rel_err(w.grad.cpu(), t(z["dw_f64"])) <= 2e-5
+    assert rel_err(b.grad.cpu(), t(z["db_f64"])) <= 2e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_mask_head_module_feeds_the_block(dtype, monkeypatch):
+    """MGAMaskHead (tail in the CUDA library) -> MaskGuidedCBAM -> loss: logits, and the gradient that flows back through dmask into the
+    head's parameters, against the same modules run with the library convolution for the tail."""
+    from mga_yolo_b200 import MGAMaskHead, MaskGuidedCBAM
+
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)  # the comparator (library convolution) must be real fp32
+    torch.manual_seed(0)
+    C, hidden, B, H, W = 64, 32, 2, 40, 40
+    head = MGAMaskHead(C, hidden).to(DEV).to(dtype)
+    blk = MaskGuidedCBAM(C).to(DEV)
+    assert set(head.state_dict()) == {"proj.0.weight", "proj.1.weight", "proj.1.bias", "proj.1.running_mean", "proj.1.running_var",
+                                      "proj.1.num_batches_tracked", "head.weight", "head.bias"}
+    x = torch.randn(B, C, H, W, device=DEV, dtype=dtype)
+    head.eval()
+
+    def step(use_kernel):
+        for p in head.parameters():
+            p.grad = None
+        xi = x.clone().requires_grad_(True)
+        feat = head.proj(xi)
+        logits = head(xi) if use_kernel else head.head(feat).float()
+        out = blk([xi, logits])
+        out.float().square().mean().backward()
+        return logits.detach().float(), xi.grad.float(), head.head.weight.grad.float().clone(), head.proj[0].weight.grad.float().clone()
+
+    got, ref = step(True), step(False)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    for a, r in zip(got, ref):
+        assert rel_err(a.cpu(), r.cpu()) <= tol
+
+
+@pytest.mark.parametrize("tag", ["gumbel", "gumbel_pmin", "hard_st"])
+def test_gate_sampling_reproduces_reference_given_its_uniforms(tag):
+    from mga_yolo_b200 import next_ops
+
+    z = np.load(GOLDEN / f"gate_{tag}.npz")
+    tau, p_min, thr = (float(v) for v in z["cfg"])
+    p = t(z["p"]).to(DEV).requires_grad_(True)
+    noise = torch.stack([t(z["u0"]), t(z["u1"])]).to(DEV)
+    out = next_ops.gate_sample(p, str(z["mode"]), tau=tau, p_min=p_min, threshold=thr, noise=noise)
+    out.backward(t(z["g"]).to(DEV))
+    if str(z["mode"]) == "hard_st":  # a soft value within rounding of the threshold may flip
+        assert (out.detach().cpu() != t(z["out"])).float().mean().item() <= 0.005
+    else:
+        assert rel_err(out.detach().cpu(), t(z["out"])) <= 1e-5
+    assert rel_err(p.grad.cpu(), t(z["dp"])) <= 1e-4
+
+
+def test_gate_noise_contract_is_philox_keyed_by_seed_and_offset():
+    from mga_yolo_b200 import _lib, next_ops
+    import ctypes as C
+
+    lib = _lib.load()
+    n = 4096
+    p = torch.full((n,), 0.3, device=DEV)
+    out, soft, noise = torch.empty_like(p), torch.empty_like(p), torch.empty(2 * n, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.mga_gate_sample_forward(p.data_ptr(), None, out.data_ptr(), soft.data_ptr(), noise.data_ptr(), n, 0, 1.0, 0.0, 0.5, 1234, 7, st), "gate")
+    u1, u2 = no.gate_uniforms(n, seed=1234, offset=7)
+    got = noise.cpu().numpy()
+    assert np.array_equal(got[:n], u1) and np.array_equal(got[n:], u2)  # bit-exact stream
+    ref_out, _ = no.gate_forward(p.cpu(), torch.from_numpy(u1), torch.from_numpy(u2), mode="gumbel", tau=1.0)
+    assert rel_err(out.cpu(), ref_out) <= 1e-5
+    a = next_ops.gate_sample(p, "gumbel", seed=5, offset=0)
+    assert torch.equal(a, next_ops.gate_sample(p, "gumbel", seed=5, offset=0))          # same (seed, offset): same sample
+    assert not torch.equal(a, next_ops.gate_sample(p, "gumbel", seed=5, offset=1))      # the caller advances the offset per call
+    b = next_ops.gate_sample(torch.full((200000,), 0.3, device=DEV), "bernoulli_detach", seed=9, offset=0)
+    assert set(b.unique().tolist()) <= {0.0, 1.0} and abs(b.mean().item() - 0.3) < 0.01  # Bernoulli(p)
+    g = next_ops.gate_sample(torch.full((200000,), 0.3, device=DEV), "gumbel", seed=9, offset=3)
+    assert abs(g.median().item() - 0.3) < 0.01  # logistic noise is symmetric: the median of sigmoid(logit(p) + noise) is p
+
+
+def test_train_mode_gate_inside_the_block(monkeypatch):
+    from mga_yolo_b200 import MaskGuidedCBAM
+
+    monkeypatch.setenv("MGA_PROB_MODE", "1")
+    monkeypatch.setenv("MGA_PROB_APPROACH", "gumbel")
+    torch.manual_seed(0)
+    blk = MaskGuidedCBAM(32).to(DEV).train()
+    x = torch.randn(2, 32, 16, 16, device=DEV, requires_grad=True)
+    m = torch.rand(2, 1, 16, 16, device=DEV, requires_grad=True)
+    o1 = blk([x, m])
+    o1.sum().backward()
+    assert torch.isfinite(o1).all() and m.grad is not None and torch.isfinite(m.grad).all() and m.grad.abs().sum() > 0
+    assert blk.gater.calls == 1 and not torch.equal(o1, blk([x, m]))  # a fresh noise stream offset per forward
+
+
+def test_collate_matches_reference_rule():
+    from mga_yolo_b200 import MaskUtils
+
+    rng = np.random.default_rng(0)
+    for dt in (np.float32, np.uint8):
+        per = [(rng.random((h, w)) > 0.5).astype(dt) if dt == np.uint8 else rng.random((h, w)).astype(dt) for h, w in ((10, 8), (7, 12), (10, 12), (1, 1))]
+        got = MaskUtils.collate_masks([torch.from_numpy(a).to(DEV) for a in per])
+        assert got.dtype == torch.float32 and np.array_equal(got.cpu().numpy(), no.collate_masks(per))
