@@ -1,4 +1,4 @@
-"""Swap the reference's `MaskCBAM` for the B200 implementation, in place.
+"""Swap the reference's `MaskCBAM` (and its neighbours `MaskECA`, `MGAMaskHead`) for the B200 implementations, in place.
 
 parse_model resolves YAML class names through `globals()` of ultralytics/nn/tasks.py and
 then tests `m is MaskCBAM` (tasks.py:1676-1682,1733-1739), so the patched object has to be
@@ -13,10 +13,17 @@ from typing import Dict, Tuple
 
 import functools
 
+from .eca import MaskECA
+from .head import MGAMaskHead
 from .module import MaskCBAM, shape_probe
 
+# YAML class name -> replacement (ultralytics/nn/tasks.py:1724 `m is MGAMaskHead`, :1733 `m is MaskECA or ... m is MaskCBAM`)
+_CLASSES = {"MaskCBAM": MaskCBAM, "MaskECA": MaskECA, "MGAMaskHead": MGAMaskHead}
 _TARGETS = (
     "mga_yolo.nn.modules.masked_cbam",
+    "mga_yolo.nn.modules.masked_eca",
+    "mga_yolo.nn.modules.segmentation",
+    "mga_yolo.model.model",  # `isinstance(m, MGAMaskHead)` against its import-time global decides which layers feed "seg" (model.py:11,217-220)
     "ultralytics.nn.tasks",
     "ultralytics.nn",
     "mga_yolo.external.ultralytics.ultralytics.nn.tasks",
@@ -48,19 +55,26 @@ def _unwrap_builder(cls) -> None:
         cls.__init__ = init._mga_original
 
 
-def install(strict: bool = False) -> list:
-    """Patch every already-imported module that exposes `MaskCBAM`; returns the patched module names.
+def install(strict: bool = False, classes=("MaskCBAM", "MaskECA", "MGAMaskHead")) -> list:
+    """Patch every already-imported module that exposes one of `classes`; returns the patched module names.
     The graph builder's `DetectionModel.__init__` (the base of MGAModel, mga_yolo/model/model.py:40) is wrapped so that
     its CPU stride probe passes through the block as a shape-only call."""
     done = []
     for name in _TARGETS:
         mod = sys.modules.get(name)
-        if mod is None or not hasattr(mod, "MaskCBAM"):
+        if mod is None:
             continue
-        key = (name, "MaskCBAM")
-        if key not in _saved:
-            _saved[key] = getattr(mod, "MaskCBAM")
-        setattr(mod, "MaskCBAM", MaskCBAM)
+        hit = False
+        for attr in classes:
+            if getattr(mod, attr, None) is None:  # (tasks.py sets the name to None when its import failed)
+                continue
+            key = (name, attr)
+            if key not in _saved:
+                _saved[key] = getattr(mod, attr)
+            setattr(mod, attr, _CLASSES[attr])
+            hit = True
+        if not hit:
+            continue
         if name.endswith("nn.tasks") and isinstance(getattr(mod, "DetectionModel", None), type):
             _wrap_builder(mod.DetectionModel)
         done.append(name)

@@ -372,6 +372,14 @@ def test_install_builds_the_reference_model_from_its_yaml():
         meta = copy.deepcopy(model).to("meta")  # whole-graph shape propagation through the Meta kernels
         out = meta(torch.empty(1, 3, 64, 64, device="meta"))
         assert set(out) == {"det", "seg"} and [t.shape[-1] for t in out["det"]] == [8, 4, 2]
+        assert len(out["seg"]) == 3  # the swapped mask heads are still recognised as the producers of "seg" (model.py:217-220)
+        # the neighbours are swapped too: the mask heads (producers of the logits) and, in the ECA model, the MaskECA blocks
+        heads = [m for m in model.model if isinstance(m, mb.MGAMaskHead)]
+        assert [m.i for m in heads] == [22, 24, 26] and all(set(h.state_dict()) >= {"head.weight", "head.bias", "proj.0.weight"} for h in heads)
+        eca = MGAModel(str(REF / "configs/models/yolov8n_eca.yaml"), nc=1, verbose=False)
+        ecas = [m for m in eca.model if isinstance(m, mb.MaskECA)]
+        assert [m.cfg.channels for m in ecas] == [64, 128, 256]
+        assert set(copy.deepcopy(eca).to("meta")(torch.empty(1, 3, 64, 64, device="meta"))) == {"det", "seg"}
     finally:
         mb.uninstall()
     from mga_yolo.external.ultralytics.ultralytics.nn import tasks
