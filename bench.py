@@ -320,7 +320,9 @@ def measure(args, lib, dev, world, levels, B, dtype, flags, steps, warmup, one_s
     sets = build_plans(levels, B, dtype, flags, dev, nsets=2)
     stream = torch.cuda.current_stream(dev)
     sptr = stream.cuda_stream
-    sides = [torch.cuda.Stream(dev) for _ in levels[1:]] if not (args.one_stream or one_stream) else []
+    # the side streams (one per extra level) run at HIGH priority: under torchrun the asynchronous NCCL all-reduce of the previous step
+    # then never takes CTA slots from the cluster kernels of the current one (+11 us per step at N >= 2)
+    sides = [torch.cuda.Stream(dev, priority=-1) for _ in levels[1:]] if not (args.one_stream or one_stream) else []
 
     def step_on(plans, main):
         if sides:
@@ -580,6 +582,10 @@ def gpu_arm(args, rank, world, local_rank):
                         "dominant_kernel": None if bw is None else {"kernel": f"{bw['kernel']}[{bw['level']}]", "ms": round(bw["ms"], 5),
                                                                      "achieved": round(bw["gbps"], 1), "frac": round(bw["frac"], 4)},
                         "kernels": [{"kernel": k["kernel"], "level": k["level"], "ms": round(k["ms"], 5), "frac": round(k.get("frac", 0.0), 4)} for k in r["kernels"]]}
+        bfp = None
+        if peaks_path.exists():
+            bfp = json.loads(peaks_path.read_text()).get("bf16_tflops_sustained")
+        wl["cfg4"] = concat_workload(dev, peak, bfp)
         line["workloads"] = wl
     if args.workload == "cfg2" and not args.batch and not strong and not args.no_workloads and 256 % world == 0:
         # BASELINE configs[2] as it is stated: YOLOv8s bf16, GLOBAL batch 256 sharded over the ranks (strong scaling: 256 / N samples
@@ -608,6 +614,61 @@ def gpu_arm(args, rank, world, local_rank):
                                              else "oracle/cbam_oracle.py forward + torch autograd backward"),
                                 "images_per_sec": round(cb / sec, 1)}
     return line
+
+
+def concat_workload(dev, peak, bf16_peak_tflops):
+    """BASELINE configs[3]: YOLOv8m (reference-YAML widths 256/512/512), batch 128 bf16, sam_cam_fusion=concat + mga_pyramid_fusion=multiply,
+    fwd+bwd through the public nn.Module.  These two modes have no reference source (parity unpinned, in-repo
+    oracle); the block's gates (s, a') come from the CUDA gates op, the 2C->C 1x1 convolution is a library GEMM (cuDNN / cuBLAS) and the
+    elementwise glue is eager torch -- NOT a fused kernel (DESIGN.md section 7 says what a tcgen05 version would take)."""
+    from mga_yolo_b200 import MaskGuidedCBAM
+
+    levels, B, dtype = [(256, 80, 80), (512, 40, 40), (512, 20, 20)], 128, torch.bfloat16
+    gen = torch.Generator(device=dev).manual_seed(5)
+    work = []
+    try:
+        for (Cc, H, W) in levels:
+            torch.manual_seed(Cc)
+            mod = MaskGuidedCBAM(Cc, sam_cam_fusion="concat", mga_pyramid_fusion="multiply").to(dev)
+            sets = [(torch.randn(B, Cc, H, W, generator=gen, device=dev).to(dtype), torch.randn(B, 1, H, W, generator=gen, device=dev),
+                     torch.randn(B, Cc, H, W, generator=gen, device=dev).to(dtype)) for _ in range(2)]
+            work.append((mod, sets))
+
+        def step(i):
+            for mod, sets in work:
+                x, mk, g = sets[i & 1]
+                xi = x.detach().requires_grad_(True)
+                mi = mk.detach().requires_grad_(True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    out = mod([xi, mi])
+                out.backward(g)
+                mod.zero_grad(set_to_none=True)
+
+        for i in range(3):
+            step(i)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 6
+        e0.record()
+        for i in range(reps):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    finally:
+        work.clear()
+        torch.cuda.empty_cache()
+    ab = algorithmic_bytes(levels, B, 2)
+    flops = sum(3 * 2.0 * (B * H * W) * (2 * Cc) * Cc for (Cc, H, W) in levels)  # forward GEMM + two backward GEMMs of the 2C->C 1x1 conv
+    return {"workload": "BASELINE configs[3]: YOLOv8m (256/512/512 ch) batch 128 bf16, sam_cam_fusion=concat, mga_pyramid_fusion=multiply (module-only fwd+bwd)",
+            "levels_CHW": levels, "batch": B, "dtype": "bfloat16", "ms_per_step": round(ms, 4), "steps": reps, "warmup": 3,
+            "value": round(ab / (ms * 1e-3) / 1e9, 1), "unit": "GB/s", "step_frac": round(ab / (ms * 1e-3) / 1e9 / peak, 4),
+            "images_per_sec": round(B / (ms * 1e-3), 1), "gemm_tflops": round(flops / (ms * 1e-3) / 1e12, 1),
+            "gemm_frac_of_bf16_sustained": None if not bf16_peak_tflops else round(flops / (ms * 1e-3) / 1e12 / bf16_peak_tflops, 4),
+            "path": "CUDA gates op (s, a') + library 1x1 convolution (cuDNN / cuBLAS GEMM) + eager elementwise: not a fused kernel",
+            "note": "oracle: in-repo PyTorch composition; reference parity unpinned"}
 
 
 def gpu_eager_baseline(dev, levels, B, dtype, alg_bytes, sam_cam):

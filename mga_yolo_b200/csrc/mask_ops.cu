@@ -179,7 +179,9 @@ __global__ void __launch_bounds__(kMultiThreads) masks_multi_kernel(const uint8_
     uint8_t* wa = reinterpret_cast<uint8_t*>(c32 + n32);  // work planes for the close: [n8] x 2
     uint8_t* wb = wa + n8;
     const uint8_t* sp = src + (size_t)b * a.H * a.W;
-    if (pre_cnt8 != nullptr) {  // two-stage form: the 8x8 block counts were made by masks_count8_kernel
+    // two-stage form: the 8x8 block counts were made by masks_count8_kernel and gridDim.y == 3: this CTA derives ONE stride (blockIdx.y)
+    const int only = pre_cnt8 != nullptr ? (int)blockIdx.y : -1;
+    if (pre_cnt8 != nullptr) {
         for (int i = threadIdx.x; i < n8; i += kMultiThreads) {
             c8[i] = pre_cnt8[(size_t)b * n8 + i];
             t8[i] = pre_tl8[(size_t)b * n8 + i];
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(kMultiThreads) masks_multi_kernel(const uint8_
     __syncthreads();
     // per stride: raw map -> (close) -> store
     for (int lvl = 0; lvl < 3; ++lvl) {
+        if (only >= 0 && lvl != only) continue;
         const int h = lvl == 0 ? h8 : (lvl == 1 ? h16 : h32), w = lvl == 0 ? w8 : (lvl == 1 ? w16 : w32), n = h * w;
         const int s = 8 << lvl;
         void* dst = lvl == 0 ? d8 : (lvl == 1 ? d16 : d32);
@@ -334,7 +337,7 @@ extern "C" int mga_masks_multi_ws(const uint8_t* src, void* dst8, void* dst16, v
         const size_t total = (size_t)B * n8;
         masks_count8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, cnt8, tl8, B, H, W);
     }
-    masks_multi_kernel<<<B, kMultiThreads, smem, st>>>(src, dst8, dst16, dst32, a, cnt8, tl8);
+    masks_multi_kernel<<<dim3(B, cnt8 ? 3 : 1), kMultiThreads, smem, st>>>(src, dst8, dst16, dst32, a, cnt8, tl8);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bad(MGA_ERR_CUDA, cudaGetErrorString(e));
     return MGA_OK;
