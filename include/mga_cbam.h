@@ -130,6 +130,14 @@ int mga_cbam_gates_backward(const mga_cbam_desc* d, const void* x, const void* m
                             const mga_cbam_params* p, const void* ctx, void* grad_x, void* grad_mask, const mga_cbam_grads* gp,
                             void* scratch, void* stream);
 
+/* Fused forward of sam_cam_fusion = concat (build-side mode, parity unpinned) on the tcgen05 tensor cores, 16-bit features:
+ *   out = k0 * x + k1 * (Wa (x * s) + Wb (x * a) + bias),   W = [Wa | Wb] (C, 2C) fp32 = fuse_sam_cam.weight, alpha = softplus(*beta),
+ *   (k0, k1) = (1 - alpha, alpha), or (0, alpha) with MGA_PYRAMID_MULTIPLY in d->flags.
+ * s (B,C) and a (B,H*W) are the fp32 gates of mga_cbam_gates_forward.  wscratch: (B + 1) * C * C elements of the feature dtype.
+ * Needs C % 128 == 0 and H*W % 8 == 0 (MGA_ERR_UNSUPPORTED otherwise: compose the mode from the gates op and a library GEMM). */
+int mga_cbam_concat_forward(const mga_cbam_desc* d, const void* x, const float* s, const float* a, const float* w, const float* bias,
+                            const float* beta, void* out, void* wscratch, void* stream);
+
 /* read-back of small saved quantities for tests / logging: which = 0 s(B,C), 1 a(B,HW) */
 int mga_cbam_ctx_view(const mga_cbam_desc* d, const void* ctx, int which, const float** ptr, size_t* count);
 

@@ -10,6 +10,7 @@
 
 #include "cbam_bwd.cuh"
 #include "cbam_cluster.cuh"
+#include "cbam_concat.cuh"
 #include "cbam_conv.cuh"
 #include "cbam_fwd.cuh"
 #include "common.cuh"
@@ -779,6 +780,49 @@ static int backward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, co
                                           static_cast<T*>(dx), dmask, gp, bs, st);
 }
 
+
+// ------------------------------------------------------------------ fused concat forward (cbam_concat.cuh)
+static bool concat_map(CUtensorMap* out, const void* base, CUtensorMapDataType dt, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) || (inner * 2) % 16) return false;
+    const cuuint64_t dims[2] = {inner, rows};
+    const cuuint64_t strides[1] = {inner * 2};
+    const cuuint32_t box[2] = {box_inner, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename T>
+static int concat_forward_t(const mga_cbam_desc* d, const void* x, const float* s, const float* a, const float* w, const float* bias, const float* beta,
+                            void* out, void* wscratch, cudaStream_t st) {
+    const int B = d->B, C = d->C, S = d->H * d->W;
+    T* wa = static_cast<T*>(wscratch);
+    T* wb = wa + (size_t)B * C * C;
+    const CUtensorMapDataType dt = std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    ConcatMaps maps;
+    if (!concat_map(&maps.wa, wa, dt, C, (uint64_t)B * C, kCcBK, kCcBM) || !concat_map(&maps.wb, wb, dt, C, C, kCcBK, kCcBM) ||
+        !concat_map(&maps.x, x, dt, S, (uint64_t)B * C, 64, kCcBK))
+        return fail(MGA_ERR_UNSUPPORTED, "mga_cbam_concat_forward: tensor maps (16-byte aligned pointers, H*W %% 8 == 0)");
+    const size_t n = (size_t)(B + 1) * C * C;
+    MGA_LAUNCH("concat_fold", st, (concat_fold_kernel<T><<<(unsigned)std::min<size_t>((n + kBlock - 1) / kBlock, (size_t)kSMs * 16), kBlock, 0, st>>>(w, s, wa, wb, B, C)));
+    static thread_local int configured_dev[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool done = false;
+    for (int v : configured_dev) done |= (v == dev);
+    if (!done) {
+        if (cudaFuncSetAttribute(concat_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCcSmemBytes) != cudaSuccess)
+            return fail(MGA_ERR_CUDA, "mga_cbam_concat_forward: cudaFuncSetAttribute");
+        for (int& v : configured_dev)
+            if (v < 0) { v = dev; break; }
+    }
+    const dim3 grid((S + kCcBN - 1) / kCcBN, C / kCcBM, B);
+    MGA_LAUNCH("concat_fwd", st, (concat_fwd_kernel<T><<<grid, kCcThreads, kCcSmemBytes, st>>>(maps, static_cast<const T*>(x), a, bias, beta, static_cast<T*>(out), C, S,
+                                                                                             (d->flags & MGA_PYRAMID_MULTIPLY) ? 1 : 0)));
+    return check_launch("mga_cbam_concat_forward");
+}
+
 }  // namespace mga
 
 using namespace mga;
@@ -933,6 +977,19 @@ int mga_cbam_gates_backward(const mga_cbam_desc* d, const void* x, const void* m
         case MGA_BF16: return backward_t<__nv_bfloat16>(sh, &g, x, mask, x, *p, ctx, grad_x, grad_mask, *gp, bs, st);
         default: return backward_t<__half>(sh, &g, x, mask, x, *p, ctx, grad_x, grad_mask, *gp, bs, st);
     }
+}
+
+
+int mga_cbam_concat_forward(const mga_cbam_desc* d, const void* x, const float* s, const float* a, const float* w, const float* bias,
+                            const float* beta, void* out, void* wscratch, void* stream) {
+    if (!d || !x || !s || !a || !w || !bias || !beta || !out || !wscratch) return fail(MGA_ERR_ARG, "null pointer argument");
+    if (d->B <= 0 || d->C <= 0 || d->H <= 0 || d->W <= 0 || d->B > 65535) return fail(MGA_ERR_ARG, "bad shape");
+    if (d->dtype != MGA_BF16 && d->dtype != MGA_F16) return fail(MGA_ERR_UNSUPPORTED, "the tensor-core concat forward takes bf16 / f16 features");
+    if (d->C % kCcBM || (d->H * d->W) % 8 || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(a) & 15))
+        return fail(MGA_ERR_UNSUPPORTED, "needs C %% 128 == 0, H*W %% 8 == 0 and 16-byte aligned tensors");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d->dtype == MGA_BF16) return concat_forward_t<__nv_bfloat16>(d, x, s, a, w, bias, beta, out, wscratch, st);
+    return concat_forward_t<__half>(d, x, s, a, w, bias, beta, out, wscratch, st);
 }
 
 int mga_cbam_ctx_view(const mga_cbam_desc* d, const void* ctx_buf, int which, const float** ptr, size_t* count) {

@@ -29,7 +29,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib, ops
+from . import _lib, next_ops, ops
 
 _GATE_MODES = ("deterministic", "gumbel", "hard_st", "bernoulli_detach")
 # sam_cam_fusion: how the channel gate s and the spatial gate a combine
@@ -210,6 +210,12 @@ class MaskGuidedCBAM(nn.Module):
         else:
             s, a = ops.cbam_gates(feat, mask, lin1.weight, lin1.bias, lin2.weight, lin2.bias, self.sam_conv.weight,
                                   flags=flags & ~_lib.PYRAMID_MULTIPLY, tiny_mask_thr=self.tiny_thr, eps=self.eps)
+            if (self.sam_cam_fusion == "concat" and self.mga_pyramid_fusion in ("add", "multiply") and next_ops.concat_fused_supported(feat)
+                    and not os.getenv("MGA_CONCAT_LIBRARY", "")):
+                # 16-bit features with C % 128 == 0: ONE tcgen05 kernel does the (virtual) concat, both 1x1 convolutions, the spatial
+                # gate and the pyramid fusion (csrc/cbam_concat.cuh); the backward is the closed form on library GEMMs
+                return next_ops.concat_fused(feat, s, a, self.fuse_sam_cam.weight, self.fuse_sam_cam.bias, self.beta,
+                                             self.mga_pyramid_fusion == "multiply")
             xs = feat * s.to(dt)[:, :, None, None]
             xa = feat * a.to(dt)
             if self.sam_cam_fusion == "concat":

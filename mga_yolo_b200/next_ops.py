@@ -286,3 +286,88 @@ def gate_sample(p: torch.Tensor, mode: str, *, tau: float = 1.0, p_min: float = 
                 noise: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Train-mode ProbMaskGater on a (B,1,H,W) map; noise contract in include/mga_cbam.h (Philox4x32-10 keyed by seed, offset)."""
     return _GateFn.apply(p, noise, GATE_MODES[mode], float(tau), float(p_min), float(threshold), int(seed), int(offset))
+
+
+# ---------------------------------------------------------------- sam_cam_fusion = concat: fused forward on the tensor cores
+_LIBDEF.define("cbam_concat_fwd(Tensor x, Tensor s, Tensor a, Tensor w, Tensor bias, Tensor beta, bool pyramid_multiply) -> Tensor")
+
+
+def concat_fused_supported(x: torch.Tensor) -> bool:
+    """Shapes / types mga_cbam_concat_forward takes (include/mga_cbam.h)."""
+    return (x.is_cuda and x.dim() == 4 and x.dtype in (torch.bfloat16, torch.float16) and x.shape[1] % 128 == 0
+            and (x.shape[2] * x.shape[3]) % 8 == 0)
+
+
+def _concat_fwd_cuda(x, s, a, w, bias, beta, pyramid_multiply):
+    lib = _lib.load()
+    x = x.contiguous()
+    B, Cc, H, W = x.shape
+    if tuple(w.shape[:2]) != (Cc, 2 * Cc):
+        raise RuntimeError(f"fuse_sam_cam weight must be ({Cc},{2 * Cc},1,1), got {tuple(w.shape)}")
+    s, a, w, bias, beta = _f32c(s), _f32c(a), _f32c(w.reshape(Cc, 2 * Cc)), _f32c(bias), _f32c(beta)
+    d = _lib.Desc(B, Cc, H, W, 1, 1, _DT[x.dtype], _lib.F32, _lib.PYRAMID_MULTIPLY if pyramid_multiply else 0, 0.0, 0.0)
+    with torch.cuda.device(x.device):
+        out = torch.empty_like(x)
+        ws = torch.empty((B + 1) * Cc * Cc, dtype=x.dtype, device=x.device)
+        rc = lib.mga_cbam_concat_forward(C.byref(d), x.data_ptr(), s.data_ptr(), a.data_ptr(), w.data_ptr(), bias.data_ptr(), beta.data_ptr(),
+                                         out.data_ptr(), ws.data_ptr(), _stream(x))
+    _lib.check(rc, "mga_cbam_concat_forward")
+    return out
+
+
+def _concat_fwd_meta(x, s, a, w, bias, beta, pyramid_multiply):
+    return torch.empty_like(x, memory_format=torch.contiguous_format)
+
+
+_LIBIMPL.impl("cbam_concat_fwd", _concat_fwd_cuda, "CUDA")
+_LIBIMPL.impl("cbam_concat_fwd", _concat_fwd_meta, "Meta")
+
+
+class _ConcatFn(torch.autograd.Function):
+    """out = k0 x + k1 (Wa (x s) + Wb (x a) + bias).  Forward: ONE tcgen05 kernel (+ the weight-folding pre-kernel).  Backward: closed form
+    on library GEMMs (torch.matmul / bmm) -- the 2C-channel concat tensor is not formed in either direction."""
+
+    @staticmethod
+    def forward(ctx, x, s, a, w, bias, beta, pyramid_multiply):
+        out = torch.ops.mga.cbam_concat_fwd(x, s, a, w, bias, beta, pyramid_multiply)
+        ctx.save_for_backward(x, s, a, w, beta, out)
+        ctx.pm = pyramid_multiply
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, s, a, w, beta, out = ctx.saved_tensors
+        B, Cc, H, W = x.shape
+        S = H * W
+        dt = x.dtype
+        alpha = torch.nn.functional.softplus(beta.float())
+        k0 = torch.zeros_like(alpha) if ctx.pm else 1.0 - alpha
+        w2 = w.reshape(Cc, 2 * Cc).float()
+        wa, wb = w2[:, :Cc].to(dt), w2[:, Cc:].to(dt)
+        xf = x.reshape(B, Cc, S)
+        g = gout.reshape(B, Cc, S).to(dt)
+        dR = alpha.to(dt) * g                                                # (B,C,S)
+        U = torch.matmul(wa.t(), dR)                                         # Wa^T dR
+        V = torch.matmul(wb.t(), dR)                                         # Wb^T dR
+        af = a.reshape(B, 1, S)
+        dx = s.to(dt)[:, :, None] * U + af.to(dt) * V
+        if not ctx.pm:
+            dx = dx + k0.to(dt) * g
+        ds = (xf.float() * U.float()).sum(dim=2)                             # (B,C)
+        da = (xf.float() * V.float()).sum(dim=1).reshape(a.shape)
+        G = torch.bmm(dR, xf.transpose(1, 2)).float()                        # (B,C,C): dR X^T
+        dwa = (G * s.float()[:, None, :]).sum(dim=0)
+        dwb = torch.bmm(dR * af.to(dt), xf.transpose(1, 2)).float().sum(dim=0)
+        dw = torch.cat([dwa, dwb], dim=1).reshape(w.shape).to(w.dtype)
+        dbias = dR.float().sum(dim=(0, 2))
+        # d out / d alpha = R - [add] x,  R = (out - k0 x) / alpha
+        gf, of, xx = g.float(), out.reshape(B, Cc, S).float(), xf.float()
+        R = (of - k0 * xx) / alpha
+        dalpha = (gf * (R if ctx.pm else R - xx)).sum()
+        dbeta = (torch.sigmoid(beta.float()) * dalpha).reshape(beta.shape).to(beta.dtype)
+        return dx.reshape(x.shape), ds.to(s.dtype), da.to(a.dtype), dw, dbias.to(dw.dtype), dbeta, None
+
+
+def concat_fused(x, s, a, w, bias, beta, pyramid_multiply: bool):
+    """Fused `sam_cam_fusion=concat` forward (tcgen05) with a library-GEMM closed-form backward; see include/mga_cbam.h."""
+    return _ConcatFn.apply(x, s, a, w, bias, beta, bool(pyramid_multiply))

@@ -199,3 +199,50 @@ def test_collate_matches_reference_rule():
         per = [(rng.random((h, w)) > 0.5).astype(dt) if dt == np.uint8 else rng.random((h, w)).astype(dt) for h, w in ((10, 8), (7, 12), (10, 12), (1, 1))]
         got = MaskUtils.collate_masks([torch.from_numpy(a).to(DEV) for a in per])
         assert got.dtype == torch.float32 and np.array_equal(got.cpu().numpy(), no.collate_masks(per))
+
+
+# ---------------------------------------------------------------- sam_cam_fusion = concat: fused tcgen05 forward
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape,pyr", [((2, 128, 20, 20), "multiply"), ((2, 256, 16, 24), "add"), ((1, 128, 80, 80), "multiply"), ((3, 256, 40, 40), "add")])
+def test_concat_fused_forward_and_backward_match_the_library_composition(shape, pyr, dtype, monkeypatch):
+    """The fused forward (csrc/cbam_concat.cuh: TMA + tcgen05.mma + TMEM epilogue) and its closed-form backward against the same module
+    run as gates op + torch.cat + F.conv2d + autograd (MGA_CONCAT_LIBRARY=1) and against the in-repo fp64 oracle.
+    Both modes are build-side definitions: 'oracle: in-repo PyTorch composition; reference parity unpinned'."""
+    from mga_yolo_b200 import MaskGuidedCBAM
+    from oracle import cbam_oracle as co
+    from tests._golden import PARAM_KEYS
+
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(C + H)
+    x = (torch.randn(B, C, H, W, generator=gen) * 0.5).to(dtype)
+    mask = torch.randn(B, 1, H, W, generator=gen)
+    g = torch.randn(B, C, H, W, generator=gen).to(dtype)
+    torch.manual_seed(C)
+    mod = MaskGuidedCBAM(C, sam_cam_fusion="concat", mga_pyramid_fusion=pyr).to(DEV)
+    with torch.no_grad():
+        mod.beta.fill_(0.3)
+        mod.fuse_sam_cam.bias.uniform_(-0.2, 0.2)
+
+    def run(library):
+        if library:
+            monkeypatch.setenv("MGA_CONCAT_LIBRARY", "1")
+        else:
+            monkeypatch.delenv("MGA_CONCAT_LIBRARY", raising=False)
+        for p in mod.parameters():
+            p.grad = None
+        xi = x.to(DEV).clone().requires_grad_(True)
+        mi = mask.to(DEV).clone().requires_grad_(True)
+        out = mod([xi, mi])
+        out.backward(g.to(DEV))
+        return [out.detach().float().cpu(), xi.grad.float().cpu(), mi.grad.float().cpu()] + [p.grad.detach().float().cpu().clone() for p in mod.parameters()]
+
+    fused, lib = run(False), run(True)
+    names = ["out", "dx", "dmask"] + [n for n, _ in mod.named_parameters()]
+    # 16-bit operands: both sides round; the fused one keeps fp32 accumulators and rounds once
+    for n, a, b in zip(names, fused, lib):
+        assert a.shape == b.shape and rel_err(a, b) <= 3e-2, (n, rel_err(a, b))
+    # against the fp64 oracle on the rounded inputs
+    p = co.CbamParams(*(mod.state_dict()[k].detach().double().cpu() for k in PARAM_KEYS))
+    ref_out = co.cbam_forward_general(x.double(), mask.double(), p, sam_cam_fusion="concat", mga_pyramid_fusion=pyr,
+                                      fuse_sam_cam=(mod.fuse_sam_cam.weight.detach().double().cpu(), mod.fuse_sam_cam.bias.detach().double().cpu()))
+    assert rel_err(fused[0], ref_out) <= 1e-2
