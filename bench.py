@@ -619,8 +619,9 @@ def gpu_arm(args, rank, world, local_rank):
 def concat_workload(dev, peak, bf16_peak_tflops):
     """BASELINE configs[3]: YOLOv8m (reference-YAML widths 256/512/512), batch 128 bf16, sam_cam_fusion=concat + mga_pyramid_fusion=multiply,
     fwd+bwd through the public nn.Module.  These two modes have no reference source (parity unpinned, in-repo
-    oracle); the block's gates (s, a') come from the CUDA gates op, the 2C->C 1x1 convolution is a library GEMM (cuDNN / cuBLAS) and the
-    elementwise glue is eager torch -- NOT a fused kernel (DESIGN.md section 7 says what a tcgen05 version would take)."""
+    oracle).  Forward: CUDA gates op (s, a') + weight-folding pre-kernel + ONE tcgen05 kernel (virtual concat, both 1x1 convolutions,
+    spatial gate, bias, pyramid fusion: csrc/cbam_concat.cuh).  Backward: three library GEMMs + one elementwise / reduction kernel +
+    the gates backward.  `library_composition` times the same module as gates op + torch.cat + F.conv2d + autograd."""
     from mga_yolo_b200 import MaskGuidedCBAM
 
     levels, B, dtype = [(256, 80, 80), (512, 40, 40), (512, 20, 20)], 128, torch.bfloat16
@@ -644,17 +645,26 @@ def concat_workload(dev, peak, bf16_peak_tflops):
                 out.backward(g)
                 mod.zero_grad(set_to_none=True)
 
-        for i in range(3):
-            step(i)
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 6
-        e0.record()
-        for i in range(reps):
-            step(i)
-        e1.record()
-        torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1) / reps
+
+        def timed():
+            for i in range(3):
+                step(i)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(reps):
+                step(i)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / reps
+
+        ms = timed()
+        os.environ["MGA_CONCAT_LIBRARY"] = "1"
+        try:
+            ms_lib = timed()
+        finally:
+            os.environ.pop("MGA_CONCAT_LIBRARY", None)
     except Exception as e:  # pragma: no cover
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     finally:
@@ -667,7 +677,8 @@ def concat_workload(dev, peak, bf16_peak_tflops):
             "value": round(ab / (ms * 1e-3) / 1e9, 1), "unit": "GB/s", "step_frac": round(ab / (ms * 1e-3) / 1e9 / peak, 4),
             "images_per_sec": round(B / (ms * 1e-3), 1), "gemm_tflops": round(flops / (ms * 1e-3) / 1e12, 1),
             "gemm_frac_of_bf16_sustained": None if not bf16_peak_tflops else round(flops / (ms * 1e-3) / 1e12 / bf16_peak_tflops, 4),
-            "path": "CUDA gates op (s, a') + library 1x1 convolution (cuDNN / cuBLAS GEMM) + eager elementwise: not a fused kernel",
+            "path": "forward: gates op + fold + ONE tcgen05 kernel (TMA, TMEM accumulators, fused epilogue); backward: 3 library GEMMs + 1 elementwise/reduction kernel + gates backward",
+            "library_composition": {"ms_per_step": round(ms_lib, 4), "note": "same module as gates op + torch.cat + F.conv2d (cuDNN) + autograd (MGA_CONCAT_LIBRARY=1)"},
             "note": "oracle: in-repo PyTorch composition; reference parity unpinned"}
 
 

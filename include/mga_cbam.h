@@ -138,6 +138,14 @@ int mga_cbam_gates_backward(const mga_cbam_desc* d, const void* x, const void* m
 int mga_cbam_concat_forward(const mga_cbam_desc* d, const void* x, const float* s, const float* a, const float* w, const float* bias,
                             const float* beta, void* out, void* wscratch, void* stream);
 
+/* Elementwise / reduction part of the backward of mga_cbam_concat_forward.  The caller provides uv (B, 2C, H*W) = [Wa^T g ; Wb^T g]
+ * (one library GEMM on the raw upstream gradient g = grad_out).  Writes grad_x = alpha (s U + a V) + k0 g, ga = g * a (left operand of
+ * the dWb GEMM), grad_a (B, H*W) = alpha sum_c x V, and per-tile partial rows: ds_part / dbias_part (B, nTiles, C) (already scaled by
+ * alpha; nTiles = ceil(H*W / 256)) and dalpha_part (B, nTiles) (sum over everything = d out / d alpha contracted with g). */
+int mga_cbam_concat_backward_elem(const mga_cbam_desc* d, const void* x, const void* grad_out, const void* uv, const float* s, const float* a,
+                                  const float* bias, const float* beta, void* grad_x, void* ga, float* ds_part, float* dbias_part, float* grad_a,
+                                  float* dalpha_part, void* stream);
+
 /* read-back of small saved quantities for tests / logging: which = 0 s(B,C), 1 a(B,HW) */
 int mga_cbam_ctx_view(const mga_cbam_desc* d, const void* ctx, int which, const float** ptr, size_t* count);
 

@@ -23,7 +23,7 @@ EXPORTS = (
     "mga_abi_version", "mga_last_error", "mga_cbam_workspace", "mga_cbam_forward", "mga_cbam_backward",
     "mga_cbam_ctx_view", "mga_mask_downsample", "mga_masks_multi", "mga_masks_multi_ws", "mga_cbam_plan", "mga_cbam_gates_forward", "mga_cbam_gates_backward", "mga_launch_count", "mga_profile_enable", "mga_profile_count",
     "mga_profile_read", "mga_eca_workspace", "mga_eca_forward", "mga_eca_backward", "mga_head_tail_forward", "mga_head_tail_backward",
-    "mga_gate_sample_forward", "mga_gate_sample_backward", "mga_collate_masks", "mga_cbam_concat_forward",
+    "mga_gate_sample_forward", "mga_gate_sample_backward", "mga_collate_masks", "mga_cbam_concat_forward", "mga_cbam_concat_backward_elem",
 )
 
 
@@ -102,6 +102,8 @@ def load() -> C.CDLL:
     lib.mga_collate_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.mga_cbam_concat_forward.argtypes = [C.POINTER(Desc)] + [C.c_void_p] * 9
     lib.mga_cbam_concat_forward.restype = C.c_int
+    lib.mga_cbam_concat_backward_elem.argtypes = [C.POINTER(Desc)] + [C.c_void_p] * 14
+    lib.mga_cbam_concat_backward_elem.restype = C.c_int
     for fn in (lib.mga_eca_workspace, lib.mga_eca_forward, lib.mga_eca_backward, lib.mga_head_tail_forward, lib.mga_head_tail_backward,
                lib.mga_gate_sample_forward, lib.mga_gate_sample_backward, lib.mga_collate_masks):
         fn.restype = C.c_int

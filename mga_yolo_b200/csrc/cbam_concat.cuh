@@ -20,9 +20,10 @@
 namespace mga {
 
 constexpr int kCcBM = 128, kCcBN = 128, kCcBK = 64, kCcStages = 4;
-constexpr int kCcThreads = 192;
+constexpr int kCcEpiWarps = 8;                       // two per TMEM lane quadrant: each takes half of the tile's pixel columns
+constexpr int kCcThreads = 64 + 32 * kCcEpiWarps;
 constexpr int kCcStageBytes = (2 * kCcBM * kCcBK + kCcBK * kCcBN) * 2;  // two weight tiles + the feature tile, 16-bit elements
-constexpr int kCcSmemBytes = kCcStages * kCcStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int kCcSmemBytes = kCcStages * kCcStageBytes + 1024 /* alignment slack */ + 256 /* barriers */ + 2 * kCcBN * 4 /* spatial gate of the tile */;
 
 struct ConcatMaps { CUtensorMap wa, wb, x; };
 
@@ -78,6 +79,53 @@ __global__ void __launch_bounds__(kBlock) concat_fold_kernel(const float* __rest
     }
 }
 
+// epilogue of one 128 x 128 tile by the 8 epilogue warps (warp indices 2..9): warp w reads TMEM lanes 32 (w % 4) .. (row co = m0 + 32 (w % 4)
+// + lane) and the pixel columns [64 h, 64 h + 64) with h = (w - 2) / 4, in chunks of 16 columns of both accumulators (y1 at tacc, y2 at
+// tacc + 128): out = k0 x + k1 (y1 + a y2 + bias).  The spatial gate of the tile's 128 pixels sits in shared memory (a_sm).
+template <typename T>
+__device__ __forceinline__ void concat_epilogue_tile(uint32_t tacc, int warp, int lane, const T* __restrict__ x, const float* a_sm,
+                                                     const float* __restrict__ bias, T* __restrict__ out, int b, int m0, int p0, int C, int S,
+                                                     float k0, float k1) {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int co = m0 + q * 32 + lane;
+    const float bco = __ldg(bias + co);
+    const uint32_t trow = tacc + ((uint32_t)(q * 32) << 16);
+    const size_t rowoff = ((size_t)b * C + co) * S;
+#pragma unroll 1
+    for (int c16 = half * 4; c16 < half * 4 + 4; ++c16) {
+        const int p = p0 + c16 * 16;
+        uint32_t y1[16], y2[16];
+        tmem_ld16(trow + c16 * 16, y1);
+        tmem_ld16(trow + kCcBN + c16 * 16, y2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (p >= S) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ph8 = p + h * 8;
+            if (ph8 >= S) break;  // (S % 8 == 0: whole 16-byte pieces)
+            const float4 a0 = *reinterpret_cast<const float4*>(a_sm + c16 * 16 + h * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(a_sm + c16 * 16 + h * 8 + 4);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = k1 * (__uint_as_float(y1[h * 8 + i]) + fmaf(av[i], __uint_as_float(y2[h * 8 + i]), bco));
+            if (k0 != 0.0f) {
+                float xv[8];
+                ldv<T, 8, kLdStream>(x + rowoff + ph8, xv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = fmaf(k0, xv[i], r[i]);
+            }
+            stv<T, 8, true>(out + rowoff + ph8, r);
+        }
+    }
+}
+// the spatial gate of pixels [p0, p0 + 128) of sample b into shared memory (epilogue threads only), then a barrier among them
+__device__ __forceinline__ void concat_stage_gate(float* a_sm, const float* __restrict__ agate, int b, int p0, int S) {
+    const int i = (int)threadIdx.x - 64;
+    if (i < kCcBN) a_sm[i] = (p0 + i < S) ? __ldg(agate + (size_t)b * S + p0 + i) : 0.0f;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kCcEpiWarps) : "memory");
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kCcThreads, 1) concat_fwd_kernel(const __grid_constant__ ConcatMaps maps, const T* __restrict__ x,
                                                                    const float* __restrict__ agate, const float* __restrict__ bias,
@@ -88,6 +136,7 @@ __global__ void __launch_bounds__(kCcThreads, 1) concat_fwd_kernel(const __grid_
     uint64_t* empty = full + kCcStages;
     uint64_t* tmem_full = empty + kCcStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    float* a_sm = reinterpret_cast<float*>(smem + kCcStages * kCcStageBytes + 256);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p0 = blockIdx.x * kCcBN, m0 = blockIdx.y * kCcBM, b = blockIdx.z;
     const int nkb = C / kCcBK;
@@ -148,49 +197,229 @@ __global__ void __launch_bounds__(kCcThreads, 1) concat_fwd_kernel(const __grid_
             umma_commit(tmem_full);
         }
     } else {
-        // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) ..: row co = m0 + 32 (w % 4) + lane, 128 pixels in chunks of 16 columns
-        const int q = warp & 3;
-        const int co = m0 + q * 32 + lane;
-        const float bt = __ldg(beta);
-        const float alpha = softplusf_acc(bt);
-        const float k0 = pyramid_multiply ? 0.0f : 1.0f - alpha, k1 = alpha;
-        const float bco = __ldg(bias + co);
+        // ---- epilogue
+        const float alpha = softplusf_acc(__ldg(beta));
+        concat_stage_gate(a_sm, agate, b, p0, S);
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        const size_t rowoff = ((size_t)b * C + co) * S;
-        const float* ap = agate + (size_t)b * S;
-#pragma unroll 1
-        for (int c16 = 0; c16 < kCcBN / 16; ++c16) {
-            const int p = p0 + c16 * 16;
-            uint32_t y1[16], y2[16];
-            tmem_ld16(trow + c16 * 16, y1);
-            tmem_ld16(trow + kCcBN + c16 * 16, y2);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (p >= S) continue;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int ph8 = p + h * 8;
-                if (ph8 >= S) break;  // (S % 8 == 0: whole 16-byte pieces)
-                const float4 a0 = __ldg(reinterpret_cast<const float4*>(ap + ph8));
-                const float4 a1 = __ldg(reinterpret_cast<const float4*>(ap + ph8 + 4));
-                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                float r[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) r[i] = k1 * (__uint_as_float(y1[h * 8 + i]) + fmaf(av[i], __uint_as_float(y2[h * 8 + i]), bco));
-                if (k0 != 0.0f) {
-                    float xv[8];
-                    ldv<T, 8, kLdStream>(x + rowoff + ph8, xv);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) r[i] = fmaf(k0, xv[i], r[i]);
-                }
-                stv<T, 8, true>(out + rowoff + ph8, r);
-            }
-        }
+        concat_epilogue_tile<T>(tmem_base, warp, lane, x, a_sm, bias, out, b, m0, p0, C, S, pyramid_multiply ? 0.0f : 1.0f - alpha, alpha);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kCcBN) : "memory");
+}
+
+
+// ---------------------------------------------------------------- C <= 256: weights RESIDENT in shared memory, persistent CTAs
+// A work item = (sample b, 128 output channels, a run of pixel tiles).  The two weight tiles of the item (2 x 128 x C 16-bit = 128 KB at
+// C = 256) are loaded once and stay; only the feature tiles stream through the 4-stage ring (one 64-channel k-block per stage), and
+// the two accumulators are double-buffered in tensor memory (512 columns), so the epilogue of tile t overlaps the MMAs of tile t + 1.
+// Weight traffic per output element drops from 2 * 2C * e / 128 bytes (every tile reloads them) to ~0: HBM/L2 see x and out only.
+constexpr int kCcResStageBytes = kCcBK * kCcBN * 2;  // one feature k-block
+__host__ __device__ inline int concat_res_smem(int C) { return (C / kCcBK) * 2 * kCcBM * kCcBK * 2 + kCcStages * kCcResStageBytes + 1024 + 256 + 2 * kCcBN * 4; }
+
+template <typename T>
+__global__ void __launch_bounds__(kCcThreads, 1) concat_fwd_res_kernel(const __grid_constant__ ConcatMaps maps, const T* __restrict__ x,
+                                                                       const float* __restrict__ agate, const float* __restrict__ bias,
+                                                                       const float* __restrict__ beta, T* __restrict__ out, int B, int C, int S,
+                                                                       int tiles_per_item, int pyramid_multiply) {
+    extern __shared__ __align__(1024) unsigned char ccsm_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ccsm_raw) + 1023) & ~(uintptr_t)1023);
+    const int nkb = C / kCcBK;
+    unsigned char* wsm = smem;                                   // [nkb][Wa' tile 16 KB | Wb tile 16 KB]
+    unsigned char* ring = smem + nkb * 2 * kCcBM * kCcBK * 2;    // [kCcStages][feature k-block 16 KB]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + kCcStages * kCcResStageBytes);
+    uint64_t* empty = full + kCcStages;
+    uint64_t* tfull = empty + kCcStages;    // [2] accumulators of buffer i are complete
+    uint64_t* tempty = tfull + 2;           // [2] ... have been drained by the epilogue
+    uint64_t* wfull = tempty + 2;
+    uint64_t* wempty = wfull + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wempty + 1);
+    float* a_sm = reinterpret_cast<float*>(ring + kCcStages * kCcResStageBytes + 256);  // [2][128]: spatial gate of the current / next tile
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nTilesN = (S + kCcBN - 1) / kCcBN, nMt = C / kCcBM;
+    const int chunks = (nTilesN + tiles_per_item - 1) / tiles_per_item;
+    const int nItems = B * nMt * chunks;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kCcStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kCcEpiWarps); }
+        mbar_init(wfull, 1);
+        mbar_init(wempty, 1);
+        fence_mbar_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.wa) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.wb) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(4 * kCcBN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer
+            unsigned kit = 0, nit = 0;
+            for (int it = blockIdx.x; it < nItems; it += gridDim.x, ++nit) {
+                const int ch = it % chunks, mt = (it / chunks) % nMt, b = it / (chunks * nMt);
+                const int m0 = mt * kCcBM, t0 = ch * tiles_per_item, t1 = min(nTilesN, t0 + tiles_per_item);
+                mbar_wait(wempty, (nit & 1) ^ 1);  // the previous item's MMAs have finished reading the weights
+                mbar_expect_tx(wfull, (uint32_t)(nkb * 2 * kCcBM * kCcBK * 2));
+                for (int kb = 0; kb < nkb; ++kb) {
+                    tma_load_2d(wsm + kb * 2 * kCcBM * kCcBK * 2, &maps.wa, kb * kCcBK, b * C + m0, wfull);
+                    tma_load_2d(wsm + kb * 2 * kCcBM * kCcBK * 2 + kCcBM * kCcBK * 2, &maps.wb, kb * kCcBK, m0, wfull);
+                }
+                for (int t = t0; t < t1; ++t)
+                    for (int kb = 0; kb < nkb; ++kb, ++kit) {
+                        const int st = kit % kCcStages, ph = (kit / kCcStages) & 1;
+                        mbar_wait(&empty[st], ph ^ 1);
+                        unsigned char* sb = ring + st * kCcResStageBytes;
+                        mbar_expect_tx(&full[st], kCcResStageBytes);
+                        tma_load_2d(sb, &maps.x, t * kCcBN, b * C + kb * kCcBK, &full[st]);
+                        tma_load_2d(sb + kCcBK * 64 * 2, &maps.x, t * kCcBN + 64, b * C + kb * kCcBK, &full[st]);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- MMA issuer
+            const uint32_t idesc = umma_instr_desc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, kCcBM, kCcBN);
+            unsigned kit = 0, nit = 0, tt = 0;
+            for (int it = blockIdx.x; it < nItems; it += gridDim.x, ++nit) {
+                const int ch = it % chunks;
+                const int t0 = ch * tiles_per_item, t1 = min(nTilesN, t0 + tiles_per_item);
+                mbar_wait(wfull, nit & 1);
+                for (int t = t0; t < t1; ++t, ++tt) {
+                    const int buf = tt & 1;
+                    mbar_wait(&tempty[buf], ((tt >> 1) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t tacc = tmem_base + buf * 2 * kCcBN;
+                    for (int kb = 0; kb < nkb; ++kb, ++kit) {
+                        const int st = kit % kCcStages, ph = (kit / kCcStages) & 1;
+                        mbar_wait(&full[st], ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sa = smem_u32(wsm + kb * 2 * kCcBM * kCcBK * 2);
+                        const uint32_t sa2 = sa + kCcBM * kCcBK * 2, sb = smem_u32(ring + st * kCcResStageBytes);
+#pragma unroll
+                        for (int k = 0; k < kCcBK / 16; ++k) {
+                            const uint64_t a1 = umma_smem_desc(sa + k * 32, 16, 1024);
+                            const uint64_t a2 = umma_smem_desc(sa2 + k * 32, 16, 1024);
+                            const uint64_t bd = umma_smem_desc(sb + k * 2048, kCcBK * 64 * 2, 1024);
+                            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                            umma_f16(tacc, a1, bd, idesc, acc);
+                            umma_f16(tacc + kCcBN, a2, bd, idesc, acc);
+                        }
+                        umma_commit(&empty[st]);
+                    }
+                    umma_commit(&tfull[buf]);
+                }
+                umma_commit(wempty);
+            }
+        }
+    } else {
+        // ---- epilogue warps
+        const float alpha = softplusf_acc(__ldg(beta));
+        const float k0 = pyramid_multiply ? 0.0f : 1.0f - alpha;
+        unsigned tt = 0;
+        for (int it = blockIdx.x; it < nItems; it += gridDim.x) {
+            const int ch = it % chunks, mt = (it / chunks) % nMt, b = it / (chunks * nMt);
+            const int t0 = ch * tiles_per_item, t1 = min(nTilesN, t0 + tiles_per_item);
+            for (int t = t0; t < t1; ++t, ++tt) {
+                const int buf = tt & 1;
+                concat_stage_gate(a_sm + buf * kCcBN, agate, b, t * kCcBN, S);  // (its previous reader, tile tt - 2, is two barriers back)
+                mbar_wait(&tfull[buf], (tt >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                concat_epilogue_tile<T>(tmem_base + buf * 2 * kCcBN, warp, lane, x, a_sm + buf * kCcBN, bias, out, b, mt * kCcBM, t * kCcBN, C, S, k0, alpha);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[buf])) : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(4 * kCcBN) : "memory");
+}
+
+}  // namespace mga
+
+namespace mga {
+
+// ---------------------------------------------------------------- backward of the concat forward: the elementwise / reduction part.
+// With U = Wa^T g and V = Wb^T g (library GEMMs on the raw upstream gradient g, stacked as uv (B, 2C, S)):
+//   dx      = alpha (s_c U + a_p V) + k0 g                     ga = g * a_p   (left operand of the dWb GEMM)
+//   ds_c    = alpha sum_p x U          da_p = alpha sum_c x V   dbias_c = alpha sum_p g
+//   dalpha  = sum x (s U + a V) + sum_c bias_c sum_p g - [add] sum g x
+// grid (tiles of 32 units, B); warp w owns channels w, w+8, ...; a lane owns one 16-byte unit.  Per-tile partial sums go to scratch rows
+// (ds_part / dbias_part: (B, nTiles, C), dalpha_part: (B, nTiles)); da is complete per pixel (a CTA covers every channel of its pixels).
+template <typename T>
+__global__ void __launch_bounds__(kBlock) concat_bwd_elem_kernel(const T* __restrict__ x, const T* __restrict__ g, const T* __restrict__ uv,
+                                                                 const float* __restrict__ s, const float* __restrict__ agate,
+                                                                 const float* __restrict__ bias, const float* __restrict__ beta, T* __restrict__ dx,
+                                                                 T* __restrict__ ga, float* __restrict__ ds_part, float* __restrict__ dbias_part,
+                                                                 float* __restrict__ da, float* __restrict__ dalpha_part, int C, int S,
+                                                                 int pyramid_multiply) {
+    constexpr int VEC = 8;
+    __shared__ float part[kWarpsPerBlock][32 * VEC];
+    __shared__ float red[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.y, tile = blockIdx.x, nT = gridDim.x, U = S / VEC;
+    const int u = tile * 32 + lane;
+    const bool act = u < U;
+    const float alpha = softplusf_acc(__ldg(beta));
+    const float k0 = pyramid_multiply ? 0.0f : 1.0f - alpha;
+    float av[VEC], vacc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) { av[e] = 0.0f; vacc[e] = 0.0f; }
+    if (act) ldf<VEC>(agate + (size_t)b * S + (size_t)u * VEC, av);
+    float dal = 0.0f;
+    for (int c = w; c < C; c += kWarpsPerBlock) {
+        float su = 0.0f, sg = 0.0f;
+        if (act) {
+            const size_t o = ((size_t)b * C + c) * S + (size_t)u * VEC;
+            const size_t ou = ((size_t)b * 2 * C + c) * S + (size_t)u * VEC;
+            float xv[VEC], gv[VEC], uu[VEC], vv[VEC], ov[VEC], gav[VEC];
+            ldv<T, VEC, kLdStream>(x + o, xv);
+            ldv<T, VEC, kLdStream>(g + o, gv);
+            ldv<T, VEC, kLdStream>(uv + ou, uu);
+            ldv<T, VEC, kLdStream>(uv + ou + (size_t)C * S, vv);
+            const float sc = __ldg(s + b * C + c);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const float t = fmaf(sc, uu[e], av[e] * vv[e]);
+                ov[e] = fmaf(alpha, t, k0 * gv[e]);
+                gav[e] = gv[e] * av[e];
+                su = fmaf(xv[e], uu[e], su);
+                sg += gv[e];
+                vacc[e] = fmaf(xv[e], vv[e], vacc[e]);
+                dal = fmaf(xv[e], t, dal);
+                if (!pyramid_multiply) dal = fmaf(-gv[e], xv[e], dal);
+            }
+            stv<T, VEC, true>(dx + o, ov);
+            stv<T, VEC, true>(ga + o, gav);
+        }
+        su = warp_sum(su);
+        sg = warp_sum(sg);
+        if (lane == 0) {
+            const size_t pi = ((size_t)b * nT + tile) * C + c;
+            ds_part[pi] = alpha * su;
+            dbias_part[pi] = alpha * sg;
+            dal = fmaf(__ldg(bias + c), sg, dal);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) part[w][lane * VEC + e] = vacc[e];
+    const float dtot = block_sum(dal, red);  // (barriers inside: `part` is complete)
+    if (threadIdx.x == 0) dalpha_part[(size_t)b * nT + tile] = dtot;
+    for (int i = threadIdx.x; i < 32 * VEC; i += kBlock) {
+        const int p = tile * 32 * VEC + i;
+        if (p >= S) continue;
+        float r = 0.0f;
+#pragma unroll
+        for (int q = 0; q < kWarpsPerBlock; ++q) r += part[q][i];
+        da[(size_t)b * S + p] = alpha * r;
+    }
 }
 
 }  // namespace mga

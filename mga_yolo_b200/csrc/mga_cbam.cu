@@ -817,6 +817,27 @@ static int concat_forward_t(const mga_cbam_desc* d, const void* x, const float* 
         for (int& v : configured_dev)
             if (v < 0) { v = dev; break; }
     }
+    static const int use_res = env_int("MGA_CONCAT_RES", 1);
+    if (use_res && concat_res_smem(C) <= kSmemLimit) {  // C <= 256: resident weights, persistent CTAs, double-buffered accumulators
+        static thread_local int res_dev[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+        bool rdone = false;
+        for (int v : res_dev) rdone |= (v == dev);
+        if (!rdone) {
+            if (cudaFuncSetAttribute(concat_fwd_res_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess)
+                return fail(MGA_ERR_CUDA, "mga_cbam_concat_forward: cudaFuncSetAttribute");
+            for (int& v : res_dev)
+                if (v < 0) { v = dev; break; }
+        }
+        const int nTilesN = (S + kCcBN - 1) / kCcBN, nMt = C / kCcBM;
+        // pixel tiles per item: the fewest items that still give every SM >= ~4 of them (weights are reloaded per item)
+        int chunks = 1;
+        while (chunks < nTilesN && (long)B * nMt * chunks < 4L * kSMs) ++chunks;
+        const int tpi = (nTilesN + chunks - 1) / chunks;
+        const int items = B * nMt * ((nTilesN + tpi - 1) / tpi);
+        MGA_LAUNCH("concat_fwd", st, (concat_fwd_res_kernel<T><<<std::min(items, kSMs), kCcThreads, concat_res_smem(C), st>>>(
+            maps, static_cast<const T*>(x), a, bias, beta, static_cast<T*>(out), B, C, S, tpi, (d->flags & MGA_PYRAMID_MULTIPLY) ? 1 : 0)));
+        return check_launch("mga_cbam_concat_forward(resident)");
+    }
     const dim3 grid((S + kCcBN - 1) / kCcBN, C / kCcBM, B);
     MGA_LAUNCH("concat_fwd", st, (concat_fwd_kernel<T><<<grid, kCcThreads, kCcSmemBytes, st>>>(maps, static_cast<const T*>(x), a, bias, beta, static_cast<T*>(out), C, S,
                                                                                              (d->flags & MGA_PYRAMID_MULTIPLY) ? 1 : 0)));
@@ -990,6 +1011,32 @@ int mga_cbam_concat_forward(const mga_cbam_desc* d, const void* x, const float* 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (d->dtype == MGA_BF16) return concat_forward_t<__nv_bfloat16>(d, x, s, a, w, bias, beta, out, wscratch, st);
     return concat_forward_t<__half>(d, x, s, a, w, bias, beta, out, wscratch, st);
+}
+
+int mga_cbam_concat_backward_elem(const mga_cbam_desc* d, const void* x, const void* grad_out, const void* uv, const float* s, const float* a,
+                                  const float* bias, const float* beta, void* grad_x, void* ga, float* ds_part, float* dbias_part, float* grad_a,
+                                  float* dalpha_part, void* stream) {
+    if (!d || !x || !grad_out || !uv || !s || !a || !bias || !beta || !grad_x || !ga || !ds_part || !dbias_part || !grad_a || !dalpha_part)
+        return fail(MGA_ERR_ARG, "null pointer argument");
+    if (d->B <= 0 || d->C <= 0 || d->H <= 0 || d->W <= 0 || d->B > 65535) return fail(MGA_ERR_ARG, "bad shape");
+    if (d->dtype != MGA_BF16 && d->dtype != MGA_F16) return fail(MGA_ERR_UNSUPPORTED, "16-bit features only");
+    const int S = d->H * d->W;
+    if (S % 8) return fail(MGA_ERR_UNSUPPORTED, "needs H*W %% 8 == 0");
+    for (const void* p : {x, grad_out, uv, (const void*)grad_x, (const void*)ga, (const void*)a})
+        if (reinterpret_cast<uintptr_t>(p) & 15) return fail(MGA_ERR_UNSUPPORTED, "16-byte aligned tensors only");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dim3 grid((S / 8 + 31) / 32, d->B);
+    const int pm = (d->flags & MGA_PYRAMID_MULTIPLY) ? 1 : 0;
+    if (d->dtype == MGA_BF16) {
+        using T = __nv_bfloat16;
+        MGA_LAUNCH("concat_bwd_elem", st, (concat_bwd_elem_kernel<T><<<grid, kBlock, 0, st>>>(static_cast<const T*>(x), static_cast<const T*>(grad_out), static_cast<const T*>(uv), s, a, bias, beta,
+            static_cast<T*>(grad_x), static_cast<T*>(ga), ds_part, dbias_part, grad_a, dalpha_part, d->C, S, pm)));
+    } else {
+        using T = __half;
+        MGA_LAUNCH("concat_bwd_elem", st, (concat_bwd_elem_kernel<T><<<grid, kBlock, 0, st>>>(static_cast<const T*>(x), static_cast<const T*>(grad_out), static_cast<const T*>(uv), s, a, bias, beta,
+            static_cast<T*>(grad_x), static_cast<T*>(ga), ds_part, dbias_part, grad_a, dalpha_part, d->C, S, pm)));
+    }
+    return check_launch("mga_cbam_concat_backward_elem");
 }
 
 int mga_cbam_ctx_view(const mga_cbam_desc* d, const void* ctx_buf, int which, const float** ptr, size_t* count) {

@@ -325,47 +325,53 @@ _LIBIMPL.impl("cbam_concat_fwd", _concat_fwd_meta, "Meta")
 
 class _ConcatFn(torch.autograd.Function):
     """out = k0 x + k1 (Wa (x s) + Wb (x a) + bias).  Forward: ONE tcgen05 kernel (+ the weight-folding pre-kernel).  Backward: closed form
-    on library GEMMs (torch.matmul / bmm) -- the 2C-channel concat tensor is not formed in either direction."""
+    = three library GEMMs (U|V = [Wa^T ; Wb^T] g; g X^T; (g a) X^T) + ONE elementwise / reduction kernel (mga_cbam_concat_backward_elem);
+    the 2C-channel concat tensor is not formed in either direction."""
 
     @staticmethod
     def forward(ctx, x, s, a, w, bias, beta, pyramid_multiply):
         out = torch.ops.mga.cbam_concat_fwd(x, s, a, w, bias, beta, pyramid_multiply)
-        ctx.save_for_backward(x, s, a, w, beta, out)
+        ctx.save_for_backward(x, s, a, w, bias, beta)
         ctx.pm = pyramid_multiply
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        x, s, a, w, beta, out = ctx.saved_tensors
+        x, s, a, w, bias, beta = ctx.saved_tensors
+        lib = _lib.load()
         B, Cc, H, W = x.shape
         S = H * W
         dt = x.dtype
-        alpha = torch.nn.functional.softplus(beta.float())
-        k0 = torch.zeros_like(alpha) if ctx.pm else 1.0 - alpha
-        w2 = w.reshape(Cc, 2 * Cc).float()
-        wa, wb = w2[:, :Cc].to(dt), w2[:, Cc:].to(dt)
-        xf = x.reshape(B, Cc, S)
-        g = gout.reshape(B, Cc, S).to(dt)
-        dR = alpha.to(dt) * g                                                # (B,C,S)
-        U = torch.matmul(wa.t(), dR)                                         # Wa^T dR
-        V = torch.matmul(wb.t(), dR)                                         # Wb^T dR
-        af = a.reshape(B, 1, S)
-        dx = s.to(dt)[:, :, None] * U + af.to(dt) * V
-        if not ctx.pm:
-            dx = dx + k0.to(dt) * g
-        ds = (xf.float() * U.float()).sum(dim=2)                             # (B,C)
-        da = (xf.float() * V.float()).sum(dim=1).reshape(a.shape)
-        G = torch.bmm(dR, xf.transpose(1, 2)).float()                        # (B,C,C): dR X^T
-        dwa = (G * s.float()[:, None, :]).sum(dim=0)
-        dwb = torch.bmm(dR * af.to(dt), xf.transpose(1, 2)).float().sum(dim=0)
+        x = x.contiguous()
+        g = gout.contiguous().to(dt)
+        w2 = w.reshape(Cc, 2 * Cc)
+        wcat_t = torch.cat([w2[:, :Cc].t(), w2[:, Cc:].t()], dim=0).to(dt).contiguous()      # (2C, C): [Wa^T ; Wb^T]
+        uv = torch.matmul(wcat_t, g.reshape(B, Cc, S))                                         # (B, 2C, S), one library GEMM
+        sf, af, bf, btf = _f32c(s), _f32c(a), _f32c(bias), _f32c(beta)
+        nT = (S // 8 + 31) // 32
+        d = _lib.Desc(B, Cc, H, W, 1, 1, _DT[dt], _lib.F32, _lib.PYRAMID_MULTIPLY if ctx.pm else 0, 0.0, 0.0)
+        with torch.cuda.device(x.device):
+            dx = torch.empty_like(x)
+            ga = torch.empty_like(x)
+            ds_part = torch.empty((B, nT, Cc), dtype=torch.float32, device=x.device)
+            db_part = torch.empty((B, nT, Cc), dtype=torch.float32, device=x.device)
+            da = torch.empty((B, S), dtype=torch.float32, device=x.device)
+            dal_part = torch.empty((B, nT), dtype=torch.float32, device=x.device)
+            rc = lib.mga_cbam_concat_backward_elem(C.byref(d), x.data_ptr(), g.data_ptr(), uv.data_ptr(), sf.data_ptr(), af.data_ptr(), bf.data_ptr(),
+                                                   btf.data_ptr(), dx.data_ptr(), ga.data_ptr(), ds_part.data_ptr(), db_part.data_ptr(), da.data_ptr(),
+                                                   dal_part.data_ptr(), _stream(x))
+        _lib.check(rc, "mga_cbam_concat_backward_elem")
+        alpha = torch.nn.functional.softplus(btf)
+        xt = x.reshape(B, Cc, S).transpose(1, 2)
+        Ga = torch.bmm(g.reshape(B, Cc, S), xt)                                                # (B,C,C): g X^T
+        Gb = torch.bmm(ga.reshape(B, Cc, S), xt)                                               # (g * a) X^T
+        dwa = alpha * torch.einsum("boi,bi->oi", Ga.float(), sf.reshape(B, Cc))
+        dwb = alpha * Gb.float().sum(dim=0)
         dw = torch.cat([dwa, dwb], dim=1).reshape(w.shape).to(w.dtype)
-        dbias = dR.float().sum(dim=(0, 2))
-        # d out / d alpha = R - [add] x,  R = (out - k0 x) / alpha
-        gf, of, xx = g.float(), out.reshape(B, Cc, S).float(), xf.float()
-        R = (of - k0 * xx) / alpha
-        dalpha = (gf * (R if ctx.pm else R - xx)).sum()
-        dbeta = (torch.sigmoid(beta.float()) * dalpha).reshape(beta.shape).to(beta.dtype)
-        return dx.reshape(x.shape), ds.to(s.dtype), da.to(a.dtype), dw, dbias.to(dw.dtype), dbeta, None
+        ds = ds_part.sum(dim=1).reshape(s.shape).to(s.dtype)
+        dbias = db_part.sum(dim=(0, 1)).to(bias.dtype)
+        dbeta = (torch.sigmoid(btf) * dal_part.double().sum().float()).reshape(beta.shape).to(beta.dtype)
+        return dx, ds, da.reshape(a.shape).to(a.dtype), dw, dbias, dbeta, None
 
 
 def concat_fused(x, s, a, w, bias, beta, pyramid_multiply: bool):

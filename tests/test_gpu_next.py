@@ -238,11 +238,18 @@ def test_concat_fused_forward_and_backward_match_the_library_composition(shape, 
 
     fused, lib = run(False), run(True)
     names = ["out", "dx", "dmask"] + [n for n, _ in mod.named_parameters()]
-    # 16-bit operands: both sides round; the fused one keeps fp32 accumulators and rounds once
-    for n, a, b in zip(names, fused, lib):
+    # the library composition rounds every intermediate to 16 bits (its parameter gradients are 16-bit reductions): compare the
+    # activations / activation gradients with it, and everything with the fp64 oracle differentiated by autograd on the rounded inputs
+    for n, a, b in list(zip(names, fused, lib))[:3]:
         assert a.shape == b.shape and rel_err(a, b) <= 3e-2, (n, rel_err(a, b))
-    # against the fp64 oracle on the rounded inputs
-    p = co.CbamParams(*(mod.state_dict()[k].detach().double().cpu() for k in PARAM_KEYS))
-    ref_out = co.cbam_forward_general(x.double(), mask.double(), p, sam_cam_fusion="concat", mga_pyramid_fusion=pyr,
-                                      fuse_sam_cam=(mod.fuse_sam_cam.weight.detach().double().cpu(), mod.fuse_sam_cam.bias.detach().double().cpu()))
-    assert rel_err(fused[0], ref_out) <= 1e-2
+    sd = {k: v.detach().double().cpu().requires_grad_(True) for k, v in mod.state_dict().items()}
+    p = co.CbamParams(*(sd[k] for k in PARAM_KEYS))
+    x64 = x.double().requires_grad_(True)
+    m64 = mask.double().requires_grad_(True)
+    ref_out = co.cbam_forward_general(x64, m64, p, sam_cam_fusion="concat", mga_pyramid_fusion=pyr,
+                                      fuse_sam_cam=(sd["fuse_sam_cam.weight"], sd["fuse_sam_cam.bias"]))
+    ref_out.backward(g.double())
+    assert rel_err(fused[0], ref_out.detach()) <= 1e-2
+    assert rel_err(fused[1], x64.grad) <= 2e-2 and rel_err(fused[2], m64.grad) <= 2e-2
+    for n, a in zip(names[3:], fused[3:]):
+        assert rel_err(a, sd[n].grad) <= 2e-2, (n, rel_err(a, sd[n].grad))
