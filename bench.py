@@ -894,8 +894,37 @@ def mask_pipeline(dev, B, imgsz, peak):
         torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1) / reps
 
-    ms_one = timed(lambda m: MaskUtils.masks_multi(m))
+    def timed_graph(fn, reps=30):
+        """The same call captured in one CUDA graph per input buffer and replayed round robin: the kernels' time without the ~35 us of
+        Python / dispatcher / allocator work per op call that bounds the eager loop at this size."""
+        graphs = []
+        for m in bufs:
+            fn(m)
+        torch.cuda.synchronize(dev)
+        keep = []
+        for m in bufs:
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                keep.append(fn(m))
+            graphs.append(gph)
+        for gph in graphs[:3]:
+            gph.replay()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            graphs[i % nbuf].replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    ms_one_eager = timed(lambda m: MaskUtils.masks_multi(m))
     ms_per = timed(lambda m: [MaskUtils.downsample_mask(m, s) for s in (8, 16, 32)])
+    try:
+        ms_one = timed_graph(lambda m: MaskUtils.masks_multi(m))
+    except Exception as e:  # pragma: no cover
+        print(f"[bench] mask pipeline graph capture failed ({e}); reporting the eager loop", file=sys.stderr)
+        ms_one = ms_one_eager
     host = bufs[0][:8].cpu().numpy()
     kind, fn = "port", mo.downsample_mask
     if reference_available():
@@ -912,10 +941,12 @@ def mask_pipeline(dev, B, imgsz, peak):
             fn(host[b], s)
     cpu_s = (time.perf_counter() - t0) / host.shape[0]
     return {"workload": f"{B} binary masks {imgsz}x{imgsz} uint8 -> strides 8/16/32, default method (block max + 3x3 close)",
-            "one_pass_ms": round(ms_one, 5), "per_stride_ms": round(ms_per, 5), "masks_per_sec": round(B / (ms_one * 1e-3), 1),
+            "one_pass_ms": round(ms_one, 5), "one_pass_eager_call_ms": round(ms_one_eager, 5), "per_stride_ms": round(ms_per, 5),
+            "masks_per_sec": round(B / (ms_one * 1e-3), 1),
             "roofline": {"bound": "hbm", "achieved": round(alg / (ms_one * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(alg / (ms_one * 1e-3) / 1e9 / peak, 4), "alg_bytes_per_launch": alg,
-                         "note": "one CTA per image: 64 CTAs on 148 SMs, launch-latency bound at this batch"},
+                         "note": "two stages (mga_masks_multi_ws): one thread per 8x8 block over the whole batch reads the masks, then one CTA per (image, stride); "
+                                 "CUDA-graph replay over 6 rotating batches (the eager op call is bounded by ~35 us of host work)"},
             "cpu_baseline": {"masks_per_sec": round(1.0 / cpu_s, 1), "cores": 1, "kind": kind,
                              "sample": "8 masks x 3 strides, " + ("the reference's MaskUtils.downsample_mask (cv2) from oracle/_ref" if kind == "reference"
                                                                   else "oracle/mask_oracle.py (numpy restatement of cv2.resize / morphologyEx)")}}
