@@ -203,7 +203,8 @@ def test_collate_matches_reference_rule():
 
 # ---------------------------------------------------------------- sam_cam_fusion = concat: fused tcgen05 forward
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("shape,pyr", [((2, 128, 20, 20), "multiply"), ((2, 256, 16, 24), "add"), ((1, 128, 80, 80), "multiply"), ((3, 256, 40, 40), "add")])
+@pytest.mark.parametrize("shape,pyr", [((2, 128, 20, 20), "multiply"), ((2, 256, 16, 24), "add"), ((1, 128, 80, 80), "multiply"), ((3, 256, 40, 40), "add"),
+                                       ((2, 256, 80, 80), "multiply"), ((2, 512, 40, 40), "multiply"), ((2, 512, 20, 20), "multiply")])  # BASELINE configs[3] levels
 def test_concat_fused_forward_and_backward_match_the_library_composition(shape, pyr, dtype, monkeypatch):
     """The fused forward (csrc/cbam_concat.cuh: TMA + tcgen05.mma + TMEM epilogue) and its closed-form backward against the same module
     run as gates op + torch.cat + F.conv2d + autograd (MGA_CONCAT_LIBRARY=1) and against the in-repo fp64 oracle.
