@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
 
     // ---- phase 5 (T2): out = x * (A*a + B)
     stamp(7);
-    if (act2) {
+    if (act2 && !sh.gates_only()) {  // (gates-only calls stop here: s and a are in the context)
         float av[VEC];
         lds_f<VEC>(aloc + ul2 * VEC, av);
         const char* p = xbytes + (size_t)g2 * rowB + (size_t)ul2 * 16;

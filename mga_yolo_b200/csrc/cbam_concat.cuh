@@ -66,16 +66,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 
 // per-sample weights with the channel gate folded in: wa[b][co][ci] = W[co][ci] * s[b][ci], wb[co][ci] = W[co][C + ci]
+// grid (C / 8 rows-of-8, B + 1): a warp owns one weight row, lanes walk its input channels (coalesced, no divisions)
 template <typename T>
 __global__ void __launch_bounds__(kBlock) concat_fold_kernel(const float* __restrict__ w, const float* __restrict__ s, T* __restrict__ wa, T* __restrict__ wb,
                                                              int B, int C) {
-    const size_t n = (size_t)(B + 1) * C * C;
-    for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (size_t)gridDim.x * kBlock) {
-        const int b = (int)(i / ((size_t)C * C));
-        const int r = (int)(i - (size_t)b * C * C);
-        const int co = r / C, ci = r - co * C;
-        if (b < B) wa[i] = from_f<T>(__ldg(w + (size_t)co * 2 * C + ci) * __ldg(s + b * C + ci));
-        else wb[r] = from_f<T>(__ldg(w + (size_t)co * 2 * C + C + ci));
+    const int lane = threadIdx.x & 31, co = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5), b = blockIdx.y;
+    if (co >= C) return;
+    const float* wr = w + (size_t)co * 2 * C;
+    if (b < B) {
+        T* dst = wa + ((size_t)b * C + co) * C;
+        const float* sb = s + (size_t)b * C;
+        for (int ci = lane; ci < C; ci += 32) dst[ci] = from_f<T>(__ldg(wr + ci) * __ldg(sb + ci));
+    } else {
+        T* dst = wb + (size_t)co * C;
+        for (int ci = lane; ci < C; ci += 32) dst[ci] = from_f<T>(__ldg(wr + C + ci));
     }
 }
 

@@ -274,7 +274,7 @@ static bool cl_geometry(const Shape& sh, int esize, bool bwd, ClGeom* out) {
     static const int kb_f = env_int("MGA_CL_KB_F", 224), kb_b = env_int("MGA_CL_KB_B", 448);
     static const int cs_f = env_int("MGA_CL_CS_F", 0), cs_b = env_int("MGA_CL_CS_B", 0);  // tuning overrides
     static const int pf_f = env_int("MGA_CL_PREFETCH_F", 0), pf_b = env_int("MGA_CL_PREFETCH_B", 0);
-    if (!enabled || sh.gates_only()) return false;
+    if (!enabled || (sh.gates_only() && bwd)) return false;  // gates-only forward = cl_fwd without its last phase; the gates backward stays per phase
     static const int max_kb_f = env_int("MGA_CL_MAXKB_F", 1 << 30), max_kb_b = env_int("MGA_CL_MAXKB_B", 1 << 30);  // tuning: larger samples -> split path
     if ((double)sh.C * sh.S * esize > 1024.0 * (bwd ? max_kb_b : max_kb_f)) return false;
     static const int min_kb_f = env_int("MGA_CL_MINKB_F", 0), min_kb_b = env_int("MGA_CL_MINKB_B", 0);              // tuning: smaller samples -> split path
@@ -327,6 +327,9 @@ static bool cl_geometry(const Shape& sh, int esize, bool bwd, ClGeom* out) {
     }
     if (!have) return false;
     if (!forced && bytes / best.CS > 2.0 * target) return false;  // sample too large to stay L2-resident: split path
+    // gates-only forward (concat modes): measured on B200 at cfg4 (bf16, B = 128) the cluster kernel wins only for small samples
+    // (512x20x20: 67 us vs 161 us per phase); with clusters of 8 / 16 the four per-phase kernels are faster (296 vs 368 us, 470 vs 594 us)
+    if (sh.gates_only() && best.CS > 4) return false;
     static const int debug = env_int("MGA_CL_DEBUG", 0);
     if (debug)
         fprintf(stderr, "[mga] cluster %s C=%d %dx%d e=%d: CS=%d rows=%d nU=%d G=%d CG=%d LPT=%d slots=%d smem=%d B\n", bwd ? "bwd" : "fwd", sh.C, sh.H,
@@ -804,8 +807,7 @@ static int concat_forward_t(const mga_cbam_desc* d, const void* x, const float* 
     if (!concat_map(&maps.wa, wa, dt, C, (uint64_t)B * C, kCcBK, kCcBM) || !concat_map(&maps.wb, wb, dt, C, C, kCcBK, kCcBM) ||
         !concat_map(&maps.x, x, dt, S, (uint64_t)B * C, 64, kCcBK))
         return fail(MGA_ERR_UNSUPPORTED, "mga_cbam_concat_forward: tensor maps (16-byte aligned pointers, H*W %% 8 == 0)");
-    const size_t n = (size_t)(B + 1) * C * C;
-    MGA_LAUNCH("concat_fold", st, (concat_fold_kernel<T><<<(unsigned)std::min<size_t>((n + kBlock - 1) / kBlock, (size_t)kSMs * 16), kBlock, 0, st>>>(w, s, wa, wb, B, C)));
+    MGA_LAUNCH("concat_fold", st, (concat_fold_kernel<T><<<dim3((C + kWarpsPerBlock - 1) / kWarpsPerBlock, B + 1), kBlock, 0, st>>>(w, s, wa, wb, B, C)));
     static thread_local int configured_dev[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -970,7 +972,7 @@ int mga_cbam_gates_forward(const mga_cbam_desc* d, const void* x, const void* ma
                            void* stream) {
     if (!d) return fail(MGA_ERR_ARG, "null descriptor");
     mga_cbam_desc g = *d;
-    g.flags |= MGA_GATES_ONLY | MGA_SAMCAM_ADD | MGA_FORCE_SPLIT;  // the spatial gate is computed from x itself (a')
+    g.flags |= MGA_GATES_ONLY | MGA_SAMCAM_ADD;  // the spatial gate is computed from x itself (a'); cluster kernel when the shape allows
     return mga_cbam_forward(&g, x, mask, p, ctx_buf /* `out` is never written in gates mode */, ctx_buf, scratch, stream);
 }
 
