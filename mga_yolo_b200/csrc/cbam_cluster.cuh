@@ -347,7 +347,8 @@ __device__ __forceinline__ void cl_fetch_halo(cgx::cluster_group& cluster, float
 // ================================================================== forward
 template <typename T>
 __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* __restrict__ x, const void* __restrict__ mask, int mdt,
-                                                                  T* __restrict__ out, Shape sh, mga_cbam_params prm, Ctx ctx, ClGeom gm) {
+                                                                  T* __restrict__ out, Shape sh, mga_cbam_params prm, Ctx ctx, const ClFwdOff o,
+                                                                  ClGeom gm) {
     constexpr int VEC = 16 / sizeof(T);
     constexpr int K = kClKF;
     constexpr int NT = kClNTF, NW = NT / 32;
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
     const int G = gm.G, CG = gm.CG;
     const bool has_mask = sh.has_mask();
     const bool save = !sh.no_save();  // inference: the planes only the backward reads are not written
-    const ClFwdOff o = cl_fwd_off(C, Hd, gm);
+    // (the shared-memory layout `o` is computed on the host: per thread it cost ~1000 instructions per warp at kernel start)
     float* wk = csm + o.wk;
     float* red = csm + o.red;
     float* s_avg = csm + o.avg;
@@ -769,7 +770,7 @@ template <typename T>
 __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* __restrict__ x, const T* __restrict__ g, const void* __restrict__ mask,
                                                                   int mdt, T* __restrict__ dx, void* __restrict__ dmask, Shape sh,
                                                                   mga_cbam_params prm, Ctx ctx, BwdScratch bs, const __grid_constant__ PlaneMaps maps,
-                                                                  ClGeom gm) {
+                                                                  const ClBwdOff o, ClGeom gm) {
     constexpr int VEC = 16 / sizeof(T);
     constexpr int K = (VEC == 4) ? kClKB : kClKB16;
     constexpr int NT = kClNTB, NW = NT / 32;
@@ -790,7 +791,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
     const int G = gm.G, CG = gm.CG;
     const bool has_mask = sh.has_mask();
     const bool multiply = !sh.samcam_add();
-    const ClBwdOff o = cl_bwd_off(C, Hd, gm);
+    // (shared-memory layout `o`: computed on the host)
     float* wsm = csm + o.wsm;
     double* redd = reinterpret_cast<double*>(csm + o.red);
     float* s_s = csm + o.s;

@@ -689,7 +689,8 @@ static int forward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, con
 #endif
     ClGeom cgm;
     if (vec > 1 && !(d->flags & MGA_FORCE_SPLIT) && cl_geometry(sh, (int)sizeof(T), false, &cgm)) {
-        const int rc = launch_cl("cl_fwd", cl_fwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), mask, d->mask_dtype, static_cast<T*>(out), sh, p, ctx);
+        const int rc = launch_cl("cl_fwd", cl_fwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), mask, d->mask_dtype, static_cast<T*>(out), sh, p, ctx,
+                                 cl_fwd_off(sh.C, sh.hidden, cgm));
         if (rc != MGA_ERR_UNSUPPORTED) return rc;  // no cluster of that shape fits this device: one kernel per phase
     }
     if (vec == 1) return forward_split<T, 1>(sh, static_cast<const T*>(x), mask, d->mask_dtype, p, static_cast<T*>(out), ctx, fs, st);
@@ -767,7 +768,7 @@ static int backward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, co
         cgm.use_tma = make_plane_maps_box(&maps, planes, sh, cgm.TWp, cgm.tileRows) ? 1 : 0;
         if (!cgm.use_tma) std::memset(&maps, 0, sizeof(maps));
         const int rc = launch_cl("cl_bwd", cl_bwd_kernel<T>, cgm, sh.B, st, static_cast<const T*>(x), static_cast<const T*>(g), mask, d->mask_dtype,
-                                 static_cast<T*>(dx), dmask, sh, p, ctx, bs, maps);
+                                 static_cast<T*>(dx), dmask, sh, p, ctx, bs, maps, cl_bwd_off(sh.C, sh.hidden, cgm));
         if (rc != MGA_OK && rc != MGA_ERR_UNSUPPORTED) return rc;
         if (rc == MGA_OK) {
         const int nw = 2 * sh.C * sh.hidden + sh.C + sh.hidden;
