@@ -277,6 +277,10 @@ __device__ __forceinline__ void cl_prefetch_share(const void* sample, size_t sam
     }
 }
 
+// n / d for small non-negative n (< 2^21) with inv = 1.0f / d precomputed: three instructions instead of ~20 for an integer division
+// by a run-time value (the strip / pixel -> (row, column) maps below sit in loops every thread runs for every item)
+__device__ __forceinline__ int fdiv_small(int n, float inv) { return __float2int_rz(((float)n + 0.5f) * inv); }
+
 template <int NT>
 __device__ __forceinline__ void cl_load_weights7(const float* __restrict__ wsam, int k, bool flip, float* w /* [3][49] */) {
     const int off = (kMaxK - k) / 2;
@@ -292,8 +296,9 @@ __device__ __forceinline__ void cl_load_weights7(const float* __restrict__ wsam,
 template <int NT>
 __device__ __forceinline__ void cl_stage_three(float* tile, int planeT, const float* const (&planes)[3], int y_lo, int rows, int H, int W, int TWp) {
     const int cpr = TWp / 4, total = rows * cpr;
+    const float icpr = 1.0f / (float)cpr;
     for (int i = threadIdx.x; i < total; i += NT) {
-        const int r = i / cpr, c = i - r * cpr, yy = y_lo + r;
+        const int r = fdiv_small(i, icpr), c = i - r * cpr, yy = y_lo + r;
         const bool in = yy >= 0 && yy < H && c >= 1 && c < cpr - 1;
         const int o = yy * W + (c - 1) * 4;
 #pragma unroll
@@ -330,9 +335,10 @@ __device__ __forceinline__ void cl_fetch_halo(cgx::cluster_group& cluster, float
                                               int W) {
     const int cpr = W / 4;  // float4 chunks per image row
     const int per = 6 * cpr;
+    const float iper = 1.0f / (float)per, icpr = 1.0f / (float)cpr;
     for (int i = threadIdx.x; i < nplanes * per; i += NT) {
-        const int pl = i / per, rem = i - pl * per;
-        const int hr = rem / cpr, ch = rem - hr * cpr;       // halo row 0..5: 3 above, 3 below
+        const int pl = fdiv_small(i, iper), rem = i - pl * per;
+        const int hr = fdiv_small(rem, icpr), ch = rem - hr * cpr;       // halo row 0..5: 3 above, 3 below
         const int tr = hr < 3 ? hr : rows + hr;              // tile row (own rows are 3 .. 3+rows-1)
         const int yy = y0 - 3 + tr;
         if (yy < 0 || yy >= H) continue;
@@ -361,6 +367,7 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
     const int b = blockIdx.x / CS;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int C = sh.C, S = sh.S, Hd = sh.hidden, W = sh.W, H = sh.H;
+    const float invW = 1.0f / (float)W;
     const int y0 = r * gm.rowsPer;
     const int rows = max(0, min(gm.rowsPer, H - y0));
     const int nP = rows * W, nU = nP / VEC, p0 = y0 * W;
@@ -528,7 +535,7 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
     __syncthreads();
     if (has_mask)
         for (int i = tid; i < nP; i += NT) {
-            const int ry = i / W, cx = i - ry * W;
+            const int ry = fdiv_small(i, invW), cx = i - ry * W;
             tile[2 * planeT + (3 + ry) * TWp + 4 + cx] = mloc[i];
         }
     {
@@ -683,7 +690,7 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
                 if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }  // torch.max: first maximal channel
             }
             const float pavg = bsum * invC;
-            const int ry = p / W, cx = p - ry * W;
+            const int ry = fdiv_small(p, invW), cx = p - ry * W;
             tile[(3 + ry) * TWp + 4 + cx] = bm;
             tile[planeT + (3 + ry) * TWp + 4 + cx] = pavg;
             if (save) {
@@ -705,10 +712,11 @@ __global__ void __launch_bounds__(kClNTF, MGA_CL_MINB_F) cl_fwd_kernel(const T* 
         float* cpart = mg;  // [3][nPmax]
         const int grp = tid / kGrp, gl = tid - grp * kGrp;
         const int spr = W / 4, nStrips = rows * spr;
+        const float ispr = 1.0f / (float)spr;
         if (grp < 3) {
             const float* wv = wk + grp * kMaxK * kMaxK;
             for (int s = gl; s < nStrips; s += kGrp) {
-                const int ry = s / spr, x0 = (s - ry * spr) * 4;
+                const int ry = fdiv_small(s, ispr), x0 = (s - ry * spr) * 4;
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 strip_conv7(tile + grp * planeT + ry * TWp + x0, TWp, wv, acc);
                 *reinterpret_cast<float4*>(cpart + (size_t)grp * nPmax + s * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -784,6 +792,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
     const int b = blockIdx.x / CS;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int C = sh.C, S = sh.S, Hd = sh.hidden, W = sh.W, H = sh.H;
+    const float invW = 1.0f / (float)W;
     const int y0 = r * gm.rowsPer;
     const int rows = max(0, min(gm.rowsPer, H - y0));
     const int nP = rows * W, nU = nP / VEC, p0 = y0 * W;
@@ -971,7 +980,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
         float t = 0.0f;
         for (int j = 0; j < slots; ++j) t += tp[(size_t)j * nPmax + p];
         const float a = aloc[p];
-        const int ry = p / W, cx = p - ry * W;
+        const int ry = fdiv_small(p, invW), cx = p - ry * W;
         dpre[(3 + ry) * TWp + 4 + cx] = k1 * t * a * (1.0f - a);
         at_acc += (double)a * (double)t;
     }
@@ -1002,13 +1011,14 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
     {
         const int grp = tid / kGrp, gl = tid - grp * kGrp;
         const int spr = W / 4, nStrips = rows * spr;
+        const float ispr = 1.0f / (float)spr;
         const float invC = 1.0f / (float)C;
         if (grp < 3) {
             const float* wv = wsm + grp * kMaxK * kMaxK;
             float* dst = grp == 0 ? d0 : (grp == 1 ? d1s : d2);
             const float sc = grp == 1 ? invC : 1.0f;
             for (int s = gl; s < nStrips; s += kGrp) {
-                const int ry = s / spr, x0 = (s - ry * spr) * 4;
+                const int ry = fdiv_small(s, ispr), x0 = (s - ry * spr) * 4;
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 strip_conv7(dpre + ry * TWp + x0, TWp, wv, acc);
                 *reinterpret_cast<float4*>(dst + s * 4) = make_float4(acc[0] * sc, acc[1] * sc, acc[2] * sc, acc[3] * sc);
@@ -1022,7 +1032,7 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
             const int pl = team / kMaxK, i7 = team - pl * kMaxK;
             float acc[kMaxK] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int s = tl; s < nStrips; s += kTeam) {
-                const int ry = s / spr, x0 = (s - ry * spr) * 4;
+                const int ry = fdiv_small(s, ispr), x0 = (s - ry * spr) * 4;
                 const float4 d = *reinterpret_cast<const float4*>(dpre + (ry + kMaxK / 2) * TWp + x0 + 4);
                 const float* cr = cat + pl * planeT + (ry + i7) * TWp + x0;
                 const float4 a4 = *reinterpret_cast<const float4*>(cr);
@@ -1111,8 +1121,9 @@ __global__ void __launch_bounds__(kClNTB, MGA_CL_MINB_B) cl_bwd_kernel(const T* 
         bin_loc[c] = t;
     }
     const double gx_cta = block_sum_d(gxs, redd);  // (barriers inside)
+    const float invC_f = 1.0f / (float)C;
     for (int i = tid; i < C * CS; i += NT) {
-        const int rr = i / C, c = i - rr * C;
+        const int rr = fdiv_small(i, invC_f), c = i - rr * C;
         cluster.map_shared_rank(epart, rr)[r * C + c] = e_loc[c];
         cluster.map_shared_rank(qpart, rr)[r * C + c] = q_loc[c];
         cluster.map_shared_rank(binpart, rr)[r * C + c] = bin_loc[c];
