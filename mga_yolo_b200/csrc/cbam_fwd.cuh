@@ -124,6 +124,72 @@ __global__ void __launch_bounds__(kBlock) cam_pool_kernel(const T* __restrict__ 
     cam_pool_body<T, VEC, TPP>(x, sh, ctx, fs, this_block());
 }
 
+
+// F1, four channels per CTA: the (B,S) mask plane m is fp32 (twice the bytes of a 16-bit feature plane) and cam_pool re-reads it for
+// every channel -- here one CTA owns channels c0..c0+3 of a sample and every unit of m is loaded once for the four of them
+// (measured at 256x80x80 bf16, batch 128: 279 us -> see profiles/r2_concat_kernel.md).  Needs C % 4 == 0; same results / tie rules.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBlock) cam_pool4_kernel(const T* __restrict__ x, Shape sh, Ctx ctx, FwdScratch fs) {
+    __shared__ float red[4][4][kWarpsPerBlock];
+    const int b = blockIdx.y, c0 = blockIdx.x * 4;
+    const int U = sh.S / VEC;
+    const T* xp = x + ((size_t)b * sh.C + c0) * sh.S;
+    const float* mp = ctx.m + (size_t)b * sh.S;
+    const bool has_mask = sh.has_mask();
+    float sxm[4], sx[4], best[4];
+    int bidx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sxm[j] = 0.0f; sx[j] = 0.0f; best[j] = -INFINITY; bidx[j] = -1; }
+#pragma unroll 2
+    for (int u = threadIdx.x; u < U; u += kBlock) {
+        float mv[VEC], v[4][VEC];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ldv<T, VEC, kLdStream>(xp + (size_t)j * sh.S + (size_t)u * VEC, v[j]);
+        if (has_mask) ldf<VEC>(mp + (size_t)u * VEC, mv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float m = has_mask ? mv[i] : 1.0f;
+                sx[j] += v[j][i];
+                sxm[j] = fmaf(v[j][i], m, sxm[j]);
+                if ((!has_mask || m > 0.5f) && v[j][i] > best[j]) { best[j] = v[j][i]; bidx[j] = u * VEC + i; }  // ascending pixels per thread
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sx[j] += __shfl_xor_sync(0xffffffffu, sx[j], o);
+            sxm[j] += __shfl_xor_sync(0xffffffffu, sxm[j], o);
+            const float ob = __shfl_xor_sync(0xffffffffu, best[j], o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx[j], o);
+            if ((oi >= 0) && (bidx[j] < 0 || ob > best[j] || (ob == best[j] && oi < bidx[j]))) { best[j] = ob; bidx[j] = oi; }
+        }
+        if (lane == 0) { red[j][0][w] = sx[j]; red[j][1][w] = sxm[j]; red[j][2][w] = best[j]; red[j][3][w] = __int_as_float(bidx[j]); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const int j = threadIdx.x;
+        float tsx = 0.0f, tsxm = 0.0f, tb = -INFINITY;
+        int ti = -1;
+        for (int q = 0; q < kWarpsPerBlock; ++q) {
+            tsx += red[j][0][q];
+            tsxm += red[j][1][q];
+            const float ob = red[j][2][q];
+            const int oi = __float_as_int(red[j][3][q]);
+            if ((oi >= 0) && (ti < 0 || ob > tb || (ob == tb && oi < ti))) { tb = ob; ti = oi; }
+        }
+        const int pl = b * sh.C + c0 + j;
+        fs.sxm[pl] = tsxm;
+        fs.sx[pl] = tsx;
+        fs.best[pl] = tb;
+        fs.bidx[pl] = ti;
+    }
+}
+
 // ------------------------------------------------------------------ F2 (one CTA per sample)
 __device__ __forceinline__ void cam_mlp_body(const Shape& sh, const mga_cbam_params& prm, const Ctx& ctx, const FwdScratch& fs, int nMaskTiles,
                                              const Blk blk, float* smem /* 2C + 2h floats */) {

@@ -639,7 +639,8 @@ static int forward_split(const Shape& sh, const T* x, const void* mask, int mask
     const int planes = sh.B * sh.C;
     MGA_LAUNCH("cam_pool", st,
         const int tpp = pool_tpp(U, VEC);
-        if (tpp == 256) cam_pool_kernel<T, VEC, 256><<<planes, kBlock, 0, st>>>(x, sh, ctx, fs);
+        if (VEC > 1 && sh.C % 4 == 0 && U >= kBlock && sh.B <= 65535) cam_pool4_kernel<T, VEC><<<dim3(sh.C / 4, sh.B), kBlock, 0, st>>>(x, sh, ctx, fs);
+        else if (tpp == 256) cam_pool_kernel<T, VEC, 256><<<planes, kBlock, 0, st>>>(x, sh, ctx, fs);
         else if (tpp == 128) cam_pool_kernel<T, VEC, 128><<<(planes + 1) / 2, kBlock, 0, st>>>(x, sh, ctx, fs);
         else if (tpp == 64) cam_pool_kernel<T, VEC, 64><<<(planes + 3) / 4, kBlock, 0, st>>>(x, sh, ctx, fs);
         else cam_pool_kernel<T, VEC, 32><<<(planes + 7) / 8, kBlock, 0, st>>>(x, sh, ctx, fs));
