@@ -239,14 +239,29 @@ __device__ __forceinline__ void cam_mlp_body(const Shape& sh, const mga_cbam_par
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // 128-bit weight loads when the rows allow it: a warp's whole row of W1 (a thread's whole row of W2) is then one batch of
+    // independent loads = one L2 round trip instead of C/256 (Hd/8) of them -- with one CTA per sample this kernel is pure latency
+    const bool vec4 = (C % 4 == 0) && (Hd % 4 == 0) && (((reinterpret_cast<uintptr_t>(prm.w1) | reinterpret_cast<uintptr_t>(prm.w2)) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(smem) & 15) == 0);
     for (int j = w; j < Hd; j += kWarpsPerBlock) {
         const float* wr = prm.w1 + (size_t)j * C;
         float pa = 0.0f, pm = 0.0f;
+        if (vec4) {
 #pragma unroll 8
-        for (int c = lane; c < C; c += 32) {
-            const float wv = __ldg(wr + c);
-            pa = fmaf(wv, s_avg[c], pa);
-            pm = fmaf(wv, s_mx[c], pm);
+            for (int c = 4 * lane; c < C; c += 128) {
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + c));
+                const float4 av = *reinterpret_cast<const float4*>(s_avg + c);
+                const float4 mv = *reinterpret_cast<const float4*>(s_mx + c);
+                pa = fmaf(wv.x, av.x, fmaf(wv.y, av.y, fmaf(wv.z, av.z, fmaf(wv.w, av.w, pa))));
+                pm = fmaf(wv.x, mv.x, fmaf(wv.y, mv.y, fmaf(wv.z, mv.z, fmaf(wv.w, mv.w, pm))));
+            }
+        } else {
+#pragma unroll 8
+            for (int c = lane; c < C; c += 32) {
+                const float wv = __ldg(wr + c);
+                pa = fmaf(wv, s_avg[c], pa);
+                pm = fmaf(wv, s_mx[c], pm);
+            }
         }
         pa = warp_sum(pa);
         pm = warp_sum(pm);
@@ -263,11 +278,20 @@ __device__ __forceinline__ void cam_mlp_body(const Shape& sh, const mga_cbam_par
     for (int c = threadIdx.x; c < C; c += kBlock) {
         const float* wr = prm.w2 + (size_t)c * Hd;
         float za = 0.0f, zm = 0.0f;
+        if (vec4) {
+#pragma unroll 4
+            for (int j = 0; j < Hd; j += 4) {
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + j));
+                za = fmaf(wv.x, s_ha[j], fmaf(wv.y, s_ha[j + 1], fmaf(wv.z, s_ha[j + 2], fmaf(wv.w, s_ha[j + 3], za))));
+                zm = fmaf(wv.x, s_hm[j], fmaf(wv.y, s_hm[j + 1], fmaf(wv.z, s_hm[j + 2], fmaf(wv.w, s_hm[j + 3], zm))));
+            }
+        } else {
 #pragma unroll 8
-        for (int j = 0; j < Hd; ++j) {
-            const float wv = __ldg(wr + j);
-            za = fmaf(wv, s_ha[j], za);
-            zm = fmaf(wv, s_hm[j], zm);
+            for (int j = 0; j < Hd; ++j) {
+                const float wv = __ldg(wr + j);
+                za = fmaf(wv, s_ha[j], za);
+                zm = fmaf(wv, s_hm[j], zm);
+            }
         }
         const float bb = prm.b2[c];
         const float z = (za + bb) + (zm + bb);  // b2 enters twice (masked_cbam.py:128)
