@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MGA_ABI_VERSION 1
+#define MGA_ABI_VERSION 2
 
 enum { MGA_OK = 0, MGA_ERR_ARG = 1, MGA_ERR_UNSUPPORTED = 2, MGA_ERR_CUDA = 3, MGA_ERR_WORKSPACE = 4 };
 
@@ -47,6 +47,7 @@ enum {
     MGA_PYRAMID_MULTIPLY = 1 << 6, /* mga_pyramid_fusion = multiply (build-side mode); default add = reference alpha-skip */
     MGA_FORCE_SPLIT = 1 << 8,      /* one kernel per phase instead of the cluster-per-sample kernels (bits 9 and 11 are retired) */
     MGA_GATES_ONLY = 1 << 10,      /* internal: compute / differentiate the two gates s(B,C), a(B,HW) only (concat fusion modes) */
+    MGA_GATES_ACC = 1 << 16,       /* internal: gates backward adds an upstream feature gradient (mga_cbam_gates_backward_acc) */
     MGA_NO_PERSIST = 1 << 14,      /* tuning library only: skip the persistent shared-memory-resident experiment even when MGA_PF=1 */
     MGA_NO_SAVE = 1 << 12          /* inference (model.eval() + no_grad, predictor.py:7-24): the forward may skip the saved-for-backward
                                       planes; ctx is then NOT valid for mga_cbam_backward (s and a are still written) */
@@ -129,6 +130,12 @@ int mga_cbam_gates_forward(const mga_cbam_desc* d, const void* x, const void* ma
 int mga_cbam_gates_backward(const mga_cbam_desc* d, const void* x, const void* mask, const float* grad_s, const float* grad_a,
                             const mga_cbam_params* p, const void* ctx, void* grad_x, void* grad_mask, const mga_cbam_grads* gp,
                             void* scratch, void* stream);
+/* Same, with an upstream feature gradient: grad_x = grad_x_acc + (gate gradients pulled back to x).  grad_x_acc (B,C,H,W, feature dtype)
+ * is what another consumer of x already produced (the concat kernels' dx); the sum costs no extra pass (the kernel that writes grad_x reads
+ * it in place of grad_out).  grad_x_acc may be NULL (= mga_cbam_gates_backward); it must not alias grad_x. */
+int mga_cbam_gates_backward_acc(const mga_cbam_desc* d, const void* x, const void* mask, const float* grad_s, const float* grad_a,
+                                const void* grad_x_acc, const mga_cbam_params* p, const void* ctx, void* grad_x, void* grad_mask,
+                                const mga_cbam_grads* gp, void* scratch, void* stream);
 
 /* Fused forward of sam_cam_fusion = concat (build-side mode, parity unpinned) on the tcgen05 tensor cores, 16-bit features:
  *   out = k0 * x + k1 * (Wa (x * s) + Wb (x * a) + bias),   W = [Wa | Wb] (C, 2C) fp32 = fuse_sam_cam.weight, alpha = softplus(*beta),
@@ -145,6 +152,11 @@ int mga_cbam_concat_forward(const mga_cbam_desc* d, const void* x, const float* 
 int mga_cbam_concat_backward_elem(const mga_cbam_desc* d, const void* x, const void* grad_out, const void* uv, const float* s, const float* a,
                                   const float* bias, const float* beta, void* grad_x, void* ga, float* ds_part, float* dbias_part, float* grad_a,
                                   float* dalpha_part, void* stream);
+
+/* Weight gradient of mga_cbam_concat_forward from the per-sample GEMM results Ga = g X^T and Gb = (g * a) X^T, both (B, C, C) of gemm_dtype
+ * (MGA_F32 / MGA_BF16 / MGA_F16): grad_w (C, 2C) fp32 = alpha * [ sum_b Ga[b] diag(s_b) | sum_b Gb[b] ], fixed summation order. */
+int mga_cbam_concat_wgrad_reduce(const mga_cbam_desc* d, const void* Ga, const void* Gb, int gemm_dtype, const float* s, const float* beta,
+                                 float* grad_w, void* stream);
 
 /* read-back of small saved quantities for tests / logging: which = 0 s(B,C), 1 a(B,HW) */
 int mga_cbam_ctx_view(const mga_cbam_desc* d, const void* ctx, int which, const float** ptr, size_t* count);

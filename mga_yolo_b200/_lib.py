@@ -11,7 +11,7 @@ from pathlib import Path
 import os as _os
 
 LIB_PATH = Path(__file__).resolve().parent / _os.environ.get("MGA_LIBNAME", "libmga_cbam.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums of include/mga_cbam.h
 F32, BF16, F16, U8 = 0, 1, 2, 3
@@ -21,9 +21,10 @@ DS_NEAREST, DS_AREA, DS_MAXPOOL, DS_AVGPOOL, DS_AREA_RAW = 0, 1, 2, 3, 4
 
 EXPORTS = (
     "mga_abi_version", "mga_last_error", "mga_cbam_workspace", "mga_cbam_forward", "mga_cbam_backward",
-    "mga_cbam_ctx_view", "mga_mask_downsample", "mga_masks_multi", "mga_masks_multi_ws", "mga_cbam_plan", "mga_cbam_gates_forward", "mga_cbam_gates_backward", "mga_launch_count", "mga_profile_enable", "mga_profile_count",
+    "mga_cbam_ctx_view", "mga_mask_downsample", "mga_masks_multi", "mga_masks_multi_ws", "mga_cbam_plan", "mga_cbam_gates_forward", "mga_cbam_gates_backward", "mga_cbam_gates_backward_acc", "mga_launch_count", "mga_profile_enable", "mga_profile_count",
     "mga_profile_read", "mga_eca_workspace", "mga_eca_forward", "mga_eca_backward", "mga_head_tail_forward", "mga_head_tail_backward",
     "mga_gate_sample_forward", "mga_gate_sample_backward", "mga_collate_masks", "mga_cbam_concat_forward", "mga_cbam_concat_backward_elem",
+    "mga_cbam_concat_wgrad_reduce",
 )
 
 
@@ -76,8 +77,11 @@ def load() -> C.CDLL:
     lib.mga_cbam_gates_forward.argtypes = [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mga_cbam_gates_backward.argtypes = [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.POINTER(Grads), C.c_void_p, C.c_void_p]
+    lib.mga_cbam_gates_backward_acc.argtypes = [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params),
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Grads), C.c_void_p, C.c_void_p]
     lib.mga_cbam_gates_forward.restype = C.c_int
     lib.mga_cbam_gates_backward.restype = C.c_int
+    lib.mga_cbam_gates_backward_acc.restype = C.c_int
     lib.mga_cbam_ctx_view.argtypes = [C.POINTER(Desc), C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.mga_mask_downsample.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p]
@@ -104,6 +108,8 @@ def load() -> C.CDLL:
     lib.mga_cbam_concat_forward.restype = C.c_int
     lib.mga_cbam_concat_backward_elem.argtypes = [C.POINTER(Desc)] + [C.c_void_p] * 14
     lib.mga_cbam_concat_backward_elem.restype = C.c_int
+    lib.mga_cbam_concat_wgrad_reduce.argtypes = [C.POINTER(Desc), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mga_cbam_concat_wgrad_reduce.restype = C.c_int
     for fn in (lib.mga_eca_workspace, lib.mga_eca_forward, lib.mga_eca_backward, lib.mga_head_tail_forward, lib.mga_head_tail_backward,
                lib.mga_gate_sample_forward, lib.mga_gate_sample_backward, lib.mga_collate_masks):
         fn.restype = C.c_int

@@ -385,7 +385,8 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* 
     const bool act = u < U;
     const bool add = sh.samcam_add();
     const bool has_mask = sh.has_mask();
-    const float k0 = sh.gates_only() ? 0.0f : ctx.consts[0], k1 = sh.gates_only() ? 0.0f : ctx.consts[1];  // gates mode: no direct g term
+    // gates mode: no direct g term; with an upstream feature gradient in place of g (MGA_GATES_ACC) it passes through with weight 1
+    const float k0 = sh.gates_only() ? (sh.gates_acc() ? 1.0f : 0.0f) : ctx.consts[0], k1 = sh.gates_only() ? 0.0f : ctx.consts[1];
     const size_t plane = (size_t)sh.B * sh.S;
 
     float av[VEC], d0[VEC], d1[VEC], mv[VEC], racc[VEC];

@@ -426,4 +426,38 @@ __global__ void __launch_bounds__(kBlock) concat_bwd_elem_kernel(const T* __rest
     }
 }
 
+
+// ---------------------------------------------------------------- weight gradient: batch reduction of the per-sample GEMM results
+//   dW[o][i]     = alpha * sum_b Ga[b][o][i] * s[b][i]      Ga = g X^T   (B, C, C)
+//   dW[o][C + i] = alpha * sum_b Gb[b][o][i]                Gb = (g a) X^T
+// One thread per (o, i), fixed summation order over the batch (deterministic), fp32 accumulation; TG = element type of the GEMM results.
+template <typename TG>
+__global__ void __launch_bounds__(kBlock) concat_wgrad_reduce_kernel(const TG* __restrict__ Ga, const TG* __restrict__ Gb, const float* __restrict__ s,
+                                                                     const float* __restrict__ beta, float* __restrict__ dw, int B, int C) {
+    const int e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= C * C) return;
+    const int o = e / C, i = e - o * C;
+    const size_t CC = (size_t)C * C;
+    float accA = 0.0f, accB = 0.0f;
+    int b = 0;
+    for (; b + 4 <= B; b += 4) {
+        float ga[4], gb[4], sv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            ga[q] = to_f<TG>(Ga[(size_t)(b + q) * CC + e]);
+            gb[q] = to_f<TG>(Gb[(size_t)(b + q) * CC + e]);
+            sv[q] = __ldg(s + (size_t)(b + q) * C + i);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { accA = fmaf(ga[q], sv[q], accA); accB += gb[q]; }
+    }
+    for (; b < B; ++b) {
+        accA = fmaf(to_f<TG>(Ga[(size_t)b * CC + e]), __ldg(s + (size_t)b * C + i), accA);
+        accB += to_f<TG>(Gb[(size_t)b * CC + e]);
+    }
+    const float alpha = softplusf_acc(__ldg(beta));
+    dw[(size_t)o * 2 * C + i] = alpha * accA;
+    dw[(size_t)o * 2 * C + C + i] = alpha * accB;
+}
+
 }  // namespace mga

@@ -348,6 +348,7 @@ struct Shape {
     __host__ __device__ bool samcam_add() const { return flags & MGA_SAMCAM_ADD; }
     __host__ __device__ bool pyramid_multiply() const { return flags & MGA_PYRAMID_MULTIPLY; }
     __host__ __device__ bool gates_only() const { return flags & MGA_GATES_ONLY; }
+    __host__ __device__ bool gates_acc() const { return flags & MGA_GATES_ACC; }
     __host__ __device__ bool no_save() const { return flags & MGA_NO_SAVE; }
 };
 

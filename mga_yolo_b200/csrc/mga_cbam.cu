@@ -981,10 +981,19 @@ int mga_cbam_gates_forward(const mga_cbam_desc* d, const void* x, const void* ma
 int mga_cbam_gates_backward(const mga_cbam_desc* d, const void* x, const void* mask, const float* grad_s, const float* grad_a,
                             const mga_cbam_params* p, const void* ctx_buf, void* grad_x, void* grad_mask, const mga_cbam_grads* gp,
                             void* scratch, void* stream) {
+    return mga_cbam_gates_backward_acc(d, x, mask, grad_s, grad_a, nullptr, p, ctx_buf, grad_x, grad_mask, gp, scratch, stream);
+}
+
+int mga_cbam_gates_backward_acc(const mga_cbam_desc* d, const void* x, const void* mask, const float* grad_s, const float* grad_a,
+                                const void* grad_x_acc, const mga_cbam_params* p, const void* ctx_buf, void* grad_x, void* grad_mask,
+                                const mga_cbam_grads* gp, void* scratch, void* stream) {
     if (!d) return fail(MGA_ERR_ARG, "null descriptor");
     if (!grad_s || !grad_a) return fail(MGA_ERR_ARG, "null gate gradient");
     mga_cbam_desc g = *d;
     g.flags |= MGA_GATES_ONLY | MGA_SAMCAM_ADD | MGA_FORCE_SPLIT;
+    if (grad_x_acc) g.flags |= MGA_GATES_ACC;
+    if (grad_x_acc && grad_x_acc == grad_x) return fail(MGA_ERR_ARG, "grad_x_acc must not alias grad_x");
+    const void* gsrc = grad_x_acc ? grad_x_acc : x;  // read as grad_out by the last kernel: weight 1 (accumulate) or 0
     Shape sh;
     if (int rc = validate(&g, &sh)) return rc;
     if (!x || !p || !ctx_buf || !grad_x || !gp || !scratch) return fail(MGA_ERR_ARG, "null pointer argument");
@@ -997,10 +1006,10 @@ int mga_cbam_gates_backward(const mga_cbam_desc* d, const void* x, const void* m
     bs.epart = const_cast<float*>(grad_s);  // (B,1,C): the single "tile" of channel-gate gradients
     bs.gxpart = const_cast<float*>(grad_s); // read but unused (feeds d beta only)
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    switch (g.dtype) {  // grad_out := x (multiplied by k0 = k1 = 0 inside bwd_dx)
-        case MGA_F32: return backward_t<float>(sh, &g, x, mask, x, *p, ctx, grad_x, grad_mask, *gp, bs, st);
-        case MGA_BF16: return backward_t<__nv_bfloat16>(sh, &g, x, mask, x, *p, ctx, grad_x, grad_mask, *gp, bs, st);
-        default: return backward_t<__half>(sh, &g, x, mask, x, *p, ctx, grad_x, grad_mask, *gp, bs, st);
+    switch (g.dtype) {  // grad_out := x (multiplied by k0 = k1 = 0 inside bwd_dx) or the upstream gradient (k0 = 1)
+        case MGA_F32: return backward_t<float>(sh, &g, x, mask, gsrc, *p, ctx, grad_x, grad_mask, *gp, bs, st);
+        case MGA_BF16: return backward_t<__nv_bfloat16>(sh, &g, x, mask, gsrc, *p, ctx, grad_x, grad_mask, *gp, bs, st);
+        default: return backward_t<__half>(sh, &g, x, mask, gsrc, *p, ctx, grad_x, grad_mask, *gp, bs, st);
     }
 }
 
@@ -1041,6 +1050,27 @@ int mga_cbam_concat_backward_elem(const mga_cbam_desc* d, const void* x, const v
             static_cast<T*>(grad_x), static_cast<T*>(ga), ds_part, dbias_part, grad_a, dalpha_part, d->C, S, pm)));
     }
     return check_launch("mga_cbam_concat_backward_elem");
+}
+
+int mga_cbam_concat_wgrad_reduce(const mga_cbam_desc* d, const void* Ga, const void* Gb, int gemm_dtype, const float* s, const float* beta,
+                                 float* grad_w, void* stream) {
+    if (!d || !Ga || !Gb || !s || !beta || !grad_w) return fail(MGA_ERR_ARG, "null pointer argument");
+    if (d->B <= 0 || d->C <= 0 || (long long)d->C * d->C > (1LL << 30)) return fail(MGA_ERR_ARG, "bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int C = d->C, grid = (C * C + kBlock - 1) / kBlock;
+    switch (gemm_dtype) {
+        case MGA_F32:
+            MGA_LAUNCH("concat_wgrad", st, (concat_wgrad_reduce_kernel<float><<<grid, kBlock, 0, st>>>(static_cast<const float*>(Ga), static_cast<const float*>(Gb), s, beta, grad_w, d->B, C)));
+            break;
+        case MGA_BF16:
+            MGA_LAUNCH("concat_wgrad", st, (concat_wgrad_reduce_kernel<__nv_bfloat16><<<grid, kBlock, 0, st>>>(static_cast<const __nv_bfloat16*>(Ga), static_cast<const __nv_bfloat16*>(Gb), s, beta, grad_w, d->B, C)));
+            break;
+        case MGA_F16:
+            MGA_LAUNCH("concat_wgrad", st, (concat_wgrad_reduce_kernel<__half><<<grid, kBlock, 0, st>>>(static_cast<const __half*>(Ga), static_cast<const __half*>(Gb), s, beta, grad_w, d->B, C)));
+            break;
+        default: return fail(MGA_ERR_ARG, "bad GEMM result dtype %d", gemm_dtype);
+    }
+    return check_launch("mga_cbam_concat_wgrad_reduce");
 }
 
 int mga_cbam_ctx_view(const mga_cbam_desc* d, const void* ctx_buf, int which, const float** ptr, size_t* count) {

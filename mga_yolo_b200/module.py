@@ -208,14 +208,16 @@ class MaskGuidedCBAM(nn.Module):
             R = ops.mask_guided_cbam(feat, mask, lin1.weight, lin1.bias, lin2.weight, lin2.bias, self.sam_conv.weight, one,
                                      flags=(flags | _lib.PYRAMID_MULTIPLY), tiny_mask_thr=self.tiny_thr, eps=self.eps)
         else:
-            s, a = ops.cbam_gates(feat, mask, lin1.weight, lin1.bias, lin2.weight, lin2.bias, self.sam_conv.weight,
-                                  flags=flags & ~_lib.PYRAMID_MULTIPLY, tiny_mask_thr=self.tiny_thr, eps=self.eps)
             if (self.sam_cam_fusion == "concat" and self.mga_pyramid_fusion in ("add", "multiply") and next_ops.concat_fused_supported(feat)
                     and not os.getenv("MGA_CONCAT_LIBRARY", "")):
-                # 16-bit features with C % 128 == 0: ONE tcgen05 kernel does the (virtual) concat, both 1x1 convolutions, the spatial
-                # gate and the pyramid fusion (csrc/cbam_concat.cuh); the backward is the closed form on library GEMMs
-                return next_ops.concat_fused(feat, s, a, self.fuse_sam_cam.weight, self.fuse_sam_cam.bias, self.beta,
-                                             self.mga_pyramid_fusion == "multiply")
+                # 16-bit features with C % 128 == 0: gates op + ONE tcgen05 kernel that does the (virtual) concat, both 1x1 convolutions,
+                # the spatial gate and the pyramid fusion (csrc/cbam_concat.cuh), as one autograd node (closed-form backward)
+                return next_ops.concat_block(feat, mask, lin1.weight, lin1.bias, lin2.weight, lin2.bias, self.sam_conv.weight,
+                                             self.fuse_sam_cam.weight, self.fuse_sam_cam.bias, self.beta,
+                                             flags=flags & ~_lib.PYRAMID_MULTIPLY, tiny_mask_thr=self.tiny_thr, eps=self.eps,
+                                             pyramid_multiply=self.mga_pyramid_fusion == "multiply")
+            s, a = ops.cbam_gates(feat, mask, lin1.weight, lin1.bias, lin2.weight, lin2.bias, self.sam_conv.weight,
+                                  flags=flags & ~_lib.PYRAMID_MULTIPLY, tiny_mask_thr=self.tiny_thr, eps=self.eps)
             xs = feat * s.to(dt)[:, :, None, None]
             xa = feat * a.to(dt)
             if self.sam_cam_fusion == "concat":

@@ -338,40 +338,87 @@ class _ConcatFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         x, s, a, w, bias, beta = ctx.saved_tensors
-        lib = _lib.load()
-        B, Cc, H, W = x.shape
-        S = H * W
-        dt = x.dtype
-        x = x.contiguous()
-        g = gout.contiguous().to(dt)
-        w2 = w.reshape(Cc, 2 * Cc)
-        wcat_t = torch.cat([w2[:, :Cc].t(), w2[:, Cc:].t()], dim=0).to(dt).contiguous()      # (2C, C): [Wa^T ; Wb^T]
-        uv = torch.matmul(wcat_t, g.reshape(B, Cc, S))                                         # (B, 2C, S), one library GEMM
-        sf, af, bf, btf = _f32c(s), _f32c(a), _f32c(bias), _f32c(beta)
-        nT = (S // 8 + 31) // 32
-        d = _lib.Desc(B, Cc, H, W, 1, 1, _DT[dt], _lib.F32, _lib.PYRAMID_MULTIPLY if ctx.pm else 0, 0.0, 0.0)
-        with torch.cuda.device(x.device):
-            dx = torch.empty_like(x)
-            ga = torch.empty_like(x)
-            ds_part = torch.empty((B, nT, Cc), dtype=torch.float32, device=x.device)
-            db_part = torch.empty((B, nT, Cc), dtype=torch.float32, device=x.device)
-            da = torch.empty((B, S), dtype=torch.float32, device=x.device)
-            dal_part = torch.empty((B, nT), dtype=torch.float32, device=x.device)
-            rc = lib.mga_cbam_concat_backward_elem(C.byref(d), x.data_ptr(), g.data_ptr(), uv.data_ptr(), sf.data_ptr(), af.data_ptr(), bf.data_ptr(),
-                                                   btf.data_ptr(), dx.data_ptr(), ga.data_ptr(), ds_part.data_ptr(), db_part.data_ptr(), da.data_ptr(),
-                                                   dal_part.data_ptr(), _stream(x))
+        dx, ds, da, dw, dbias, dbeta = _concat_backward(x, s, a, w, bias, beta, gout, ctx.pm)
+        return dx, ds, da, dw, dbias, dbeta, None
+
+
+def _concat_backward(x, s, a, w, bias, beta, gout, pyramid_multiply):
+    """Closed-form backward of cbam_concat_fwd: (dx, ds, da, dw, dbias, dbeta).  GEMMs from the library (U|V = [Wa^T ; Wb^T] g and the two
+    per-sample weight-gradient products, fp32 results), everything else in two kernels of this library."""
+    lib = _lib.load()
+    B, Cc, H, W = x.shape
+    S = H * W
+    dt = x.dtype
+    x = x.contiguous()
+    g = gout.contiguous().to(dt)
+    w2 = w.reshape(Cc, 2 * Cc)
+    wcat_t = torch.cat([w2[:, :Cc].t(), w2[:, Cc:].t()], dim=0).to(dt).contiguous()      # (2C, C): [Wa^T ; Wb^T]
+    uv = torch.matmul(wcat_t, g.reshape(B, Cc, S))                                         # (B, 2C, S), one library GEMM
+    sf, af, bf, btf = _f32c(s), _f32c(a), _f32c(bias), _f32c(beta)
+    nT = (S // 8 + 31) // 32
+    d = _lib.Desc(B, Cc, H, W, 1, 1, _DT[dt], _lib.F32, _lib.PYRAMID_MULTIPLY if pyramid_multiply else 0, 0.0, 0.0)
+    with torch.cuda.device(x.device):
+        dx = torch.empty_like(x)
+        ga = torch.empty_like(x)
+        ds_part = torch.empty((B, nT, Cc), dtype=torch.float32, device=x.device)
+        db_part = torch.empty((B, nT, Cc), dtype=torch.float32, device=x.device)
+        da = torch.empty((B, S), dtype=torch.float32, device=x.device)
+        dal_part = torch.empty((B, nT), dtype=torch.float32, device=x.device)
+        rc = lib.mga_cbam_concat_backward_elem(C.byref(d), x.data_ptr(), g.data_ptr(), uv.data_ptr(), sf.data_ptr(), af.data_ptr(), bf.data_ptr(),
+                                               btf.data_ptr(), dx.data_ptr(), ga.data_ptr(), ds_part.data_ptr(), db_part.data_ptr(), da.data_ptr(),
+                                               dal_part.data_ptr(), _stream(x))
         _lib.check(rc, "mga_cbam_concat_backward_elem")
-        alpha = torch.nn.functional.softplus(btf)
+        del uv
+        # weight gradient: two per-sample GEMMs with fp32 results, then ONE kernel sums them over the batch (the channel gate folded in)
         xt = x.reshape(B, Cc, S).transpose(1, 2)
-        Ga = torch.bmm(g.reshape(B, Cc, S), xt)                                                # (B,C,C): g X^T
-        Gb = torch.bmm(ga.reshape(B, Cc, S), xt)                                               # (g * a) X^T
-        dwa = alpha * torch.einsum("boi,bi->oi", Ga.float(), sf.reshape(B, Cc))
-        dwb = alpha * Gb.float().sum(dim=0)
-        dw = torch.cat([dwa, dwb], dim=1).reshape(w.shape).to(w.dtype)
-        ds = ds_part.sum(dim=1).reshape(s.shape).to(s.dtype)
-        dbias = db_part.sum(dim=(0, 1)).to(bias.dtype)
-        dbeta = (torch.sigmoid(btf) * dal_part.double().sum().float()).reshape(beta.shape).to(beta.dtype)
-        return dx, ds, da.reshape(a.shape).to(a.dtype), dw, dbias, dbeta, None
+        Ga = torch.bmm(g.reshape(B, Cc, S), xt, out_dtype=torch.float32)                       # (B,C,C): g X^T
+        Gb = torch.bmm(ga.reshape(B, Cc, S), xt, out_dtype=torch.float32)                      # (g * a) X^T
+        dw32 = torch.empty((Cc, 2 * Cc), dtype=torch.float32, device=x.device)
+        rc = lib.mga_cbam_concat_wgrad_reduce(C.byref(d), Ga.data_ptr(), Gb.data_ptr(), _lib.F32, sf.data_ptr(), btf.data_ptr(), dw32.data_ptr(),
+                                              _stream(x))
+        _lib.check(rc, "mga_cbam_concat_wgrad_reduce")
+    dw = dw32.reshape(w.shape).to(w.dtype)
+    ds = ds_part.sum(dim=1).reshape(s.shape).to(s.dtype)
+    dbias = db_part.sum(dim=(0, 1)).to(bias.dtype)
+    dbeta = (torch.sigmoid(btf) * dal_part.double().sum().float()).reshape(beta.shape).to(beta.dtype)
+    return dx, ds, da.reshape(a.shape).to(a.dtype), dw, dbias, dbeta
+
+
+class _ConcatBlockFn(torch.autograd.Function):
+    """The whole `sam_cam_fusion = concat` block -- gates op + fused concat -- as ONE autograd node: the feature gradient through the two
+    1x1 convolutions and the one through the gates are summed inside the kernel that writes grad_x (mga_cbam_gates_backward_acc), not by
+    an extra pass over two N-sized tensors."""
+
+    @staticmethod
+    def forward(ctx, x, mask, w1, b1, w2, b2, wsam, wf, bf, beta, flags, tiny_thr, eps, pyramid_multiply):
+        s, a, saved = torch.ops.mga.cbam_gates_fwd(x, mask, w1, b1, w2, b2, wsam, flags, tiny_thr, eps)
+        out = torch.ops.mga.cbam_concat_fwd(x, s, a, wf, bf, beta, pyramid_multiply)
+        ctx.save_for_backward(x, mask, w1, b1, w2, b2, wsam, wf, bf, beta, s, a, saved)
+        ctx.cfg = (flags, tiny_thr, eps, pyramid_multiply)
+        ctx.param_shapes = tuple(t.shape for t in (w1, b1, w2, b2, wsam))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, mask, w1, b1, w2, b2, wsam, wf, bf, beta, s, a, saved = ctx.saved_tensors
+        flags, tiny_thr, eps, pm = ctx.cfg
+        dx_c, ds, da, dwf, dbf, dbeta = _concat_backward(x, s, a, wf, bf, beta, gout, pm)
+        need_mask = mask is not None and ctx.needs_input_grad[1]
+        dx, dmask, flat = torch.ops.mga.cbam_gates_bwd(ds, da, x, mask, w1, b1, w2, b2, wsam, saved, flags, tiny_thr, eps, need_mask, dx_c)
+        grads, o = [], 0
+        for shp in ctx.param_shapes:
+            n = 1
+            for v in shp:
+                n *= v
+            grads.append(flat[o:o + n].view(shp))
+            o += n
+        return (dx, dmask, *grads, dwf, dbf, dbeta, None, None, None, None)
+
+
+def concat_block(x, mask, w1, b1, w2, b2, wsam, wf, bf, beta, *, flags: int, tiny_mask_thr: float, eps: float, pyramid_multiply: bool):
+    """out = k0 x + k1 (Wa (x s) + Wb (x a') + bias) with the gates (s, a') of the block computed from (x, mask): gates op + tcgen05 concat
+    kernel forward, one autograd node (see _ConcatBlockFn)."""
+    return _ConcatBlockFn.apply(x, mask, w1, b1, w2, b2, wsam, wf, bf, beta, int(flags), float(tiny_mask_thr), float(eps), bool(pyramid_multiply))
 
 
 def concat_fused(x, s, a, w, bias, beta, pyramid_multiply: bool):

@@ -36,7 +36,7 @@ _LIBDEF.define(
 )
 _LIBDEF.define(
     "cbam_gates_bwd(Tensor grad_s, Tensor grad_a, Tensor x, Tensor? mask, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor wsam, "
-    "Tensor ctx, int flags, float tiny_thr, float eps, bool need_mask_grad) -> (Tensor, Tensor?, Tensor)"
+    "Tensor ctx, int flags, float tiny_thr, float eps, bool need_mask_grad, Tensor? grad_x_acc=None) -> (Tensor, Tensor?, Tensor)"
 )
 _LIBDEF.define("mask_downsample(Tensor src, int stride, int method, float thresh, bool close3x3, bool out_float) -> Tensor")
 _LIBDEF.define("masks_multi(Tensor src, int method, float thresh, bool close3x3, bool out_float) -> (Tensor, Tensor, Tensor)")
@@ -196,9 +196,13 @@ def _cbam_gates_fwd_cuda(x, mask, w1, b1, w2, b2, wsam, flags, tiny_thr, eps):
     return views[0], views[1], ctx
 
 
-def _cbam_gates_bwd_cuda(grad_s, grad_a, x, mask, w1, b1, w2, b2, wsam, ctx, flags, tiny_thr, eps, need_mask_grad):
+def _cbam_gates_bwd_cuda(grad_s, grad_a, x, mask, w1, b1, w2, b2, wsam, ctx, flags, tiny_thr, eps, need_mask_grad, grad_x_acc=None):
     lib = _lib.load()
     x = x.contiguous()
+    if grad_x_acc is not None:  # upstream feature gradient: summed into dx by the kernel that writes it (no extra pass)
+        if grad_x_acc.shape != x.shape:
+            raise RuntimeError(f"grad_x_acc {tuple(grad_x_acc.shape)} does not match x {tuple(x.shape)}")
+        grad_x_acc = grad_x_acc.to(x.dtype).contiguous()
     mask = None if mask is None else mask.contiguous()
     grad_s = grad_s.float().contiguous()
     grad_a = grad_a.float().contiguous()
@@ -216,10 +220,11 @@ def _cbam_gates_bwd_cuda(grad_s, grad_a, x, mask, w1, b1, w2, b2, wsam, ctx, fla
             offs.append(offs[-1] + v)
         gp = _lib.Grads(*(flat.data_ptr() + 4 * o for o in offs[:-1]))
         scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=x.device)
-        rc = lib.mga_cbam_gates_backward(C.byref(d), x.data_ptr(), None if mask is None else mask.data_ptr(), grad_s.data_ptr(),
-                                         grad_a.data_ptr(), C.byref(prm), ctx.data_ptr(), dx.data_ptr(),
-                                         None if dmask is None else dmask.data_ptr(), C.byref(gp), scratch.data_ptr(), _stream(x))
-    _lib.check(rc, "mga_cbam_gates_backward")
+        rc = lib.mga_cbam_gates_backward_acc(C.byref(d), x.data_ptr(), None if mask is None else mask.data_ptr(), grad_s.data_ptr(),
+                                             grad_a.data_ptr(), None if grad_x_acc is None else grad_x_acc.data_ptr(), C.byref(prm),
+                                             ctx.data_ptr(), dx.data_ptr(), None if dmask is None else dmask.data_ptr(), C.byref(gp),
+                                             scratch.data_ptr(), _stream(x))
+    _lib.check(rc, "mga_cbam_gates_backward_acc")
     return dx, dmask, flat
 
 
@@ -249,7 +254,7 @@ def _cbam_gates_fwd_meta(x, mask, w1, b1, w2, b2, wsam, flags, tiny_thr, eps):
             x.new_empty(_ctx_bytes_of(x, mask, w1, wsam, flags, tiny_thr, eps), dtype=torch.uint8))
 
 
-def _cbam_gates_bwd_meta(grad_s, grad_a, x, mask, w1, b1, w2, b2, wsam, ctx, flags, tiny_thr, eps, need_mask_grad):
+def _cbam_gates_bwd_meta(grad_s, grad_a, x, mask, w1, b1, w2, b2, wsam, ctx, flags, tiny_thr, eps, need_mask_grad, grad_x_acc=None):
     dmask = torch.empty_like(mask, memory_format=torch.contiguous_format) if (mask is not None and need_mask_grad) else None
     return torch.empty_like(x, memory_format=torch.contiguous_format), dmask, x.new_empty(_grad_numel(x, w1, wsam), dtype=torch.float32)
 
