@@ -153,6 +153,18 @@ int mga_cbam_concat_backward_elem(const mga_cbam_desc* d, const void* x, const v
                                   const float* bias, const float* beta, void* grad_x, void* ga, float* ds_part, float* dbias_part, float* grad_a,
                                   float* dalpha_part, void* stream);
 
+/* Backward of mga_cbam_concat_forward with respect to the features and the gates, on the tcgen05 tensor cores: U = Wa^T g and V = Wb^T g
+ * are the two accumulators of ONE kernel whose epilogue finishes the closed form (U, V never reach memory):
+ *   grad_x = alpha (s_c U + a_p V) + k0 grad_out        ga = grad_out * a_p   (B,C,H*W, feature dtype; left operand of the dWb GEMM)
+ *   ds_part, dbias_part (B, 2 nT, C)  per-(128-pixel tile, half) partial sums over pixels:   ds = sum over dim 1, dbias = sum over dims 0, 1
+ *   da_part (B, C / 32, H*W)          per-32-channel partial sums:                            grad_a = sum over dim 1
+ *   dalpha_part (B, nT, C / 16)       partial sums of d out / d alpha:                        d beta = sigmoid(beta) * sum
+ * with nT = ceil(H*W / 128); every partial buffer is written (never accumulated): deterministic.  wscratch: 2 * C * C elements of the
+ * feature dtype (the transposed weights).  Same shape / dtype conditions as mga_cbam_concat_forward. */
+int mga_cbam_concat_backward_dx(const mga_cbam_desc* d, const void* x, const void* grad_out, const float* s, const float* a, const float* w,
+                                const float* bias, const float* beta, void* grad_x, void* ga, float* ds_part, float* dbias_part, float* da_part,
+                                float* dalpha_part, void* wscratch, void* stream);
+
 /* Weight gradient of mga_cbam_concat_forward from the per-sample GEMM results Ga = g X^T and Gb = (g * a) X^T, both (B, C, C) of gemm_dtype
  * (MGA_F32 / MGA_BF16 / MGA_F16): grad_w (C, 2C) fp32 = alpha * [ sum_b Ga[b] diag(s_b) | sum_b Gb[b] ], fixed summation order. */
 int mga_cbam_concat_wgrad_reduce(const mga_cbam_desc* d, const void* Ga, const void* Gb, int gemm_dtype, const float* s, const float* beta,

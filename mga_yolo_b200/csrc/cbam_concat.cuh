@@ -123,6 +123,98 @@ __device__ __forceinline__ void concat_epilogue_tile(uint32_t tacc, int warp, in
         }
     }
 }
+// ---- backward (MODE 1 of the two GEMM kernels below): the same two-accumulator GEMM on the upstream gradient,
+//        U = Wa^T g,  V = Wb^T g   (weights transposed by concat_transpose_kernel, shared by the batch; feature operand = g),
+// and everything else of the closed-form backward in the epilogue, on the fp32 accumulators (U, V never reach memory):
+//   dx   = alpha (s_c U + a_p V) + k0 g          ga = g a_p  (left operand of the dWb GEMM)
+//   ds_c = alpha sum_p x U      dbias_c = alpha sum_p g      da_p = alpha sum_c x V      dalpha = sum x (s U + a V) + sum_c bias_c sum_p g - [add] sum g x
+// A lane owns one channel row of the tile: the per-channel sums are lane-private over the warp's 64 pixel columns (written per (pixel
+// tile, half) -> ds_part / dbias_part (B, 2 nTilesN, C)); the per-pixel sum over channels is a warp reduction over the 32 rows
+// (-> da_part (B, C / 32, S)); dalpha per warp (-> dalpha_part (B, nTilesN, C / 128 * 8)).  All partial buffers are written, never
+// accumulated: deterministic, no atomics.
+struct ConcatBwd {
+    const void* x;       // saved features (B, C, S)
+    const float* s;      // channel gate (B, C)
+    void* ga;            // out: g * a' (B, C, S)
+    float* ds_part;
+    float* db_part;
+    float* da_part;
+    float* dal_part;
+};
+
+template <typename T>
+__device__ __forceinline__ void concat_epilogue_bwd_tile(uint32_t tacc, int warp, int lane, const T* __restrict__ g, const float* a_sm,
+                                                         const float* __restrict__ bias, T* __restrict__ dx, const ConcatBwd& bw, int b, int m0,
+                                                         int p0, int C, int S, float k0, float alpha, int pyramid_multiply) {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int c = m0 + q * 32 + lane;
+    const float sc = __ldg(bw.s + (size_t)b * C + c);
+    const uint32_t trow = tacc + ((uint32_t)(q * 32) << 16);
+    const size_t rowoff = ((size_t)b * C + c) * S;
+    const T* __restrict__ xf = static_cast<const T*>(bw.x);
+    T* __restrict__ gaf = static_cast<T*>(bw.ga);
+    float* __restrict__ dap = bw.da_part + ((size_t)b * (C / 32) + (m0 / 32 + q)) * S;
+    const int nTilesN = (S + kCcBN - 1) / kCcBN;
+    float su = 0.0f, sg = 0.0f, dal = 0.0f;
+#pragma unroll 1
+    for (int c16 = half * 4; c16 < half * 4 + 4; ++c16) {
+        const int p = p0 + c16 * 16;
+        uint32_t y1[16], y2[16];
+        tmem_ld16(trow + c16 * 16, y1);
+        tmem_ld16(trow + kCcBN + c16 * 16, y2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (p >= S) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ph8 = p + h * 8;
+            if (ph8 >= S) break;  // (S % 8 == 0: whole 16-byte pieces; warp-uniform)
+            const float4 a0 = *reinterpret_cast<const float4*>(a_sm + c16 * 16 + h * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(a_sm + c16 * 16 + h * 8 + 4);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float xv[8], gv[8], ov[8], gav[8], va[8];
+            ldv<T, 8, kLdStream>(xf + rowoff + ph8, xv);
+            ldv<T, 8, kLdStream>(g + rowoff + ph8, gv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float U = __uint_as_float(y1[h * 8 + i]), V = __uint_as_float(y2[h * 8 + i]);
+                const float t = fmaf(sc, U, av[i] * V);
+                ov[i] = fmaf(alpha, t, k0 * gv[i]);
+                gav[i] = gv[i] * av[i];
+                su = fmaf(xv[i], U, su);
+                sg += gv[i];
+                va[i] = xv[i] * V;
+                dal = fmaf(xv[i], t, dal);
+                if (!pyramid_multiply) dal = fmaf(-gv[i], xv[i], dal);
+            }
+            stv<T, 8, true>(dx + rowoff + ph8, ov);
+            stv<T, 8, true>(gaf + rowoff + ph8, gav);
+            float keep = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float r = warp_sum(va[i]);
+                if (lane == i) keep = r;
+            }
+            if (lane < 8) dap[ph8 + lane] = alpha * keep;
+        }
+    }
+    const size_t pi = ((size_t)b * (2 * nTilesN) + (size_t)(p0 / kCcBN) * 2 + half) * C + c;
+    bw.ds_part[pi] = alpha * su;
+    bw.db_part[pi] = alpha * sg;
+    dal = fmaf(__ldg(bias + c), sg, dal);
+    dal = warp_sum(dal);
+    if (lane == 0) bw.dal_part[((size_t)b * nTilesN + p0 / kCcBN) * (size_t)(C / kCcBM * 8) + (m0 / kCcBM) * 8 + (warp - 2)] = dal;
+}
+
+// W (C, 2C) fp32 -> wat[ci][co] = W[co][ci], wbt[ci][co] = W[co][C + ci] in the feature dtype (A operands of the backward GEMMs, K = co contiguous)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) concat_transpose_kernel(const float* __restrict__ w, T* __restrict__ wat, T* __restrict__ wbt, int C) {
+    const int e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= C * C) return;
+    const int ci = e / C, co = e - ci * C;
+    wat[e] = from_f<T>(__ldg(w + (size_t)co * 2 * C + ci));
+    wbt[e] = from_f<T>(__ldg(w + (size_t)co * 2 * C + C + ci));
+}
+
 // the spatial gate of pixels [p0, p0 + 128) of sample b into shared memory (epilogue threads only), then a barrier among them
 __device__ __forceinline__ void concat_stage_gate(float* a_sm, const float* __restrict__ agate, int b, int p0, int S) {
     const int i = (int)threadIdx.x - 64;
@@ -130,10 +222,11 @@ __device__ __forceinline__ void concat_stage_gate(float* a_sm, const float* __re
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kCcEpiWarps) : "memory");
 }
 
-template <typename T>
+template <typename T, int MODE = 0 /* 0: forward, 1: backward (x := grad_out, out := grad_x, weights transposed and batch-shared) */>
 __global__ void __launch_bounds__(kCcThreads, 1) concat_fwd_kernel(const __grid_constant__ ConcatMaps maps, const T* __restrict__ x,
                                                                    const float* __restrict__ agate, const float* __restrict__ bias,
-                                                                   const float* __restrict__ beta, T* __restrict__ out, int C, int S, int pyramid_multiply) {
+                                                                   const float* __restrict__ beta, T* __restrict__ out, int C, int S, int pyramid_multiply,
+                                                                   const ConcatBwd bw) {
     extern __shared__ __align__(1024) unsigned char ccsm_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ccsm_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kCcStages * kCcStageBytes);
@@ -169,7 +262,7 @@ __global__ void __launch_bounds__(kCcThreads, 1) concat_fwd_kernel(const __grid_
                 mbar_wait(&empty[st], ph ^ 1);
                 unsigned char* sa = smem + st * kCcStageBytes;
                 mbar_expect_tx(&full[st], kCcStageBytes);
-                tma_load_2d(sa, &maps.wa, kb * kCcBK, b * C + m0, &full[st]);
+                tma_load_2d(sa, &maps.wa, kb * kCcBK, MODE == 0 ? b * C + m0 : m0, &full[st]);
                 tma_load_2d(sa + kCcBM * kCcBK * 2, &maps.wb, kb * kCcBK, m0, &full[st]);
                 unsigned char* sb = sa + 2 * kCcBM * kCcBK * 2;
                 tma_load_2d(sb, &maps.x, p0, b * C + kb * kCcBK, &full[st]);
@@ -206,7 +299,11 @@ __global__ void __launch_bounds__(kCcThreads, 1) concat_fwd_kernel(const __grid_
         concat_stage_gate(a_sm, agate, b, p0, S);
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        concat_epilogue_tile<T>(tmem_base, warp, lane, x, a_sm, bias, out, b, m0, p0, C, S, pyramid_multiply ? 0.0f : 1.0f - alpha, alpha);
+        if constexpr (MODE == 0)
+            concat_epilogue_tile<T>(tmem_base, warp, lane, x, a_sm, bias, out, b, m0, p0, C, S, pyramid_multiply ? 0.0f : 1.0f - alpha, alpha);
+        else
+            concat_epilogue_bwd_tile<T>(tmem_base, warp, lane, x, a_sm, bias, out, bw, b, m0, p0, C, S, pyramid_multiply ? 0.0f : 1.0f - alpha, alpha,
+                                        pyramid_multiply);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
@@ -222,11 +319,11 @@ __global__ void __launch_bounds__(kCcThreads, 1) concat_fwd_kernel(const __grid_
 constexpr int kCcResStageBytes = kCcBK * kCcBN * 2;  // one feature k-block
 __host__ __device__ inline int concat_res_smem(int C) { return (C / kCcBK) * 2 * kCcBM * kCcBK * 2 + kCcStages * kCcResStageBytes + 1024 + 256 + 2 * kCcBN * 4; }
 
-template <typename T>
+template <typename T, int MODE = 0>
 __global__ void __launch_bounds__(kCcThreads, 1) concat_fwd_res_kernel(const __grid_constant__ ConcatMaps maps, const T* __restrict__ x,
                                                                        const float* __restrict__ agate, const float* __restrict__ bias,
                                                                        const float* __restrict__ beta, T* __restrict__ out, int B, int C, int S,
-                                                                       int tiles_per_item, int pyramid_multiply) {
+                                                                       int tiles_per_item, int pyramid_multiply, const ConcatBwd bw) {
     extern __shared__ __align__(1024) unsigned char ccsm_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ccsm_raw) + 1023) & ~(uintptr_t)1023);
     const int nkb = C / kCcBK;
@@ -273,7 +370,7 @@ __global__ void __launch_bounds__(kCcThreads, 1) concat_fwd_res_kernel(const __g
                 mbar_wait(wempty, (nit & 1) ^ 1);  // the previous item's MMAs have finished reading the weights
                 mbar_expect_tx(wfull, (uint32_t)(nkb * 2 * kCcBM * kCcBK * 2));
                 for (int kb = 0; kb < nkb; ++kb) {
-                    tma_load_2d(wsm + kb * 2 * kCcBM * kCcBK * 2, &maps.wa, kb * kCcBK, b * C + m0, wfull);
+                    tma_load_2d(wsm + kb * 2 * kCcBM * kCcBK * 2, &maps.wa, kb * kCcBK, MODE == 0 ? b * C + m0 : m0, wfull);
                     tma_load_2d(wsm + kb * 2 * kCcBM * kCcBK * 2 + kCcBM * kCcBK * 2, &maps.wb, kb * kCcBK, m0, wfull);
                 }
                 for (int t = t0; t < t1; ++t)
@@ -335,7 +432,11 @@ __global__ void __launch_bounds__(kCcThreads, 1) concat_fwd_res_kernel(const __g
                 concat_stage_gate(a_sm + buf * kCcBN, agate, b, t * kCcBN, S);  // (its previous reader, tile tt - 2, is two barriers back)
                 mbar_wait(&tfull[buf], (tt >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                concat_epilogue_tile<T>(tmem_base + buf * 2 * kCcBN, warp, lane, x, a_sm + buf * kCcBN, bias, out, b, mt * kCcBM, t * kCcBN, C, S, k0, alpha);
+                if constexpr (MODE == 0)
+                    concat_epilogue_tile<T>(tmem_base + buf * 2 * kCcBN, warp, lane, x, a_sm + buf * kCcBN, bias, out, b, mt * kCcBM, t * kCcBN, C, S, k0, alpha);
+                else
+                    concat_epilogue_bwd_tile<T>(tmem_base + buf * 2 * kCcBN, warp, lane, x, a_sm + buf * kCcBN, bias, out, bw, b, mt * kCcBM, t * kCcBN, C,
+                                                S, k0, alpha, pyramid_multiply);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[buf])) : "memory");

@@ -788,6 +788,10 @@ static int backward_t(const Shape& sh, const mga_cbam_desc* d, const void* x, co
 
 // ------------------------------------------------------------------ fused concat forward (cbam_concat.cuh)
 static bool concat_map(CUtensorMap* out, const void* base, CUtensorMapDataType dt, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
+    // The driver entry point needs a current context on the CALLING thread.  A thread that has made no runtime call yet (autograd's
+    // backward thread when every allocation came from the caching allocator) has none: bind the primary context first.
+    static thread_local bool bound = false;
+    if (!bound) { cudaFree(nullptr); bound = true; }
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) || (inner * 2) % 16) return false;
     const cuuint64_t dims[2] = {inner, rows};
@@ -796,6 +800,49 @@ static bool concat_map(CUtensorMap* out, const void* base, CUtensorMapDataType d
     const cuuint32_t estr[2] = {1, 1};
     return enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// launch of the GEMM kernel pair (MODE 0: forward, 1: backward): resident-weight persistent kernel for C <= 256, streaming kernel otherwise
+template <typename T, int MODE>
+static int concat_launch(const mga_cbam_desc* d, const ConcatMaps& maps, const T* epi_feat, const float* a, const float* bias, const float* beta,
+                         T* out, const ConcatBwd& bw, cudaStream_t st, const char* what) {
+    const int B = d->B, C = d->C, S = d->H * d->W;
+    const int pm = (d->flags & MGA_PYRAMID_MULTIPLY) ? 1 : 0;
+    static thread_local int configured_dev[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool done = false;
+    for (int v : configured_dev) done |= (v == dev);
+    if (!done) {
+        if (cudaFuncSetAttribute(concat_fwd_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCcSmemBytes) != cudaSuccess)
+            return fail(MGA_ERR_CUDA, "%s: cudaFuncSetAttribute", what);
+        for (int& v : configured_dev)
+            if (v < 0) { v = dev; break; }
+    }
+    static const int use_res = env_int("MGA_CONCAT_RES", 1);
+    if (use_res && concat_res_smem(C) <= kSmemLimit) {  // C <= 256: resident weights, persistent CTAs, double-buffered accumulators
+        static thread_local int res_dev[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+        bool rdone = false;
+        for (int v : res_dev) rdone |= (v == dev);
+        if (!rdone) {
+            if (cudaFuncSetAttribute(concat_fwd_res_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess)
+                return fail(MGA_ERR_CUDA, "%s: cudaFuncSetAttribute", what);
+            for (int& v : res_dev)
+                if (v < 0) { v = dev; break; }
+        }
+        const int nTilesN = (S + kCcBN - 1) / kCcBN, nMt = C / kCcBM;
+        // pixel tiles per item: the fewest items that still give every SM >= ~4 of them (weights are reloaded per item)
+        int chunks = 1;
+        while (chunks < nTilesN && (long)B * nMt * chunks < 4L * kSMs) ++chunks;
+        const int tpi = (nTilesN + chunks - 1) / chunks;
+        const int items = B * nMt * ((nTilesN + tpi - 1) / tpi);
+        MGA_LAUNCH(MODE == 0 ? "concat_fwd" : "concat_bwd_dx", st, (concat_fwd_res_kernel<T, MODE><<<std::min(items, kSMs), kCcThreads, concat_res_smem(C), st>>>(
+            maps, epi_feat, a, bias, beta, out, B, C, S, tpi, pm, bw)));
+        return check_launch(what);
+    }
+    const dim3 grid((S + kCcBN - 1) / kCcBN, C / kCcBM, B);
+    MGA_LAUNCH(MODE == 0 ? "concat_fwd" : "concat_bwd_dx", st, (concat_fwd_kernel<T, MODE><<<grid, kCcThreads, kCcSmemBytes, st>>>(maps, epi_feat, a, bias, beta, out, C, S, pm, bw)));
+    return check_launch(what);
 }
 
 template <typename T>
@@ -810,42 +857,27 @@ static int concat_forward_t(const mga_cbam_desc* d, const void* x, const float* 
         !concat_map(&maps.x, x, dt, S, (uint64_t)B * C, 64, kCcBK))
         return fail(MGA_ERR_UNSUPPORTED, "mga_cbam_concat_forward: tensor maps (16-byte aligned pointers, H*W %% 8 == 0)");
     MGA_LAUNCH("concat_fold", st, (concat_fold_kernel<T><<<dim3((C + kWarpsPerBlock - 1) / kWarpsPerBlock, B + 1), kBlock, 0, st>>>(w, s, wa, wb, B, C)));
-    static thread_local int configured_dev[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    bool done = false;
-    for (int v : configured_dev) done |= (v == dev);
-    if (!done) {
-        if (cudaFuncSetAttribute(concat_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCcSmemBytes) != cudaSuccess)
-            return fail(MGA_ERR_CUDA, "mga_cbam_concat_forward: cudaFuncSetAttribute");
-        for (int& v : configured_dev)
-            if (v < 0) { v = dev; break; }
-    }
-    static const int use_res = env_int("MGA_CONCAT_RES", 1);
-    if (use_res && concat_res_smem(C) <= kSmemLimit) {  // C <= 256: resident weights, persistent CTAs, double-buffered accumulators
-        static thread_local int res_dev[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
-        bool rdone = false;
-        for (int v : res_dev) rdone |= (v == dev);
-        if (!rdone) {
-            if (cudaFuncSetAttribute(concat_fwd_res_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess)
-                return fail(MGA_ERR_CUDA, "mga_cbam_concat_forward: cudaFuncSetAttribute");
-            for (int& v : res_dev)
-                if (v < 0) { v = dev; break; }
-        }
-        const int nTilesN = (S + kCcBN - 1) / kCcBN, nMt = C / kCcBM;
-        // pixel tiles per item: the fewest items that still give every SM >= ~4 of them (weights are reloaded per item)
-        int chunks = 1;
-        while (chunks < nTilesN && (long)B * nMt * chunks < 4L * kSMs) ++chunks;
-        const int tpi = (nTilesN + chunks - 1) / chunks;
-        const int items = B * nMt * ((nTilesN + tpi - 1) / tpi);
-        MGA_LAUNCH("concat_fwd", st, (concat_fwd_res_kernel<T><<<std::min(items, kSMs), kCcThreads, concat_res_smem(C), st>>>(
-            maps, static_cast<const T*>(x), a, bias, beta, static_cast<T*>(out), B, C, S, tpi, (d->flags & MGA_PYRAMID_MULTIPLY) ? 1 : 0)));
-        return check_launch("mga_cbam_concat_forward(resident)");
-    }
-    const dim3 grid((S + kCcBN - 1) / kCcBN, C / kCcBM, B);
-    MGA_LAUNCH("concat_fwd", st, (concat_fwd_kernel<T><<<grid, kCcThreads, kCcSmemBytes, st>>>(maps, static_cast<const T*>(x), a, bias, beta, static_cast<T*>(out), C, S,
-                                                                                             (d->flags & MGA_PYRAMID_MULTIPLY) ? 1 : 0)));
-    return check_launch("mga_cbam_concat_forward");
+    return concat_launch<T, 0>(d, maps, static_cast<const T*>(x), a, bias, beta, static_cast<T*>(out), ConcatBwd{}, st, "mga_cbam_concat_forward");
+}
+
+// backward: U = Wa^T g, V = Wb^T g on the tensor cores, the rest of the closed form in the epilogue (cbam_concat.cuh, MODE 1)
+template <typename T>
+static int concat_backward_dx_t(const mga_cbam_desc* d, const void* x, const void* g, const float* s, const float* a, const float* w, const float* bias,
+                                const float* beta, void* dx, void* ga, float* ds_part, float* db_part, float* da_part, float* dal_part, void* wscratch,
+                                cudaStream_t st) {
+    const int B = d->B, C = d->C, S = d->H * d->W;
+    T* wat = static_cast<T*>(wscratch);
+    T* wbt = wat + (size_t)C * C;
+    const CUtensorMapDataType dt = std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    ConcatMaps maps;
+    const bool m1 = concat_map(&maps.wa, wat, dt, C, C, kCcBK, kCcBM), m2 = concat_map(&maps.wb, wbt, dt, C, C, kCcBK, kCcBM),
+               m3 = concat_map(&maps.x, g, dt, S, (uint64_t)B * C, 64, kCcBK);
+    if (!m1 || !m2 || !m3)
+        return fail(MGA_ERR_UNSUPPORTED, "mga_cbam_concat_backward_dx: tensor maps (16-byte aligned pointers, H*W %% 8 == 0) [wa %d wb %d g %d; g=%p ws=%p]",
+                    (int)m1, (int)m2, (int)m3, g, wscratch);
+    MGA_LAUNCH("concat_transpose", st, (concat_transpose_kernel<T><<<(C * C + kBlock - 1) / kBlock, kBlock, 0, st>>>(w, wat, wbt, C)));
+    const ConcatBwd bw{x, s, ga, ds_part, db_part, da_part, dal_part};
+    return concat_launch<T, 1>(d, maps, static_cast<const T*>(g), a, bias, beta, static_cast<T*>(dx), bw, st, "mga_cbam_concat_backward_dx");
 }
 
 }  // namespace mga
@@ -1050,6 +1082,22 @@ int mga_cbam_concat_backward_elem(const mga_cbam_desc* d, const void* x, const v
             static_cast<T*>(grad_x), static_cast<T*>(ga), ds_part, dbias_part, grad_a, dalpha_part, d->C, S, pm)));
     }
     return check_launch("mga_cbam_concat_backward_elem");
+}
+
+int mga_cbam_concat_backward_dx(const mga_cbam_desc* d, const void* x, const void* grad_out, const float* s, const float* a, const float* w,
+                                const float* bias, const float* beta, void* grad_x, void* ga, float* ds_part, float* dbias_part, float* da_part,
+                                float* dalpha_part, void* wscratch, void* stream) {
+    if (!d || !x || !grad_out || !s || !a || !w || !bias || !beta || !grad_x || !ga || !ds_part || !dbias_part || !da_part || !dalpha_part || !wscratch)
+        return fail(MGA_ERR_ARG, "null pointer argument");
+    if (d->B <= 0 || d->C <= 0 || d->H <= 0 || d->W <= 0 || d->B > 65535) return fail(MGA_ERR_ARG, "bad shape");
+    if (d->dtype != MGA_BF16 && d->dtype != MGA_F16) return fail(MGA_ERR_UNSUPPORTED, "the tensor-core concat backward takes bf16 / f16 features");
+    if (d->C % kCcBM || (d->H * d->W) % 8) return fail(MGA_ERR_UNSUPPORTED, "needs C %% 128 == 0 and H*W %% 8 == 0");
+    for (const void* p : {x, grad_out, (const void*)grad_x, (const void*)ga, (const void*)a, (const void*)wscratch})
+        if (reinterpret_cast<uintptr_t>(p) & 15) return fail(MGA_ERR_UNSUPPORTED, "16-byte aligned tensors only");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d->dtype == MGA_BF16)
+        return concat_backward_dx_t<__nv_bfloat16>(d, x, grad_out, s, a, w, bias, beta, grad_x, ga, ds_part, dbias_part, da_part, dalpha_part, wscratch, st);
+    return concat_backward_dx_t<__half>(d, x, grad_out, s, a, w, bias, beta, grad_x, ga, ds_part, dbias_part, da_part, dalpha_part, wscratch, st);
 }
 
 int mga_cbam_concat_wgrad_reduce(const mga_cbam_desc* d, const void* Ga, const void* Gb, int gemm_dtype, const float* s, const float* beta,

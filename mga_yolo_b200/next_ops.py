@@ -343,32 +343,49 @@ class _ConcatFn(torch.autograd.Function):
 
 
 def _concat_backward(x, s, a, w, bias, beta, gout, pyramid_multiply):
-    """Closed-form backward of cbam_concat_fwd: (dx, ds, da, dw, dbias, dbeta).  GEMMs from the library (U|V = [Wa^T ; Wb^T] g and the two
-    per-sample weight-gradient products, fp32 results), everything else in two kernels of this library."""
+    """Closed-form backward of cbam_concat_fwd: (dx, ds, da, dw, dbias, dbeta).
+    Default: ONE tcgen05 kernel (mga_cbam_concat_backward_dx: U = Wa^T g and V = Wb^T g as its two accumulators, the elementwise /
+    reduction part of the closed form in its epilogue), two per-sample library GEMMs (g X^T, (g a) X^T) and ONE batch-reduce kernel for
+    the weight gradient.  MGA_CONCAT_BWD_LIBRARY=1 keeps the round-2a form (U|V by a library GEMM + mga_cbam_concat_backward_elem)."""
+    import os
+
     lib = _lib.load()
     B, Cc, H, W = x.shape
     S = H * W
     dt = x.dtype
     x = x.contiguous()
     g = gout.contiguous().to(dt)
-    w2 = w.reshape(Cc, 2 * Cc)
-    wcat_t = torch.cat([w2[:, :Cc].t(), w2[:, Cc:].t()], dim=0).to(dt).contiguous()      # (2C, C): [Wa^T ; Wb^T]
-    uv = torch.matmul(wcat_t, g.reshape(B, Cc, S))                                         # (B, 2C, S), one library GEMM
+    w2 = _f32c(w.reshape(Cc, 2 * Cc))
     sf, af, bf, btf = _f32c(s), _f32c(a), _f32c(bias), _f32c(beta)
-    nT = (S // 8 + 31) // 32
     d = _lib.Desc(B, Cc, H, W, 1, 1, _DT[dt], _lib.F32, _lib.PYRAMID_MULTIPLY if pyramid_multiply else 0, 0.0, 0.0)
     with torch.cuda.device(x.device):
         dx = torch.empty_like(x)
         ga = torch.empty_like(x)
-        ds_part = torch.empty((B, nT, Cc), dtype=torch.float32, device=x.device)
-        db_part = torch.empty((B, nT, Cc), dtype=torch.float32, device=x.device)
-        da = torch.empty((B, S), dtype=torch.float32, device=x.device)
-        dal_part = torch.empty((B, nT), dtype=torch.float32, device=x.device)
-        rc = lib.mga_cbam_concat_backward_elem(C.byref(d), x.data_ptr(), g.data_ptr(), uv.data_ptr(), sf.data_ptr(), af.data_ptr(), bf.data_ptr(),
-                                               btf.data_ptr(), dx.data_ptr(), ga.data_ptr(), ds_part.data_ptr(), db_part.data_ptr(), da.data_ptr(),
-                                               dal_part.data_ptr(), _stream(x))
-        _lib.check(rc, "mga_cbam_concat_backward_elem")
-        del uv
+        if os.getenv("MGA_CONCAT_BWD_LIBRARY", ""):
+            wcat_t = torch.cat([w2[:, :Cc].t(), w2[:, Cc:].t()], dim=0).to(dt).contiguous()  # (2C, C): [Wa^T ; Wb^T]
+            uv = torch.matmul(wcat_t, g.reshape(B, Cc, S))                                     # (B, 2C, S), one library GEMM
+            nT = (S // 8 + 31) // 32
+            ds_part = torch.empty((B, nT, Cc), dtype=torch.float32, device=x.device)
+            db_part = torch.empty((B, nT, Cc), dtype=torch.float32, device=x.device)
+            da = torch.empty((B, S), dtype=torch.float32, device=x.device)
+            dal_part = torch.empty((B, nT), dtype=torch.float32, device=x.device)
+            rc = lib.mga_cbam_concat_backward_elem(C.byref(d), x.data_ptr(), g.data_ptr(), uv.data_ptr(), sf.data_ptr(), af.data_ptr(), bf.data_ptr(),
+                                                   btf.data_ptr(), dx.data_ptr(), ga.data_ptr(), ds_part.data_ptr(), db_part.data_ptr(),
+                                                   da.data_ptr(), dal_part.data_ptr(), _stream(x))
+            _lib.check(rc, "mga_cbam_concat_backward_elem")
+            del uv
+        else:
+            nT = (S + 127) // 128
+            ds_part = torch.empty((B, 2 * nT, Cc), dtype=torch.float32, device=x.device)
+            db_part = torch.empty((B, 2 * nT, Cc), dtype=torch.float32, device=x.device)
+            da_part = torch.empty((B, Cc // 32, S), dtype=torch.float32, device=x.device)
+            dal_part = torch.empty((B, nT, Cc // 16), dtype=torch.float32, device=x.device)
+            ws = torch.empty(2 * Cc * Cc, dtype=dt, device=x.device)
+            rc = lib.mga_cbam_concat_backward_dx(C.byref(d), x.data_ptr(), g.data_ptr(), sf.data_ptr(), af.data_ptr(), w2.data_ptr(), bf.data_ptr(),
+                                                 btf.data_ptr(), dx.data_ptr(), ga.data_ptr(), ds_part.data_ptr(), db_part.data_ptr(),
+                                                 da_part.data_ptr(), dal_part.data_ptr(), ws.data_ptr(), _stream(x))
+            _lib.check(rc, "mga_cbam_concat_backward_dx")
+            da = da_part.sum(dim=1)
         # weight gradient: two per-sample GEMMs with fp32 results, then ONE kernel sums them over the batch (the channel gate folded in)
         xt = x.reshape(B, Cc, S).transpose(1, 2)
         Ga = torch.bmm(g.reshape(B, Cc, S), xt, out_dtype=torch.float32)                       # (B,C,C): g X^T
