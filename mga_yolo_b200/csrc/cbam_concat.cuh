@@ -142,8 +142,43 @@ struct ConcatBwd {
     float* dal_part;
 };
 
+// this thread's pieces of x and grad_out for its row and the 64 pixel columns of its half of the tile: issued BEFORE the wait for the
+// accumulators, so their latency hides behind the tile's MMAs (the first version loaded them chunk by chunk after the wait: 1284 us at
+// cfg4-P3 against 912 us, every chunk a serial round trip to L2 / HBM)
+struct ConcatBwdRegs { uint4 xr[8], gr[8]; };
 template <typename T>
-__device__ __forceinline__ void concat_epilogue_bwd_tile(uint32_t tacc, int warp, int lane, const T* __restrict__ g, const float* a_sm,
+__device__ __forceinline__ void concat_epilogue_bwd_prefetch(ConcatBwdRegs& r, int warp, int lane, const T* __restrict__ g, const ConcatBwd& bw, int b,
+                                                             int m0, int p0, int C, int S) {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const size_t rowoff = ((size_t)b * C + m0 + q * 32 + lane) * S;
+    const T* __restrict__ xf = static_cast<const T*>(bw.x);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int p = p0 + half * 64 + k * 8;
+        if (p < S) {  // (S % 8 == 0: whole 16-byte pieces; warp-uniform)
+            r.xr[k] = __ldg(reinterpret_cast<const uint4*>(xf + rowoff + p));
+            r.gr[k] = __ldg(reinterpret_cast<const uint4*>(g + rowoff + p));
+        }
+    }
+}
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4& t, float (&v)[8]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        } else {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            v[2 * i] = f.x;
+            v[2 * i + 1] = f.y;
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void concat_epilogue_bwd_tile(uint32_t tacc, const ConcatBwdRegs& r, int warp, int lane, const float* a_sm,
                                                          const float* __restrict__ bias, T* __restrict__ dx, const ConcatBwd& bw, int b, int m0,
                                                          int p0, int C, int S, float k0, float alpha, int pyramid_multiply) {
     const int q = warp & 3, half = (warp - 2) >> 2;
@@ -151,13 +186,13 @@ __device__ __forceinline__ void concat_epilogue_bwd_tile(uint32_t tacc, int warp
     const float sc = __ldg(bw.s + (size_t)b * C + c);
     const uint32_t trow = tacc + ((uint32_t)(q * 32) << 16);
     const size_t rowoff = ((size_t)b * C + c) * S;
-    const T* __restrict__ xf = static_cast<const T*>(bw.x);
     T* __restrict__ gaf = static_cast<T*>(bw.ga);
     float* __restrict__ dap = bw.da_part + ((size_t)b * (C / 32) + (m0 / 32 + q)) * S;
     const int nTilesN = (S + kCcBN - 1) / kCcBN;
     float su = 0.0f, sg = 0.0f, dal = 0.0f;
-#pragma unroll 1
-    for (int c16 = half * 4; c16 < half * 4 + 4; ++c16) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c16 = half * 4 + cc;
         const int p = p0 + c16 * 16;
         uint32_t y1[16], y2[16];
         tmem_ld16(trow + c16 * 16, y1);
@@ -167,13 +202,13 @@ __device__ __forceinline__ void concat_epilogue_bwd_tile(uint32_t tacc, int warp
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int ph8 = p + h * 8;
-            if (ph8 >= S) break;  // (S % 8 == 0: whole 16-byte pieces; warp-uniform)
+            if (ph8 >= S) break;
             const float4 a0 = *reinterpret_cast<const float4*>(a_sm + c16 * 16 + h * 8);
             const float4 a1 = *reinterpret_cast<const float4*>(a_sm + c16 * 16 + h * 8 + 4);
             const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             float xv[8], gv[8], ov[8], gav[8], va[8];
-            ldv<T, 8, kLdStream>(xf + rowoff + ph8, xv);
-            ldv<T, 8, kLdStream>(g + rowoff + ph8, gv);
+            unpack8<T>(r.xr[cc * 2 + h], xv);
+            unpack8<T>(r.gr[cc * 2 + h], gv);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float U = __uint_as_float(y1[h * 8 + i]), V = __uint_as_float(y2[h * 8 + i]);
@@ -188,13 +223,31 @@ __device__ __forceinline__ void concat_epilogue_bwd_tile(uint32_t tacc, int warp
             }
             stv<T, 8, true>(dx + rowoff + ph8, ov);
             stv<T, 8, true>(gaf + rowoff + ph8, gav);
-            float keep = 0.0f;
+            // per-pixel sum over the warp's 32 channel rows: transposing butterfly (9 shuffles for 8 columns), lane l ends with column (l >> 2) & 7
+            {
+                const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
+                float w4[4], w2[2], w1;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float r = warp_sum(va[i]);
-                if (lane == i) keep = r;
+                for (int i = 0; i < 4; ++i) {  // lanes with bit 4 keep columns 4..7, the others 0..3
+                    const float send = hi16 ? va[i] : va[4 + i];
+                    const float got = __shfl_xor_sync(0xffffffffu, send, 16);
+                    w4[i] = (hi16 ? va[4 + i] : va[i]) + got;
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {  // bit 3: columns +2, +3 of the kept four
+                    const float send = hi8 ? w4[i] : w4[2 + i];
+                    const float got = __shfl_xor_sync(0xffffffffu, send, 8);
+                    w2[i] = (hi8 ? w4[2 + i] : w4[i]) + got;
+                }
+                {
+                    const float send = hi4 ? w2[0] : w2[1];
+                    const float got = __shfl_xor_sync(0xffffffffu, send, 4);
+                    w1 = (hi4 ? w2[1] : w2[0]) + got;
+                }
+                w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+                w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+                if ((lane & 3) == 0) dap[ph8 + (hi16 ? 4 : 0) + (hi8 ? 2 : 0) + (hi4 ? 1 : 0)] = alpha * w1;
             }
-            if (lane < 8) dap[ph8 + lane] = alpha * keep;
         }
     }
     const size_t pi = ((size_t)b * (2 * nTilesN) + (size_t)(p0 / kCcBN) * 2 + half) * C + c;
@@ -297,12 +350,14 @@ __global__ void __launch_bounds__(kCcThreads, 1) concat_fwd_kernel(const __grid_
         // ---- epilogue
         const float alpha = softplusf_acc(__ldg(beta));
         concat_stage_gate(a_sm, agate, b, p0, S);
+        [[maybe_unused]] ConcatBwdRegs pre;
+        if constexpr (MODE == 1) concat_epilogue_bwd_prefetch<T>(pre, warp, lane, x, bw, b, m0, p0, C, S);
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if constexpr (MODE == 0)
             concat_epilogue_tile<T>(tmem_base, warp, lane, x, a_sm, bias, out, b, m0, p0, C, S, pyramid_multiply ? 0.0f : 1.0f - alpha, alpha);
         else
-            concat_epilogue_bwd_tile<T>(tmem_base, warp, lane, x, a_sm, bias, out, bw, b, m0, p0, C, S, pyramid_multiply ? 0.0f : 1.0f - alpha, alpha,
+            concat_epilogue_bwd_tile<T>(tmem_base, pre, warp, lane, a_sm, bias, out, bw, b, m0, p0, C, S, pyramid_multiply ? 0.0f : 1.0f - alpha, alpha,
                                         pyramid_multiply);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -430,12 +485,14 @@ __global__ void __launch_bounds__(kCcThreads, 1) concat_fwd_res_kernel(const __g
             for (int t = t0; t < t1; ++t, ++tt) {
                 const int buf = tt & 1;
                 concat_stage_gate(a_sm + buf * kCcBN, agate, b, t * kCcBN, S);  // (its previous reader, tile tt - 2, is two barriers back)
+                [[maybe_unused]] ConcatBwdRegs pre;
+                if constexpr (MODE == 1) concat_epilogue_bwd_prefetch<T>(pre, warp, lane, x, bw, b, mt * kCcBM, t * kCcBN, C, S);
                 mbar_wait(&tfull[buf], (tt >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if constexpr (MODE == 0)
                     concat_epilogue_tile<T>(tmem_base + buf * 2 * kCcBN, warp, lane, x, a_sm + buf * kCcBN, bias, out, b, mt * kCcBM, t * kCcBN, C, S, k0, alpha);
                 else
-                    concat_epilogue_bwd_tile<T>(tmem_base + buf * 2 * kCcBN, warp, lane, x, a_sm + buf * kCcBN, bias, out, bw, b, mt * kCcBM, t * kCcBN, C,
+                    concat_epilogue_bwd_tile<T>(tmem_base + buf * 2 * kCcBN, pre, warp, lane, a_sm + buf * kCcBN, bias, out, bw, b, mt * kCcBM, t * kCcBN, C,
                                                 S, k0, alpha, pyramid_multiply);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();

@@ -346,7 +346,7 @@ def _concat_backward(x, s, a, w, bias, beta, gout, pyramid_multiply):
     """Closed-form backward of cbam_concat_fwd: (dx, ds, da, dw, dbias, dbeta).
     Default: ONE tcgen05 kernel (mga_cbam_concat_backward_dx: U = Wa^T g and V = Wb^T g as its two accumulators, the elementwise /
     reduction part of the closed form in its epilogue), two per-sample library GEMMs (g X^T, (g a) X^T) and ONE batch-reduce kernel for
-    the weight gradient.  MGA_CONCAT_BWD_LIBRARY=1 keeps the round-2a form (U|V by a library GEMM + mga_cbam_concat_backward_elem)."""
+    the weight gradient; narrow levels (C <= 256) take U|V from a library GEMM + mga_cbam_concat_backward_elem (see the dispatch note)."""
     import os
 
     lib = _lib.load()
@@ -361,7 +361,11 @@ def _concat_backward(x, s, a, w, bias, beta, gout, pyramid_multiply):
     with torch.cuda.device(x.device):
         dx = torch.empty_like(x)
         ga = torch.empty_like(x)
-        if os.getenv("MGA_CONCAT_BWD_LIBRARY", ""):
+        # Measured on B200 (cfg4, B = 128 bf16, tools/concat_bwd_prof.py): the tcgen05 backward beats library GEMM + elementwise kernel for
+        # C > 256 (512x40x40: 474 vs 522 us, 512x20x20: 134 vs 164 us); at C <= 256 its row-per-lane epilogue (4 global accesses per 16 B of
+        # accumulator row) is the bound (256x80x80: 912 vs 766 us), so that width keeps the library form.  MGA_CONCAT_BWD = tc | library forces one.
+        force = os.getenv("MGA_CONCAT_BWD", "")
+        if force == "library" or (force != "tc" and Cc <= 256):
             wcat_t = torch.cat([w2[:, :Cc].t(), w2[:, Cc:].t()], dim=0).to(dt).contiguous()  # (2C, C): [Wa^T ; Wb^T]
             uv = torch.matmul(wcat_t, g.reshape(B, Cc, S))                                     # (B, 2C, S), one library GEMM
             nT = (S // 8 + 31) // 32

@@ -205,7 +205,8 @@ def test_collate_matches_reference_rule():
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape,pyr", [((2, 128, 20, 20), "multiply"), ((2, 256, 16, 24), "add"), ((1, 128, 80, 80), "multiply"), ((3, 256, 40, 40), "add"),
                                        ((2, 256, 80, 80), "multiply"), ((2, 512, 40, 40), "multiply"), ((2, 512, 20, 20), "multiply")])  # BASELINE configs[3] levels
-def test_concat_fused_forward_and_backward_match_the_library_composition(shape, pyr, dtype, monkeypatch):
+@pytest.mark.parametrize("bwd", ["tc", "library"])  # backward: tcgen05 kernel (mga_cbam_concat_backward_dx) / library GEMM + elementwise kernel
+def test_concat_fused_forward_and_backward_match_the_library_composition(shape, pyr, dtype, bwd, monkeypatch):
     """The fused forward (csrc/cbam_concat.cuh: TMA + tcgen05.mma + TMEM epilogue) and its closed-form backward against the same module
     run as gates op + torch.cat + F.conv2d + autograd (MGA_CONCAT_LIBRARY=1) and against the in-repo fp64 oracle.
     Both modes are build-side definitions: 'oracle: in-repo PyTorch composition; reference parity unpinned'."""
@@ -214,6 +215,7 @@ def test_concat_fused_forward_and_backward_match_the_library_composition(shape, 
     from tests._golden import PARAM_KEYS
 
     B, C, H, W = shape
+    monkeypatch.setenv("MGA_CONCAT_BWD", bwd)
     gen = torch.Generator().manual_seed(C + H)
     x = (torch.randn(B, C, H, W, generator=gen) * 0.5).to(dtype)
     mask = torch.randn(B, 1, H, W, generator=gen)
