@@ -677,7 +677,7 @@ def concat_workload(dev, peak, bf16_peak_tflops):
             "value": round(ab / (ms * 1e-3) / 1e9, 1), "unit": "GB/s", "step_frac": round(ab / (ms * 1e-3) / 1e9 / peak, 4),
             "images_per_sec": round(B / (ms * 1e-3), 1), "gemm_tflops": round(flops / (ms * 1e-3) / 1e12, 1),
             "gemm_frac_of_bf16_sustained": None if not bf16_peak_tflops else round(flops / (ms * 1e-3) / 1e12 / bf16_peak_tflops, 4),
-            "path": "forward: gates op + fold + ONE tcgen05 kernel (TMA, TMEM accumulators, fused epilogue); backward: 3 library GEMMs + 1 elementwise/reduction kernel + gates backward",
+            "path": "forward: gates op + fold + ONE tcgen05 kernel (TMA, TMEM accumulators, fused epilogue); backward: levels with C > 256 = ONE tcgen05 kernel (U, V in TMEM, closed form in the epilogue), C <= 256 = library GEMM + elementwise kernel; weight gradient = 2 per-sample library GEMMs (fp32) + 1 batch-reduce kernel; gates backward accumulates the concat dx (one autograd node)",
             "library_composition": {"ms_per_step": round(ms_lib, 4), "note": "same module as gates op + torch.cat + F.conv2d (cuDNN) + autograd (MGA_CONCAT_LIBRARY=1)"},
             "note": "oracle: in-repo PyTorch composition; reference parity unpinned"}
 

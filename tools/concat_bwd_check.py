@@ -1,9 +1,12 @@
+"""Direct C-ABI check of mga_cbam_concat_backward_dx (tcgen05 backward of the concat mode) against a torch composition; then the same
+through the nn.Module on autograd's thread.  usage: python tools/concat_bwd_check.py [512]  (512: one cfg4-P4-shaped call, the ncu target)"""
 import ctypes as C, torch, sys
 sys.path.insert(0, ".")
 from mga_yolo_b200 import _lib
 lib = _lib.load()
 dev = torch.device("cuda:0")
-for (B, Cc, H, W) in [(2, 128, 20, 20), (2, 256, 16, 24), (128, 256, 80, 80)]:
+SHAPES = [(32, 512, 40, 40)] if len(sys.argv) > 1 and sys.argv[1] == "512" else [(2, 128, 20, 20), (2, 256, 16, 24), (128, 256, 80, 80)]
+for (B, Cc, H, W) in SHAPES:
     S = H * W
     dt = torch.bfloat16
     x = torch.randn(B, Cc, H, W, device=dev).to(dt); g = torch.randn_like(x)
