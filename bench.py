@@ -895,28 +895,27 @@ def mask_pipeline(dev, B, imgsz, peak):
         return e0.elapsed_time(e1) / reps
 
     def timed_graph(fn, reps=30):
-        """The same call captured in one CUDA graph per input buffer and replayed round robin: the kernels' time without the ~35 us of
-        Python / dispatcher / allocator work per op call that bounds the eager loop at this size."""
-        graphs = []
+        """The same call on the 6 rotating batches captured in ONE CUDA graph (a dataloader processes batch after batch) and replayed: the
+        kernels' time without the ~35 us of Python / dispatcher / allocator work per op call that bounds the eager loop at this size, and
+        without one graph launch per 20-microsecond call."""
         for m in bufs:
             fn(m)
         torch.cuda.synchronize(dev)
         keep = []
-        for m in bufs:
-            gph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gph):
+        gph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gph):
+            for m in bufs:
                 keep.append(fn(m))
-            graphs.append(gph)
-        for gph in graphs[:3]:
+        for _ in range(3):
             gph.replay()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(reps):
-            graphs[i % nbuf].replay()
+            gph.replay()
         e1.record()
         torch.cuda.synchronize(dev)
-        return e0.elapsed_time(e1) / reps
+        return e0.elapsed_time(e1) / (reps * nbuf)
 
     ms_one_eager = timed(lambda m: MaskUtils.masks_multi(m))
     ms_per = timed(lambda m: [MaskUtils.downsample_mask(m, s) for s in (8, 16, 32)])
@@ -945,8 +944,9 @@ def mask_pipeline(dev, B, imgsz, peak):
             "masks_per_sec": round(B / (ms_one * 1e-3), 1),
             "roofline": {"bound": "hbm", "achieved": round(alg / (ms_one * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(alg / (ms_one * 1e-3) / 1e9 / peak, 4), "alg_bytes_per_launch": alg,
-                         "note": "two stages (mga_masks_multi_ws): one thread per 8x8 block over the whole batch reads the masks, then one CTA per (image, stride); "
-                                 "CUDA-graph replay over 6 rotating batches (the eager op call is bounded by ~35 us of host work)"},
+                         "note": "two stages (mga_masks_multi_ws): one thread per 8x8 block over the whole batch reads the masks, then one CTA per (8-row band, "
+                                 "image, stride) derives the maps + 3x3 close; 6 rotating batches captured in one CUDA graph, replayed (the eager op call is "
+                                 "bounded by ~35 us of host work)"},
             "cpu_baseline": {"masks_per_sec": round(1.0 / cpu_s, 1), "cores": 1, "kind": kind,
                              "sample": "8 masks x 3 strides, " + ("the reference's MaskUtils.downsample_mask (cv2) from oracle/_ref" if kind == "reference"
                                                                   else "oracle/mask_oracle.py (numpy restatement of cv2.resize / morphologyEx)")}}

@@ -264,6 +264,85 @@ __global__ void __launch_bounds__(kMultiThreads) masks_multi_kernel(const uint8_
     }
 }
 
+
+// Stage 2 of the two-stage form, banded: grid (row bands, B, 3 strides), one CTA = kBandRows output rows of ONE stride of ONE image.
+// The raw map of the band plus a 2-row halo comes from the stage-1 block counts (L2 hits: 6.4 KB per image at 640x640), the 3x3 close
+// (dilate rows [r0-1, r1+1), erode rows [r0, r1); neighbours outside the MAP are ignored, exactly as in masks_multi_kernel) runs in
+// shared memory.  64 images x (10 + 5 + 3) bands = 1152 CTAs instead of 192: the stage is no longer one latency chain per image.
+constexpr int kBandRows = 8, kBandThreads = 256;
+__device__ __forceinline__ void multi_raw(int c, uint8_t tl, int s2, const MultiArgs& a, uint8_t* u, float* f) {
+    if (a.method == MGA_DS_NEAREST) { *u = tl; *f = (float)tl; }
+    else if (a.method == MGA_DS_MAXPOOL) { *u = (uint8_t)(c > 0); *f = (float)*u; }
+    else if (a.method == MGA_DS_AVGPOOL) { *f = __fdiv_rn((float)c, (float)s2); *u = (uint8_t)(*f > 0.0f); }
+    else {
+        *u = sat_u8_rne(__fmul_rn((float)c, __fdiv_rn(1.0f, (float)s2)));
+        if (a.binarise) { *u = (uint8_t)((float)*u > a.thresh); *f = (float)*u; }
+        else *f = fminf(fmaxf((float)*u, 0.0f), 1.0f);
+    }
+}
+__global__ void __launch_bounds__(kBandThreads) masks_band_kernel(void* __restrict__ d8, void* __restrict__ d16, void* __restrict__ d32, MultiArgs a,
+                                                                 const uint8_t* __restrict__ cnt8, const uint8_t* __restrict__ tl8) {
+    extern __shared__ __align__(16) uint8_t bsm[];
+    const int lvl = blockIdx.z, b = blockIdx.y;
+    const int h8 = a.H / 8, w8 = a.W / 8, n8 = h8 * w8;
+    const int h = h8 >> lvl, w = w8 >> lvl, n = h * w;
+    const int r0 = blockIdx.x * kBandRows;
+    if (r0 >= h) return;
+    const int r1 = min(h, r0 + kBandRows);
+    const int q0 = max(0, r0 - 2), q1 = min(h, r1 + 2);  // raw rows held
+    uint8_t* raw = bsm;                                  // [(kBandRows + 4) * w]
+    uint8_t* dil = raw + (kBandRows + 4) * w;            // [(kBandRows + 2) * w]
+    const uint8_t* c8 = cnt8 + (size_t)b * n8;
+    const uint8_t* t8 = tl8 + (size_t)b * n8;
+    const int s = 8 << lvl, s2 = s * s, sub = 1 << lvl;
+    void* dst = lvl == 0 ? d8 : (lvl == 1 ? d16 : d32);
+    uint8_t* du = static_cast<uint8_t*>(dst) + (size_t)b * n;
+    float* df = static_cast<float*>(dst) + (size_t)b * n;
+    const float iw = 1.0f / (float)w;
+    for (int i = threadIdx.x; i < (q1 - q0) * w; i += kBandThreads) {
+        const int ry = (int)(((float)i + 0.5f) * iw), x = i - ry * w, y = q0 + ry;
+        int c = 0;
+        for (int dy = 0; dy < sub; ++dy)
+            for (int dx = 0; dx < sub; ++dx) c += c8[((y << lvl) + dy) * w8 + (x << lvl) + dx];
+        const uint8_t tl = t8[(y << lvl) * w8 + (x << lvl)];
+        uint8_t u;
+        float f;
+        multi_raw(c, tl, s2, a, &u, &f);
+        if (a.close3x3) raw[ry * w + x] = u;
+        else if (y >= r0 && y < r1) {
+            if (a.out_f32) df[y * w + x] = f;
+            else du[y * w + x] = u;
+        }
+    }
+    if (!a.close3x3) return;
+    __syncthreads();
+    const int e0 = max(0, r0 - 1), e1 = min(h, r1 + 1);  // dilated rows held
+    for (int i = threadIdx.x; i < (e1 - e0) * w; i += kBandThreads) {
+        const int ry = (int)(((float)i + 0.5f) * iw), x = i - ry * w, y = e0 + ry;
+        int v = 0;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int yy = y + dy, xx = x + dx;
+                if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+                v = max(v, (int)raw[(yy - q0) * w + xx]);
+            }
+        dil[ry * w + x] = (uint8_t)v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (r1 - r0) * w; i += kBandThreads) {
+        const int ry = (int)(((float)i + 0.5f) * iw), x = i - ry * w, y = r0 + ry;
+        int v = 255;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int yy = y + dy, xx = x + dx;
+                if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+                v = min(v, (int)dil[(yy - e0) * w + xx]);
+            }
+        if (a.out_f32) df[y * w + x] = (float)v;
+        else du[y * w + x] = (uint8_t)v;
+    }
+}
+
 }  // namespace mga
 
 using namespace mga;
@@ -337,7 +416,13 @@ extern "C" int mga_masks_multi_ws(const uint8_t* src, void* dst8, void* dst16, v
         const size_t total = (size_t)B * n8;
         masks_count8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, cnt8, tl8, B, H, W);
     }
-    masks_multi_kernel<<<dim3(B, cnt8 ? 3 : 1), kMultiThreads, smem, st>>>(src, dst8, dst16, dst32, a, cnt8, tl8);
+    if (cnt8) {  // stage 2, banded: (row bands of the stride-8 map, image, stride)
+        const int h8 = H / 8, w8 = W / 8;
+        const size_t bsmem = (size_t)(2 * kBandRows + 6) * w8;
+        masks_band_kernel<<<dim3((h8 + kBandRows - 1) / kBandRows, B, 3), kBandThreads, bsmem, st>>>(dst8, dst16, dst32, a, cnt8, tl8);
+    } else {
+        masks_multi_kernel<<<dim3(B, 1), kMultiThreads, smem, st>>>(src, dst8, dst16, dst32, a, nullptr, nullptr);
+    }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bad(MGA_ERR_CUDA, cudaGetErrorString(e));
     return MGA_OK;
