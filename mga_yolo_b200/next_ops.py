@@ -362,8 +362,8 @@ def _concat_backward(x, s, a, w, bias, beta, gout, pyramid_multiply):
         dx = torch.empty_like(x)
         ga = torch.empty_like(x)
         # Measured on B200 (cfg4, B = 128 bf16, tools/concat_bwd_prof.py): the tcgen05 backward beats library GEMM + elementwise kernel for
-        # C > 256 (512x40x40: 474 vs 522 us, 512x20x20: 134 vs 164 us); at C <= 256 its row-per-lane epilogue (4 global accesses per 16 B of
-        # accumulator row) is the bound (256x80x80: 912 vs 766 us), so that width keeps the library form.  MGA_CONCAT_BWD = tc | library forces one.
+        # C > 256 (512x40x40: 474 vs 522 us, 512x20x20: 134 vs 164 us); at C <= 256 the epilogue of the resident-weight kernel (8 warps, one
+        # accumulator row per lane) is the bound (256x80x80: 912 vs 766 us), so that width keeps the library form.  MGA_CONCAT_BWD = tc | library forces one.
         force = os.getenv("MGA_CONCAT_BWD", "")
         if force == "library" or (force != "tc" and Cc <= 256):
             wcat_t = torch.cat([w2[:, :Cc].t(), w2[:, Cc:].t()], dim=0).to(dt).contiguous()  # (2C, C): [Wa^T ; Wb^T]
