@@ -20,7 +20,12 @@
 namespace mga {
 
 constexpr int kCcBM = 128, kCcBN = 128, kCcBK = 64, kCcStages = 4;
-constexpr int kCcEpiWarps = 8;                       // two per TMEM lane quadrant: each takes half of the tile's pixel columns
+#ifndef MGA_CC_EPI_WARPS
+#define MGA_CC_EPI_WARPS 8
+#endif
+constexpr int kCcEpiWarps = MGA_CC_EPI_WARPS;        // kCcEpiSplit per TMEM lane quadrant: each takes 1 / kCcEpiSplit of the tile's pixel columns
+constexpr int kCcEpiSplit = kCcEpiWarps / 4;         // 2 (64 columns per warp) or 4 (32 columns per warp)
+constexpr int kCcEpiChunks = 8 / kCcEpiSplit;        // 16-column accumulator chunks per warp
 constexpr int kCcThreads = 64 + 32 * kCcEpiWarps;
 constexpr int kCcStageBytes = (2 * kCcBM * kCcBK + kCcBK * kCcBN) * 2;  // two weight tiles + the feature tile, 16-bit elements
 constexpr int kCcSmemBytes = kCcStages * kCcStageBytes + 1024 /* alignment slack */ + 256 /* barriers */ + 2 * kCcBN * 4 /* spatial gate of the tile */;
@@ -96,7 +101,7 @@ __device__ __forceinline__ void concat_epilogue_tile(uint32_t tacc, int warp, in
     const uint32_t trow = tacc + ((uint32_t)(q * 32) << 16);
     const size_t rowoff = ((size_t)b * C + co) * S;
 #pragma unroll 1
-    for (int c16 = half * 4; c16 < half * 4 + 4; ++c16) {
+    for (int c16 = half * kCcEpiChunks; c16 < half * kCcEpiChunks + kCcEpiChunks; ++c16) {
         const int p = p0 + c16 * 16;
         uint32_t y1[16], y2[16];
         tmem_ld16(trow + c16 * 16, y1);
@@ -145,7 +150,7 @@ struct ConcatBwd {
 // this thread's pieces of x and grad_out for its row and the 64 pixel columns of its half of the tile: issued BEFORE the wait for the
 // accumulators, so their latency hides behind the tile's MMAs (the first version loaded them chunk by chunk after the wait: 1284 us at
 // cfg4-P3 against 912 us, every chunk a serial round trip to L2 / HBM)
-struct ConcatBwdRegs { uint4 xr[8], gr[8]; };
+struct ConcatBwdRegs { uint4 xr[2 * kCcEpiChunks], gr[2 * kCcEpiChunks]; };
 template <typename T>
 __device__ __forceinline__ void concat_epilogue_bwd_prefetch(ConcatBwdRegs& r, int warp, int lane, const T* __restrict__ g, const ConcatBwd& bw, int b,
                                                              int m0, int p0, int C, int S) {
@@ -153,8 +158,8 @@ __device__ __forceinline__ void concat_epilogue_bwd_prefetch(ConcatBwdRegs& r, i
     const size_t rowoff = ((size_t)b * C + m0 + q * 32 + lane) * S;
     const T* __restrict__ xf = static_cast<const T*>(bw.x);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int p = p0 + half * 64 + k * 8;
+    for (int k = 0; k < 2 * kCcEpiChunks; ++k) {
+        const int p = p0 + half * (16 * kCcEpiChunks) + k * 8;
         if (p < S) {  // (S % 8 == 0: whole 16-byte pieces; warp-uniform)
             r.xr[k] = __ldg(reinterpret_cast<const uint4*>(xf + rowoff + p));
             r.gr[k] = __ldg(reinterpret_cast<const uint4*>(g + rowoff + p));
@@ -191,8 +196,8 @@ __device__ __forceinline__ void concat_epilogue_bwd_tile(uint32_t tacc, const Co
     const int nTilesN = (S + kCcBN - 1) / kCcBN;
     float su = 0.0f, sg = 0.0f, dal = 0.0f;
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-        const int c16 = half * 4 + cc;
+    for (int cc = 0; cc < kCcEpiChunks; ++cc) {
+        const int c16 = half * kCcEpiChunks + cc;
         const int p = p0 + c16 * 16;
         uint32_t y1[16], y2[16];
         tmem_ld16(trow + c16 * 16, y1);
@@ -250,12 +255,12 @@ __device__ __forceinline__ void concat_epilogue_bwd_tile(uint32_t tacc, const Co
             }
         }
     }
-    const size_t pi = ((size_t)b * (2 * nTilesN) + (size_t)(p0 / kCcBN) * 2 + half) * C + c;
+    const size_t pi = ((size_t)b * (kCcEpiSplit * nTilesN) + (size_t)(p0 / kCcBN) * kCcEpiSplit + half) * C + c;
     bw.ds_part[pi] = alpha * su;
     bw.db_part[pi] = alpha * sg;
     dal = fmaf(__ldg(bias + c), sg, dal);
     dal = warp_sum(dal);
-    if (lane == 0) bw.dal_part[((size_t)b * nTilesN + p0 / kCcBN) * (size_t)(C / kCcBM * 8) + (m0 / kCcBM) * 8 + (warp - 2)] = dal;
+    if (lane == 0) bw.dal_part[((size_t)b * nTilesN + p0 / kCcBN) * (size_t)(C / kCcBM * kCcEpiWarps) + (m0 / kCcBM) * kCcEpiWarps + (warp - 2)] = dal;
 }
 
 // W (C, 2C) fp32 -> wat[ci][co] = W[co][ci], wbt[ci][co] = W[co][C + ci] in the feature dtype (A operands of the backward GEMMs, K = co contiguous)

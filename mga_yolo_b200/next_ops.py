@@ -380,10 +380,11 @@ def _concat_backward(x, s, a, w, bias, beta, gout, pyramid_multiply):
             del uv
         else:
             nT = (S + 127) // 128
-            ds_part = torch.empty((B, 2 * nT, Cc), dtype=torch.float32, device=x.device)
-            db_part = torch.empty((B, 2 * nT, Cc), dtype=torch.float32, device=x.device)
+            ew = int(os.getenv("MGA_CC_EPI_WARPS", "8"))  # epilogue warps of the library build (tuning builds may carry 16)
+            ds_part = torch.empty((B, (ew // 4) * nT, Cc), dtype=torch.float32, device=x.device)
+            db_part = torch.empty((B, (ew // 4) * nT, Cc), dtype=torch.float32, device=x.device)
             da_part = torch.empty((B, Cc // 32, S), dtype=torch.float32, device=x.device)
-            dal_part = torch.empty((B, nT, Cc // 16), dtype=torch.float32, device=x.device)
+            dal_part = torch.empty((B, nT, (Cc // 128) * ew), dtype=torch.float32, device=x.device)
             ws = torch.empty(2 * Cc * Cc, dtype=dt, device=x.device)
             rc = lib.mga_cbam_concat_backward_dx(C.byref(d), x.data_ptr(), g.data_ptr(), sf.data_ptr(), af.data_ptr(), w2.data_ptr(), bf.data_ptr(),
                                                  btf.data_ptr(), dx.data_ptr(), ga.data_ptr(), ds_part.data_ptr(), db_part.data_ptr(),

@@ -14,7 +14,8 @@ for (B, Cc, H, W) in SHAPES:
     bias = torch.zeros(Cc, device=dev); beta = torch.zeros((), device=dev)
     nT = (S + 127) // 128
     dx = torch.empty_like(x); ga = torch.empty_like(x)
-    dsp = torch.empty(B, 2 * nT, Cc, device=dev); dbp = torch.empty_like(dsp); dap = torch.empty(B, Cc // 32, S, device=dev); dal = torch.empty(B, nT, Cc // 16, device=dev)
+    EW = int(__import__('os').getenv('MGA_CC_EPI_WARPS', '8'))
+    dsp = torch.empty(B, (EW // 4) * nT, Cc, device=dev); dbp = torch.empty_like(dsp); dap = torch.empty(B, Cc // 32, S, device=dev); dal = torch.empty(B, nT, (Cc // 128) * EW, device=dev)
     ws = torch.empty(2 * Cc * Cc, dtype=dt, device=dev)
     d = _lib.Desc(B, Cc, H, W, 1, 1, _lib.BF16, _lib.F32, _lib.PYRAMID_MULTIPLY, 0.0, 0.0)
     rc = lib.mga_cbam_concat_backward_dx(C.byref(d), x.data_ptr(), g.data_ptr(), s.data_ptr(), a.data_ptr(), w.data_ptr(), bias.data_ptr(), beta.data_ptr(),
