@@ -35,12 +35,13 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce1_kernel(cons
     }
     const size_t base = ((size_t)b * C) * sh.S;
     // channels are taken KB at a time: all loads of a batch are issued before anything consumes them
-    constexpr int KB0 = VEC == 8 ? MGA_KB2 / 2 : MGA_KB2;
+    constexpr int KB0 = VEC == 8 ? MGA_KB2_16 : MGA_KB2;
     constexpr int KB = KB0 / UPT > 0 ? KB0 / UPT : 1;
     // (warp-uniform bound: the shuffles inside need every lane, also when C is not a multiple of the channels per warp load)
     for (int cw = tm.w * TM_::CPW; cw < C; cw += TM_::kChanStep * KB) {
         const int c0 = cw + tm.sub;
-        float xv[KB][UPT][VEC], gv[KB][UPT][VEC], e[KB], gxs[KB];
+        RawV xr[KB][UPT], gr[KB][UPT];  // held raw (zero bits = 0.0 in every element type), unpacked at use
+        float e[KB], gxs[KB];
 #pragma unroll
         for (int kc = 0; kc < KB; ++kc) {
             const int c = c0 + kc * TM_::kChanStep;
@@ -48,11 +49,11 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce1_kernel(cons
             for (int k = 0; k < UPT; ++k) {
                 const int u = tm.unit(tile, k);
                 if (u < U && c < C) {
-                    ldv<T, VEC, kLdKeepL2>(x + base + (size_t)c * sh.S + (size_t)u * VEC, xv[kc][k]);
-                    ldv<T, VEC, kLdKeepL2>(g + base + (size_t)c * sh.S + (size_t)u * VEC, gv[kc][k]);
+                    xr[kc][k] = ldraw<T, VEC, kLdKeepL2>(x + base + (size_t)c * sh.S + (size_t)u * VEC);
+                    gr[kc][k] = ldraw<T, VEC, kLdKeepL2>(g + base + (size_t)c * sh.S + (size_t)u * VEC);
                 } else {
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) { xv[kc][k][i] = 0.0f; gv[kc][k][i] = 0.0f; }
+                    xr[kc][k].t = make_uint4(0u, 0u, 0u, 0u);
+                    gr[kc][k].t = make_uint4(0u, 0u, 0u, 0u);
                 }
             }
         }
@@ -62,14 +63,18 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce1_kernel(cons
             const float q = (multiply && c < C) ? __ldg(sp + c) : 1.0f;
             e[kc] = 0.0f; gxs[kc] = 0.0f;
 #pragma unroll
-            for (int k = 0; k < UPT; ++k)
+            for (int k = 0; k < UPT; ++k) {
+                float xv[VEC], gv[VEC];
+                unpackv<T, VEC>(xr[kc][k], xv);
+                unpackv<T, VEC>(gr[kc][k], gv);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
-                    const float gx = gv[kc][k][i] * xv[kc][k][i];
+                    const float gx = gv[i] * xv[i];
                     tacc[k][i] = fmaf(gx, q, tacc[k][i]);
                     e[kc] = fmaf(gx, av[k][i], e[kc]);
                     gxs[kc] += gx;
                 }
+            }
         }
 #pragma unroll
         for (int kc = 0; kc < KB; ++kc) {
@@ -202,23 +207,21 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce2_kernel(cons
         }
     }
     const size_t base = ((size_t)b * C) * sh.S;
-    constexpr int KB0 = VEC == 8 ? MGA_KB1 / 2 : MGA_KB1;
+    constexpr int KB0 = VEC == 8 ? MGA_KB1_16 : MGA_KB1;
     constexpr int KB = KB0 / UPT > 0 ? KB0 / UPT : 1;
     // (warp-uniform bound: the shuffles inside need every lane, also when C is not a multiple of the channels per warp load)
     for (int cw = tm.w * TM_::CPW; cw < C; cw += TM_::kChanStep * KB) {
         const int c0 = cw + tm.sub;
-        float xv[KB][UPT][VEC], qv[KB];
+        RawV xr[KB][UPT];  // held raw, unpacked at use
+        float qv[KB];
 #pragma unroll
         for (int kc = 0; kc < KB; ++kc) {
             const int c = c0 + kc * TM_::kChanStep;
 #pragma unroll
             for (int k = 0; k < UPT; ++k) {
                 const int u = tm.unit(tile, k);
-                if (u < U && c < C) ldv<T, VEC, kLdKeepL2>(x + base + (size_t)c * sh.S + (size_t)u * VEC, xv[kc][k]);
-                else {
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) xv[kc][k][i] = 0.0f;
-                }
+                if (u < U && c < C) xr[kc][k] = ldraw<T, VEC, kLdKeepL2>(x + base + (size_t)c * sh.S + (size_t)u * VEC);
+                else xr[kc][k].t = make_uint4(0u, 0u, 0u, 0u);
             }
         }
 #pragma unroll
@@ -226,9 +229,12 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce2_kernel(cons
             const int c = c0 + kc * TM_::kChanStep;
             qv[kc] = 0.0f;
 #pragma unroll
-            for (int k = 0; k < UPT; ++k)
+            for (int k = 0; k < UPT; ++k) {
+                float xv[VEC];
+                unpackv<T, VEC>(xr[kc][k], xv);
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) qv[kc] = fmaf(xv[kc][k][i], d1[k][i] + (ix[k][i] == c ? d0[k][i] : 0.0f), qv[kc]);
+                for (int i = 0; i < VEC; ++i) qv[kc] = fmaf(xv[i], d1[k][i] + (ix[k][i] == c ? d0[k][i] : 0.0f), qv[kc]);
+            }
         }
 #pragma unroll
         for (int kc = 0; kc < KB; ++kc) qv[kc] = group_sum<LPT>(qv[kc]);
@@ -372,7 +378,8 @@ __global__ void __launch_bounds__(kBlock) bwd_mlp_kernel(Shape sh, mga_cbam_para
 // ------------------------------------------------------------------ B5
 // over (x,g): dx (streaming store) and R_p = sum_c cA_c x -> dmask.  Thread mapping: TileMap with UPT = 1.
 template <typename T, int VEC, int LPT>
-__global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ g, const void* __restrict__ mask,
+// (16-bit: 48 per-pixel registers + two channels of raw (x, g) loads need ~80 registers: three CTAs per SM instead of four)
+__global__ void __launch_bounds__(kBlock, VEC == 8 ? 3 : MGA_TILE_MINB) bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ g, const void* __restrict__ mask,
                                                                        int mdt, T* __restrict__ dx, void* __restrict__ dmask, Shape sh, Ctx ctx,
                                                                        BwdScratch bs) {
     using TM_ = TileMap<LPT, 1, VEC>;
@@ -406,15 +413,15 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* 
     }
     const size_t base = ((size_t)b * C) * sh.S + (size_t)u * VEC;
     if (act) {
-        constexpr int KB = VEC == 8 ? MGA_KB2 / 2 : MGA_KB2;  // channels per batch: 2*KB independent 128-bit loads in flight per thread
+        constexpr int KB = VEC == 8 ? MGA_KB2_16 : MGA_KB2;  // channels per batch: 2*KB independent 128-bit loads in flight per thread, held raw
         for (int c0 = tm.chan0(); c0 < C; c0 += TM_::kChanStep * KB) {
-            float xv[KB][VEC], gv[KB][VEC];
+            RawV xr[KB], gr[KB];
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
                 const int c = c0 + k * TM_::kChanStep;
                 if (c < C) {
-                    ldv<T, VEC, kLdLastUse>(x + base + (size_t)c * sh.S, xv[k]);
-                    ldv<T, VEC, kLdLastUse>(g + base + (size_t)c * sh.S, gv[k]);
+                    xr[k] = ldraw<T, VEC, kLdLastUse>(x + base + (size_t)c * sh.S);
+                    gr[k] = ldraw<T, VEC, kLdLastUse>(g + base + (size_t)c * sh.S);
                 }
             }
 #pragma unroll
@@ -422,19 +429,21 @@ __global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_dx_kernel(const T* 
                 const int c = c0 + k * TM_::kChanStep;
                 if (c >= C) continue;
                 const int bc = b * C + c;
-                float ov[VEC];
+                float ov[VEC], xvk[VEC], gvk[VEC];
+                unpackv<T, VEC>(xr[k], xvk);
+                unpackv<T, VEC>(gr[k], gvk);
                 const float s = __ldg(ctx.s + bc), cA = __ldg(bs.cA + bc), cG = __ldg(bs.cG + bc), cM = __ldg(bs.cM + bc);
                 const int am = __ldg(ctx.amax + bc);
                 const float q = add ? 1.0f : s;
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
                     const float gate = add ? (s + av[i]) : (s * av[i]);
-                    float v = gv[k][i] * fmaf(k1, gate, k0);
+                    float v = gvk[i] * fmaf(k1, gate, k0);
                     v = fmaf(q, d1[i] + (ix[i] == c ? d0[i] : 0.0f), v);
                     v = fmaf(cA, mv[i], v) + cG;
                     if (u * VEC + i == am) v += cM;
                     ov[i] = v;
-                    racc[i] = fmaf(cA, xv[k][i], racc[i]);
+                    racc[i] = fmaf(cA, xvk[i], racc[i]);
                 }
                 stv<T, VEC, true>(dx + base + (size_t)c * sh.S, ov);
             }

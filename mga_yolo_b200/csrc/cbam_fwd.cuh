@@ -325,17 +325,17 @@ __device__ __forceinline__ void sam_reduce_body(const T* __restrict__ x, const S
 #pragma unroll
         for (int i = 0; i < VEC; ++i) { vmax[k][i] = -INFINITY; vsum[k][i] = 0.0f; vidx[k][i] = 0x7fffffff; }
     const T* xp = x + ((size_t)b * C) * sh.S;
-    constexpr int KB0 = VEC == 8 ? MGA_KB1 / 2 : MGA_KB1;
+    constexpr int KB0 = VEC == 8 ? MGA_KB1_16 : MGA_KB1;
     constexpr int KB = KB0 / UPT > 0 ? KB0 / UPT : 1;
     for (int c0 = tm.chan0(); c0 < C; c0 += TM_::kChanStep * KB) {
-        float v[KB][UPT][VEC];
+        RawV raw[KB][UPT];  // held raw, unpacked at use: KB * UPT loads of 16 bytes in flight per thread for every element type
 #pragma unroll
         for (int kc = 0; kc < KB; ++kc) {
             const int c = c0 + kc * TM_::kChanStep;
 #pragma unroll
             for (int k = 0; k < UPT; ++k) {
                 const int u = tm.unit(tile, k);
-                if (c < C && u < U) ldv<T, VEC, kLdKeepL2>(xp + (size_t)c * sh.S + (size_t)u * VEC, v[kc][k]);
+                if (c < C && u < U) raw[kc][k] = ldraw<T, VEC, kLdKeepL2>(xp + (size_t)c * sh.S + (size_t)u * VEC);
             }
         }
 #pragma unroll
@@ -346,9 +346,11 @@ __device__ __forceinline__ void sam_reduce_body(const T* __restrict__ x, const S
 #pragma unroll
             for (int k = 0; k < UPT; ++k) {
                 if (tm.unit(tile, k) >= U) continue;
+                float v[VEC];
+                unpackv<T, VEC>(raw[kc][k], v);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
-                    const float y = v[kc][k][i] * q;
+                    const float y = v[i] * q;
                     vsum[k][i] += y;
                     if (y > vmax[k][i]) { vmax[k][i] = y; vidx[k][i] = c; }
                 }

@@ -25,6 +25,12 @@ constexpr int kSMs = 148;            // B200
 #ifndef MGA_KB1
 #define MGA_KB1 4
 #endif
+#ifndef MGA_KB1_16
+#define MGA_KB1_16 4  // ... of the 16-bit instantiations, which hold their loads RAW (4 registers per 16 bytes) and unpack at use: as many bytes in flight as fp32 (was 2 loads: unpacked fp32 registers)
+#endif
+#ifndef MGA_KB2_16
+#define MGA_KB2_16 2  // 16-bit instantiations of the (x, g) kernels: channels per batch, loads held raw (was 1)
+#endif
 #ifndef MGA_KB2
 #define MGA_KB2 2
 #endif
@@ -60,6 +66,52 @@ __device__ __forceinline__ unsigned long long l2_policy_last() {
     unsigned long long p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
+}
+
+// The same load kept RAW (4 registers per 16 bytes whatever the element type) and unpacked when it is consumed: a 16-bit unit unpacks to
+// 8 fp32 registers, so loops that keep several loads in flight hold them raw (twice the bytes in flight per register).
+struct RawV { uint4 t; };
+template <typename T, int VEC, int MODE = 0>
+__device__ __forceinline__ RawV ldraw(const T* __restrict__ p) {
+    constexpr int kMode = (MGA_L2_HINTS || MODE < 2) ? MODE : 1;
+    RawV r;
+    if constexpr (VEC == 1) {
+        r.t = make_uint4(__float_as_uint(to_f<T>(p[0])), 0u, 0u, 0u);
+    } else if constexpr (kMode == kLdStream) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.t.x), "=r"(r.t.y), "=r"(r.t.z), "=r"(r.t.w) : "l"(p));
+    } else if constexpr (kMode == kLdKeepL2) {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=r"(r.t.x), "=r"(r.t.y), "=r"(r.t.z), "=r"(r.t.w) : "l"(p), "l"(l2_policy_keep()));
+    } else if constexpr (kMode == kLdLastUse) {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=r"(r.t.x), "=r"(r.t.y), "=r"(r.t.z), "=r"(r.t.w) : "l"(p), "l"(l2_policy_last()));
+    } else {
+        r.t = __ldg(reinterpret_cast<const uint4*>(p));
+    }
+    return r;
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void unpackv(const RawV& r, float (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+        v[0] = __uint_as_float(r.t.x);
+    } else if constexpr (sizeof(T) == 4) {
+        static_assert(VEC == 4, "fp32 vector is 4 wide");
+        v[0] = __uint_as_float(r.t.x); v[1] = __uint_as_float(r.t.y); v[2] = __uint_as_float(r.t.z); v[3] = __uint_as_float(r.t.w);
+    } else {
+        static_assert(VEC == 8, "16-bit vector is 8 wide");
+        const uint32_t w[4] = {r.t.x, r.t.y, r.t.z, r.t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                v[2 * i] = __uint_as_float(w[i] << 16);
+                v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+            } else {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                v[2 * i] = f.x;
+                v[2 * i + 1] = f.y;
+            }
+        }
+    }
 }
 
 // 128-bit (or scalar) global load of VEC consecutive elements into fp32 registers.
