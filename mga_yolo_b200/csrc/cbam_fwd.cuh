@@ -65,12 +65,13 @@ __device__ __forceinline__ void cam_pool_body(const T* __restrict__ x, const Sha
     float sxm = 0.0f, sx = 0.0f, best = -INFINITY;
     int bidx = -1;
     for (int u0 = lt; u0 < U; u0 += 4 * TPP) {
-        float v[4][VEC], mv[4][VEC];
+        RawV raw[4];
+        float mv[4][VEC];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int u = u0 + q * TPP;
             if (u < U) {
-                ldv<T, VEC, kLdKeepL2>(xp + (size_t)u * VEC, v[q]);
+                raw[q] = ldraw<T, VEC, kLdKeepL2>(xp + (size_t)u * VEC);
                 if (has_mask) ldf<VEC>(mp + (size_t)u * VEC, mv[q]);
             }
         }
@@ -78,12 +79,14 @@ __device__ __forceinline__ void cam_pool_body(const T* __restrict__ x, const Sha
         for (int q = 0; q < 4; ++q) {
             const int u = u0 + q * TPP;
             if (u < U) {
+                float v[VEC];
+                unpackv<T, VEC>(raw[q], v);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
                     const float m = has_mask ? mv[q][i] : 1.0f;
-                    sx += v[q][i];
-                    sxm = fmaf(v[q][i], m, sxm);
-                    if ((!has_mask || m > 0.5f) && v[q][i] > best) { best = v[q][i]; bidx = u * VEC + i; }
+                    sx += v[i];
+                    sxm = fmaf(v[i], m, sxm);
+                    if ((!has_mask || m > 0.5f) && v[i] > best) { best = v[i]; bidx = u * VEC + i; }
                 }
             }
         }
@@ -142,18 +145,21 @@ __global__ void __launch_bounds__(kBlock) cam_pool4_kernel(const T* __restrict__
     for (int j = 0; j < 4; ++j) { sxm[j] = 0.0f; sx[j] = 0.0f; best[j] = -INFINITY; bidx[j] = -1; }
 #pragma unroll 2
     for (int u = threadIdx.x; u < U; u += kBlock) {
-        float mv[VEC], v[4][VEC];
+        float mv[VEC];
+        RawV raw[4];  // held raw, unpacked channel by channel (a 16-bit unit would otherwise occupy 8 registers while in flight)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ldv<T, VEC, kLdStream>(xp + (size_t)j * sh.S + (size_t)u * VEC, v[j]);
+        for (int j = 0; j < 4; ++j) raw[j] = ldraw<T, VEC, kLdStream>(xp + (size_t)j * sh.S + (size_t)u * VEC);
         if (has_mask) ldf<VEC>(mp + (size_t)u * VEC, mv);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+            float v[VEC];
+            unpackv<T, VEC>(raw[j], v);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
                 const float m = has_mask ? mv[i] : 1.0f;
-                sx[j] += v[j][i];
-                sxm[j] = fmaf(v[j][i], m, sxm[j]);
-                if ((!has_mask || m > 0.5f) && v[j][i] > best[j]) { best[j] = v[j][i]; bidx[j] = u * VEC + i; }  // ascending pixels per thread
+                sx[j] += v[i];
+                sxm[j] = fmaf(v[i], m, sxm[j]);
+                if ((!has_mask || m > 0.5f) && v[i] > best[j]) { best[j] = v[i]; bidx[j] = u * VEC + i; }  // ascending pixels per thread
             }
         }
     }
