@@ -14,7 +14,7 @@ namespace mga {
 // ------------------------------------------------------------------ B1
 // over (x,g): T_p (per pixel) and E_c, Gx_c (per channel, per-tile partials).  Thread mapping: TileMap (common.cuh).
 template <typename T, int VEC, int LPT, int UPT>
-__global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce1_kernel(const T* __restrict__ x, const T* __restrict__ g, Shape sh, Ctx ctx,
+__global__ void __launch_bounds__(kBlock, VEC == 8 ? MGA_TILE_MINB_16 : MGA_TILE_MINB) bwd_reduce1_kernel(const T* __restrict__ x, const T* __restrict__ g, Shape sh, Ctx ctx,
                                                                             BwdScratch bs, int nT) {
     using TM_ = TileMap<LPT, UPT, VEC>;
     constexpr int TP = TM_::TP;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kBlock) bwd_conv_kernel(Shape sh, const float*
 // ------------------------------------------------------------------ B3 (multiply mode)
 // over x: Q_c = sum_p x (dcat1/C + [idx == c] dcat0), per-tile partials.  Thread mapping: TileMap.
 template <typename T, int VEC, int LPT, int UPT>
-__global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) bwd_reduce2_kernel(const T* __restrict__ x, Shape sh, Ctx ctx, BwdScratch bs, int nT) {
+__global__ void __launch_bounds__(kBlock, VEC == 8 ? MGA_TILE_MINB_16 : MGA_TILE_MINB) bwd_reduce2_kernel(const T* __restrict__ x, Shape sh, Ctx ctx, BwdScratch bs, int nT) {
     using TM_ = TileMap<LPT, UPT, VEC>;
     const TM_ tm;
     const int b = blockIdx.y, tile = blockIdx.x;

@@ -404,7 +404,7 @@ __device__ __forceinline__ void sam_reduce_body(const T* __restrict__ x, const S
     }
 }
 template <typename T, int VEC, int LPT, int UPT>
-__global__ void __launch_bounds__(kBlock, MGA_TILE_MINB) sam_reduce_kernel(const T* __restrict__ x, Shape sh, Ctx ctx) {
+__global__ void __launch_bounds__(kBlock, VEC == 8 ? MGA_TILE_MINB_16 : MGA_TILE_MINB) sam_reduce_kernel(const T* __restrict__ x, Shape sh, Ctx ctx) {
     sam_reduce_body<T, VEC, LPT, UPT>(x, sh, ctx, this_block());
 }
 

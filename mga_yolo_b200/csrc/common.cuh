@@ -19,6 +19,9 @@ constexpr int kWarpsPerBlock = kBlock / kWarp;
 constexpr int kSMs = 148;            // B200
 // tuning knobs of the tile kernels (sam_reduce, bwd_reduce1/2, bwd_dx): resident CTAs per SM the register
 // allocation must allow, and channels per load batch (x-only kernels / x+g kernels)
+#ifndef MGA_TILE_MINB_16
+#define MGA_TILE_MINB_16 3  // ... of their 16-bit instantiations (80 registers: six raw loads in flight; measured on cfg5: 0.650 -> 0.630 ms)
+#endif
 #ifndef MGA_TILE_MINB
 #define MGA_TILE_MINB 4
 #endif
@@ -26,7 +29,7 @@ constexpr int kSMs = 148;            // B200
 #define MGA_KB1 4
 #endif
 #ifndef MGA_KB1_16
-#define MGA_KB1_16 4  // ... of the 16-bit instantiations, which hold their loads RAW (4 registers per 16 bytes) and unpack at use: as many bytes in flight as fp32 (was 2 loads: unpacked fp32 registers)
+#define MGA_KB1_16 6  // ... of the 16-bit instantiations, which hold their loads RAW (4 registers per 16 bytes) and unpack at use: as many bytes in flight as fp32 (was 2 loads: unpacked fp32 registers)
 #endif
 #ifndef MGA_KB2_16
 #define MGA_KB2_16 2  // 16-bit instantiations of the (x, g) kernels: channels per batch, loads held raw (was 1)
