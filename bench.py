@@ -757,6 +757,37 @@ def bind_to_gpu_numa(local_rank):
         return None
 
 
+def pcie_probe(dev):
+    """Raw pinned-host <-> device copy bandwidth of THIS box (256 MiB, copy streams): the e2e number is bounded by it, and the boxes differ
+    (device->host was seen at 55 GB/s on most and ~20 GB/s on some)."""
+    n = 256 << 20
+    h_in, h_out = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_a, d_b = torch.empty(n, dtype=torch.uint8, device=dev), torch.ones(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(up, down, reps=4):
+        def once():
+            if up:
+                with torch.cuda.stream(s1):
+                    d_a.copy_(h_in, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_b, non_blocking=True)
+        once()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            once()
+        for s_ in (s1, s2):
+            torch.cuda.current_stream(dev).wait_stream(s_)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return round((int(up) + int(down)) * n / (e0.elapsed_time(e1) / reps) / 1e6, 1)
+
+    return {"h2d_GBps": run(True, False), "d2h_GBps": run(False, True), "both_GBps": run(True, True)}
+
+
 def e2e_module(args, dev, local_rank, levels, B, dtype, world, alg_bytes):
     """Public API path with HOST buffers in and out: pinned host x / mask / grad_out -> H2D -> MaskGuidedCBAM forward ->
     autograd backward -> out, dx, dmask and the flat weight gradients -> D2H into pinned host memory.  Everything a caller of the
@@ -857,7 +888,12 @@ def e2e_module(args, dev, local_rank, levels, B, dtype, world, alg_bytes):
 
     ms_full, steps = timed(True)
     ms_grads, _ = timed(False)
+    try:
+        probe = pcie_probe(dev)
+    except Exception as e:  # pragma: no cover
+        probe = {"error": str(e)}
     return {"value": round(world * alg_bytes / (ms_full * 1e-3) / 1e9, 2), "unit": "GB/s", "ms_per_step": round(ms_full, 4), "steps": steps,
+            "pcie_probe": probe,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full, "images_per_sec": round(world * B / (ms_full * 1e-3), 1),
             "numa_node_of_pinned_buffers": numa,
             "api": "mga_yolo_b200.MaskGuidedCBAM forward + torch.autograd backward; pinned host x/mask/grad_out in (copy stream, overlapped with the kernels "
