@@ -807,7 +807,8 @@ def e2e_module(args, dev, local_rank, levels, B, dtype, world, alg_bytes):
         hm = torch.randn(B, 1, H, W, generator=gen).pin_memory()
         hg = torch.randn(B, Cc, H, W, generator=gen).to(dtype).pin_memory()
         host.append((hx, hm, hg))
-        devb.append((torch.empty_like(hx, device=dev), torch.empty_like(hm, device=dev), torch.empty_like(hg, device=dev)))
+        # two device input sets per level: the copies of step i + 1 run while step i computes and its results leave
+        devb.append([(torch.empty_like(hx, device=dev), torch.empty_like(hm, device=dev), torch.empty_like(hg, device=dev)) for _ in range(2)])
         hres.append((torch.empty_like(hx).pin_memory(), torch.empty_like(hx).pin_memory(), torch.empty_like(hm).pin_memory()))  # out, dx, dmask
     reducer = FlatGradReducer([p for m in mods for p in m.parameters()])
     hgrad = torch.empty(reducer.numel, dtype=torch.float32).pin_memory()
@@ -820,23 +821,28 @@ def e2e_module(args, dev, local_rank, levels, B, dtype, world, alg_bytes):
     main_s = torch.cuda.current_stream(dev)
     copy_s = torch.cuda.Stream(dev)
     back_s = torch.cuda.Stream(dev)
-    ev_copied = [torch.cuda.Event() for _ in levels]
-    ev_done = [torch.cuda.Event() for _ in levels]
+    ev_copied = [[torch.cuda.Event() for _ in levels] for _ in range(2)]
+    ev_done = [[torch.cuda.Event() for _ in levels] for _ in range(2)]
     ev_back = [torch.cuda.Event() for _ in levels]
-    for e in ev_done + ev_back:
+    for e in ev_done[0] + ev_done[1] + ev_back:
         e.record(main_s)
     keep = [None] * len(levels)  # results of the previous step stay alive until their D2H copy has been issued
+    nstep = [0]
 
     def step(full):
+        st_ = nstep[0] & 1
+        nstep[0] += 1
         with torch.cuda.stream(copy_s):
-            for li, ((hx, hm, hg), (dx_, dm_, dg_)) in enumerate(zip(host, devb)):
-                copy_s.wait_event(ev_done[li])
+            for li, ((hx, hm, hg), sets) in enumerate(zip(host, devb)):
+                dx_, dm_, dg_ = sets[st_]
+                copy_s.wait_event(ev_done[st_][li])  # the step before last has finished reading this set
                 dx_.copy_(hx, non_blocking=True)
                 dm_.copy_(hm, non_blocking=True)
                 dg_.copy_(hg, non_blocking=True)
-                ev_copied[li].record(copy_s)
-        for li, (m, (dx_, dm_, dg_)) in enumerate(zip(mods, devb)):
-            main_s.wait_event(ev_copied[li])
+                ev_copied[st_][li].record(copy_s)
+        for li, (m, sets) in enumerate(zip(mods, devb)):
+            dx_, dm_, dg_ = sets[st_]
+            main_s.wait_event(ev_copied[st_][li])
             xin = dx_.requires_grad_(True)
             min_ = dm_.requires_grad_(True)
             out = m([xin, min_])
@@ -846,10 +852,10 @@ def e2e_module(args, dev, local_rank, levels, B, dtype, world, alg_bytes):
             min_.grad = None
             dx_.requires_grad_(False)
             dm_.requires_grad_(False)
-            ev_done[li].record(main_s)
+            ev_done[st_][li].record(main_s)
             if full:
                 ho, hdx, hdm = hres[li]
-                back_s.wait_event(ev_done[li])
+                back_s.wait_event(ev_done[st_][li])
                 with torch.cuda.stream(back_s):
                     ho.copy_(out.detach(), non_blocking=True)
                     hdx.copy_(gx, non_blocking=True)
@@ -896,8 +902,8 @@ def e2e_module(args, dev, local_rank, levels, B, dtype, world, alg_bytes):
             "pcie_probe": probe,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full, "images_per_sec": round(world * B / (ms_full * 1e-3), 1),
             "numa_node_of_pinned_buffers": numa,
-            "api": "mga_yolo_b200.MaskGuidedCBAM forward + torch.autograd backward; pinned host x/mask/grad_out in (copy stream, overlapped with the kernels "
-                   "of the previous level); out, dx, dmask and the flat weight grads back to pinned host memory (second copy stream, full duplex)",
+            "api": "mga_yolo_b200.MaskGuidedCBAM forward + torch.autograd backward; pinned host x/mask/grad_out in (copy stream, two device input sets: the copies "
+                   "of step i + 1 overlap the kernels and the result copies of step i); out, dx, dmask and the flat weight grads back to pinned host memory (second copy stream, full duplex)",
             "result_stays_on_device": {"value": round(world * alg_bytes / (ms_grads * 1e-3) / 1e9, 2), "ms_per_step": round(ms_grads, 4),
                                        "d2h_bytes_per_step": hgrad.numel() * 4,
                                        "note": "same step when only the weight gradients return to the host (out feeds Detect and dx the neck's backward on the device, "
