@@ -868,6 +868,8 @@ def e2e_module(args, dev, local_rank, levels, B, dtype, world, alg_bytes):
             reducer.all_reduce()
         hgrad.copy_(reducer.flat, non_blocking=True)
 
+    host_ms = [0.0]
+
     def timed(full):
         steps = max(5, min(args.steps, 20))
         for _ in range(3):
@@ -878,9 +880,11 @@ def e2e_module(args, dev, local_rank, levels, B, dtype, world, alg_bytes):
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         for _ in range(steps):
             reducer.zero()
             step(full)
+        host_ms[0] = (time.perf_counter() - t_host) * 1e3 / steps  # CPU time to ENQUEUE a step (nothing waits inside the loop)
         for e in ev_back:
             main_s.wait_event(e)  # the closing event is after the last result has reached host memory
         e1.record()
@@ -893,17 +897,115 @@ def e2e_module(args, dev, local_rank, levels, B, dtype, world, alg_bytes):
         return ms, steps
 
     ms_full, steps = timed(True)
+    host_full = host_ms[0]
+    eager_results = [tuple(t.clone() for t in trip) for trip in hres] + [hgrad.clone()]  # to check the graph replays against (deterministic kernels)
     ms_grads, _ = timed(False)
+
+    # The same step captured in CUDA graphs (torch.cuda.graph around the public module calls and torch.autograd.backward), software
+    # pipelined: graph p computes on device input set p and returns its results while it copies the NEXT step's inputs into set 1 - p.
+    # One graph launch per step instead of ~100 host-side calls: the eager pipeline above is host bound on boxes with a slow CPU
+    # (host_enqueue_ms_per_step), this one is bound by the PCIe link only.  Single-GPU runs only (the all-reduce stays eager).
+    def graph_pipeline():
+        cap_s = torch.cuda.Stream(dev)
+        graphs, keepg = [], []
+        torch.cuda.synchronize(dev)
+        # the parameters' AccumulateGrad nodes remember the stream they were created on: drop every autograd graph of the eager steps
+        # and run two steps on the capture stream first, so that the capture never touches the default stream
+        for li in range(len(levels)):
+            keep[li] = None
+        with torch.cuda.stream(cap_s):
+            for _ in range(2):
+                reducer.zero()
+                for m, sets in zip(mods, devb):
+                    dx_, dm_, dg_ = sets[0]
+                    xin, min_ = dx_.requires_grad_(True), dm_.requires_grad_(True)
+                    out = m([xin, min_])
+                    torch.autograd.backward(out, dg_, inputs=[xin, min_, *m.parameters()])
+                    xin.grad = None
+                    min_.grad = None
+                    dx_.requires_grad_(False)
+                    dm_.requires_grad_(False)
+                    del out, xin, min_
+        torch.cuda.synchronize(dev)
+        for p in (0, 1):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=cap_s):
+                cur = torch.cuda.current_stream(dev)
+                copy_s.wait_stream(cur)
+                with torch.cuda.stream(copy_s):  # next step's inputs
+                    for (hx, hm, hg), sets in zip(host, devb):
+                        for dst, src in zip(sets[1 - p], (hx, hm, hg)):
+                            dst.copy_(src, non_blocking=True)
+                reducer.zero()
+                for li, (m, sets) in enumerate(zip(mods, devb)):
+                    dx_, dm_, dg_ = sets[p]
+                    xin, min_ = dx_.requires_grad_(True), dm_.requires_grad_(True)
+                    out = m([xin, min_])
+                    torch.autograd.backward(out, dg_, inputs=[xin, min_, *m.parameters()])
+                    gx, gm = xin.grad, min_.grad
+                    xin.grad = None
+                    min_.grad = None
+                    dx_.requires_grad_(False)
+                    dm_.requires_grad_(False)
+                    keepg.append((out, gx, gm))
+                    back_s.wait_stream(cur)
+                    with torch.cuda.stream(back_s):  # this level's results leave while the next level computes
+                        ho, hdx, hdm = hres[li]
+                        ho.copy_(out.detach(), non_blocking=True)
+                        hdx.copy_(gx, non_blocking=True)
+                        hdm.copy_(gm, non_blocking=True)
+                hgrad.copy_(reducer.flat, non_blocking=True)
+                cur.wait_stream(copy_s)
+                cur.wait_stream(back_s)
+            graphs.append(g)
+        steps_g = max(5, min(args.steps, 20))
+        with torch.cuda.stream(cap_s):
+            for (hx, hm, hg), sets in zip(host, devb):  # inputs of the first step
+                for dst, src in zip(sets[0], (hx, hm, hg)):
+                    dst.copy_(src, non_blocking=True)
+            k = 0
+            for _ in range(4):  # warm-up replays (even count: the next replay is graph 0 again, its inputs prefetched by the last graph 1)
+                graphs[k & 1].replay()
+                k += 1
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cap_s)
+            t_host = time.perf_counter()
+            for _ in range(steps_g):
+                graphs[k & 1].replay()
+                k += 1
+            host_g = (time.perf_counter() - t_host) * 1e3 / steps_g
+            e1.record(cap_s)
+            torch.cuda.synchronize(dev)
+        same = all(torch.equal(a, b) for trip, ref in zip(hres, eager_results[:-1]) for a, b in zip(trip, ref)) and torch.equal(hgrad, eager_results[-1])
+        if not same:
+            raise RuntimeError("graph replays returned other results than the eager pipeline")
+        return e0.elapsed_time(e1) / steps_g, host_g, keepg
+
+    ms_graph = host_graph = None
+    if world == 1:
+        try:
+            ms_graph, host_graph, _keep_alive = graph_pipeline()
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] e2e graph pipeline unavailable ({type(e).__name__}: {e}); reporting the eager pipeline", file=sys.stderr)
+            ms_graph = None
+    eager = {"value": round(world * alg_bytes / (ms_full * 1e-3) / 1e9, 2), "ms_per_step": round(ms_full, 4), "host_enqueue_ms_per_step": round(host_full, 3),
+             "note": "the same step issued call by call from Python (copy stream + compute stream + result stream, two device input sets)"}
+    if ms_graph is not None:
+        ms_full, host_full = ms_graph, host_graph
     try:
         probe = pcie_probe(dev)
     except Exception as e:  # pragma: no cover
         probe = {"error": str(e)}
     return {"value": round(world * alg_bytes / (ms_full * 1e-3) / 1e9, 2), "unit": "GB/s", "ms_per_step": round(ms_full, 4), "steps": steps,
-            "pcie_probe": probe,
+            "pcie_probe": probe, "host_enqueue_ms_per_step": round(host_full, 3), "eager_pipeline": eager,
+            "cuda_graph": ms_graph is not None,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full, "images_per_sec": round(world * B / (ms_full * 1e-3), 1),
             "numa_node_of_pinned_buffers": numa,
             "api": "mga_yolo_b200.MaskGuidedCBAM forward + torch.autograd backward; pinned host x/mask/grad_out in (copy stream, two device input sets: the copies "
-                   "of step i + 1 overlap the kernels and the result copies of step i); out, dx, dmask and the flat weight grads back to pinned host memory (second copy stream, full duplex)",
+                   "of step i + 1 overlap the kernels and the result copies of step i); out, dx, dmask and the flat weight grads back to pinned host memory (second copy "
+                   "stream, full duplex)" + ("; the step (copies included) is captured once with torch.cuda.graph around these public calls and replayed, one graph "
+                                             "launch per step -- `eager_pipeline` is the same step issued call by call" if ms_graph is not None else ""),
             "result_stays_on_device": {"value": round(world * alg_bytes / (ms_grads * 1e-3) / 1e9, 2), "ms_per_step": round(ms_grads, 4),
                                        "d2h_bytes_per_step": hgrad.numel() * 4,
                                        "note": "same step when only the weight gradients return to the host (out feeds Detect and dx the neck's backward on the device, "
