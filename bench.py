@@ -659,10 +659,47 @@ def concat_workload(dev, peak, bf16_peak_tflops):
             torch.cuda.synchronize(dev)
             return e0.elapsed_time(e1) / reps
 
-        ms = timed()
+        def timed_graph():
+            """The same two steps (input sets 0 / 1) captured in CUDA graphs and replayed: the device time of the step without the
+            ~100 host-side calls per level, which bound the eager loop on boxes with a slow CPU (4.3 ms on one box, 6.3 ms on another)."""
+            cap_s = torch.cuda.Stream(dev)
+            torch.cuda.synchronize(dev)
+            with torch.cuda.stream(cap_s):  # (the parameters' AccumulateGrad nodes must be created on the capture stream)
+                for i in range(2):
+                    step(i)
+            torch.cuda.synchronize(dev)
+            graphs = []
+            for i in range(2):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=cap_s):
+                    step(i)
+                graphs.append(gph)
+            with torch.cuda.stream(cap_s):
+                for i in range(2):
+                    graphs[i].replay()
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(cap_s)
+                for i in range(reps):
+                    graphs[i & 1].replay()
+                e1.record(cap_s)
+                torch.cuda.synchronize(dev)
+            del graphs
+            return e0.elapsed_time(e1) / reps
+
+        def best():
+            eager = timed()
+            try:
+                return timed_graph(), eager, True
+            except Exception as e:  # pragma: no cover
+                print(f"[bench] cfg4 graph capture unavailable ({type(e).__name__}: {str(e)[:120]}); reporting the eager loop", file=sys.stderr)
+                torch.cuda.synchronize(dev)
+                return eager, eager, False
+
+        ms, ms_eager, graphed = best()
         os.environ["MGA_CONCAT_LIBRARY"] = "1"
         try:
-            ms_lib = timed()
+            ms_lib, ms_lib_eager, lib_graphed = best()
         finally:
             os.environ.pop("MGA_CONCAT_LIBRARY", None)
     except Exception as e:  # pragma: no cover
@@ -674,11 +711,12 @@ def concat_workload(dev, peak, bf16_peak_tflops):
     flops = sum(3 * 2.0 * (B * H * W) * (2 * Cc) * Cc for (Cc, H, W) in levels)  # forward GEMM + two backward GEMMs of the 2C->C 1x1 conv
     return {"workload": "BASELINE configs[3]: YOLOv8m (256/512/512 ch) batch 128 bf16, sam_cam_fusion=concat, mga_pyramid_fusion=multiply (module-only fwd+bwd)",
             "levels_CHW": levels, "batch": B, "dtype": "bfloat16", "ms_per_step": round(ms, 4), "steps": reps, "warmup": 3,
+            "cuda_graph": graphed, "eager_ms_per_step": round(ms_eager, 4),
             "value": round(ab / (ms * 1e-3) / 1e9, 1), "unit": "GB/s", "step_frac": round(ab / (ms * 1e-3) / 1e9 / peak, 4),
             "images_per_sec": round(B / (ms * 1e-3), 1), "gemm_tflops": round(flops / (ms * 1e-3) / 1e12, 1),
             "gemm_frac_of_bf16_sustained": None if not bf16_peak_tflops else round(flops / (ms * 1e-3) / 1e12 / bf16_peak_tflops, 4),
             "path": "forward: gates op + fold + ONE tcgen05 kernel (TMA, TMEM accumulators, fused epilogue); backward: levels with C > 256 = ONE tcgen05 kernel (U, V in TMEM, closed form in the epilogue), C <= 256 = library GEMM + elementwise kernel; weight gradient = 2 per-sample library GEMMs (fp32) + 1 batch-reduce kernel; gates backward accumulates the concat dx (one autograd node)",
-            "library_composition": {"ms_per_step": round(ms_lib, 4), "note": "same module as gates op + torch.cat + F.conv2d (cuDNN) + autograd (MGA_CONCAT_LIBRARY=1)"},
+            "library_composition": {"ms_per_step": round(ms_lib, 4), "cuda_graph": lib_graphed, "eager_ms_per_step": round(ms_lib_eager, 4), "note": "same module as gates op + torch.cat + F.conv2d (cuDNN) + autograd (MGA_CONCAT_LIBRARY=1)"},
             "note": "oracle: in-repo PyTorch composition; reference parity unpinned"}
 
 
