@@ -563,6 +563,11 @@ def gpu_arm(args, rank, world, local_rank):
     if solo and not args.no_cpu and args.workload == "cfg2":
         line["mask_pipeline"] = mask_pipeline(dev, B, 640, peak)
         line["inference_b1"] = inference_b1(dev, levels, dtype, os.cpu_count() or 1)
+        try:
+            line["spade_block"] = spade_block(dev, levels, B, dtype, peak)
+        except Exception as e:  # pragma: no cover
+            line["spade_block"] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
     if solo and not args.no_workloads and args.workload == "cfg2":
         # the other BASELINE configs that fit one GPU: same step, same rules, fewer timed steps
         wl = {}
@@ -1132,6 +1137,56 @@ def mask_pipeline(dev, B, imgsz, peak):
             "cpu_baseline": {"masks_per_sec": round(1.0 / cpu_s, 1), "cores": 1, "kind": kind,
                              "sample": "8 masks x 3 strides, " + ("the reference's MaskUtils.downsample_mask (cv2) from oracle/_ref" if kind == "reference"
                                                                   else "oracle/mask_oracle.py (numpy restatement of cv2.resize / morphologyEx)")}}
+
+
+def spade_block(dev, levels, B, dtype, peak):
+    """SURVEY 8f-4 neighbour: the feature side of MaskSPADE (instance statistics + gamma * xhat + beta, and its closed-form backward) through
+    torch.ops.mga.spade_fwd / spade_bwd at the same pyramid shapes; gamma / beta stand for the outputs of the block's mask branch.
+    Algorithmic bytes per level: forward x, gamma, beta in + y out = 4 N e; backward x, g, gamma in + dx, d gamma out = 5 N e."""
+    e = torch.empty((), dtype=dtype).element_size()
+    sets = []
+    for (C, H, W) in levels:
+        gen = torch.Generator(device=dev).manual_seed(C)
+        sets.append(tuple(torch.randn(B, C, H, W, device=dev, dtype=dtype, generator=gen) for _ in range(4)))  # x, gamma, beta, g
+    alg = sum(9 * B * C * H * W * e for (C, H, W) in levels)
+
+    def step():
+        for x, gm, bt, g in sets:
+            _, stats = torch.ops.mga.spade_fwd(x, gm, bt, 1e-6)
+            torch.ops.mga.spade_bwd(g, x, gm, stats, True)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    reps = 10
+    per = []
+    for li, (x, gm, bt, g) in enumerate(sets):  # per-kernel durations (P3 alone touches 0.9 GB per pass: nothing stays in L2)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        tf = tb = 0.0
+        for _ in range(reps):
+            ev[0].record()
+            _, stats = torch.ops.mga.spade_fwd(x, gm, bt, 1e-6)
+            ev[1].record()
+            torch.ops.mga.spade_bwd(g, x, gm, stats, True)
+            ev[2].record()
+            torch.cuda.synchronize(dev)
+            tf += ev[0].elapsed_time(ev[1])
+            tb += ev[1].elapsed_time(ev[2])
+        n = B * levels[li][0] * levels[li][1] * levels[li][2] * e
+        per.append({"level": f"P{3 + li}", "fwd_ms": round(tf / reps, 5), "bwd_ms": round(tb / reps, 5),
+                    "fwd_frac": round(4 * n / (tf / reps * 1e-3) / 1e9 / peak, 4), "bwd_frac": round(5 * n / (tb / reps * 1e-3) / 1e9 / peak, 4)})
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    return {"workload": f"MaskSPADE feature side (mga_spade_forward / mga_spade_backward), levels {levels}, batch {B}, {str(dtype).split('.')[-1]}",
+            "ms_per_step": round(ms, 5), "value": round(alg / (ms * 1e-3) / 1e9, 1), "unit": "GB/s", "algorithmic_bytes_per_step": alg,
+            "roofline": {"bound": "hbm", "achieved": round(alg / (ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s", "frac": round(alg / (ms * 1e-3) / 1e9 / peak, 4)},
+            "kernels": per, "launches_per_step": 2 * len(levels),
+            "note": "eager op calls on one stream (6 launches per step); the mask branch that produces gamma / beta is library convolution work and not timed here"}
 
 
 def inference_b1(dev, levels, dtype, threads):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MGA_ABI_VERSION 2
+#define MGA_ABI_VERSION 3
 
 enum { MGA_OK = 0, MGA_ERR_ARG = 1, MGA_ERR_UNSUPPORTED = 2, MGA_ERR_CUDA = 3, MGA_ERR_WORKSPACE = 4 };
 
@@ -235,6 +235,18 @@ int mga_gate_sample_backward(const float* grad_out, const float* p, const float*
 /* Zero-pad + stack of per-sample masks of ONE pyramid stride (mga_yolo/data/dataset.py:149-169): items is a DEVICE array of B records
  * { const void* src; int32_t h, w; } (16 bytes each), src uint8 or float32 (h,w) maps; dst (B,1,H,W) float32 with H >= h_i, W >= w_i. */
 int mga_collate_masks(const void* items_dev, float* dst, int32_t B, int32_t H, int32_t W, int32_t src_dtype, void* stream);
+
+/* MaskSPADE, feature side (mga_yolo/nn/modules/masked_spade.py:73,126-143): out = gamma * IN(x) + beta with IN = affine-free
+ * InstanceNorm2d (per (sample, channel) mean / biased variance over H*W, rstd = 1/sqrt(var + eps)).  x, out, grad_out, grad_x: (B,C,H,W)
+ * of `dtype`; gamma, beta, grad_gamma: (B,C,H,W) of `mod_dtype` = `dtype` or MGA_F32 (the outputs of the block's mask branch
+ * conv_gamma / conv_beta, which stay with the caller: dense 3x3 convolutions); gamma == beta == NULL is the mask-less branch
+ * (plain normalisation, masked_spade.py:128-130).  stats: (B,C,2) fp32 = mean, rstd, written by forward and read by backward.
+ * Backward: grad_gamma = g * xhat (written when not NULL), grad_beta = g (the caller's tensor, nothing to compute),
+ * grad_x = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)) with dxhat = g * gamma (g when gamma == NULL). */
+int mga_spade_forward(const void* x, const void* gamma, const void* beta, void* out, float* stats, int32_t B, int32_t C, int32_t H, int32_t W, float eps,
+                      int32_t dtype, int32_t mod_dtype, void* stream);
+int mga_spade_backward(const void* x, const void* grad_out, const void* gamma, const float* stats, void* grad_x, void* grad_gamma, int32_t B, int32_t C,
+                       int32_t H, int32_t W, int32_t dtype, int32_t mod_dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@ Public surface (mirrors the reference's operator interface for this path):
     install / uninstall         swap the class inside the reference's Ultralytics graph builder
     ops.mask_guided_cbam        functional form;  torch.ops.mga.{cbam_fwd,cbam_bwd,mask_downsample}
     MaskECA                     nn.Module drop-in for mga_yolo/nn/modules/masked_eca.py (shares the masked-pool front end)
+    MaskSPADE                   nn.Module drop-in for mga_yolo/nn/modules/masked_spade.py (instance norm + modulation + backward in CUDA)
     MGAMaskHead                 mirror of mga_yolo/nn/modules/segmentation.py whose 3x3 logit tail runs in the CUDA library
     next_ops.gate_sample        train-mode ProbMaskGater (Philox noise contract);  MaskUtils.collate_masks  zero-pad collate
 """
@@ -19,9 +20,10 @@ from .mask_ops import MaskUtils
 from .module import MaskCBAM, MaskGate, MaskGuidedCBAM
 from .eca import MaskECA
 from .head import MGAMaskHead
+from .spade import MaskSPADE
 
 __all__ = [
     "MaskGuidedCBAM", "MaskCBAM", "MaskGate", "MGAHookManager", "MaskUtils", "install", "uninstall",
-    "FlatGradReducer", "shard_range", "ops", "next_ops", "MaskECA", "MGAMaskHead",
+    "FlatGradReducer", "shard_range", "ops", "next_ops", "MaskECA", "MGAMaskHead", "MaskSPADE",
 ]
 __version__ = "0.1.0"

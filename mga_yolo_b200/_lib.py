@@ -11,7 +11,7 @@ from pathlib import Path
 import os as _os
 
 LIB_PATH = Path(__file__).resolve().parent / _os.environ.get("MGA_LIBNAME", "libmga_cbam.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # enums of include/mga_cbam.h
 F32, BF16, F16, U8 = 0, 1, 2, 3
@@ -24,7 +24,7 @@ EXPORTS = (
     "mga_cbam_ctx_view", "mga_mask_downsample", "mga_masks_multi", "mga_masks_multi_ws", "mga_cbam_plan", "mga_cbam_gates_forward", "mga_cbam_gates_backward", "mga_cbam_gates_backward_acc", "mga_launch_count", "mga_profile_enable", "mga_profile_count",
     "mga_profile_read", "mga_eca_workspace", "mga_eca_forward", "mga_eca_backward", "mga_head_tail_forward", "mga_head_tail_backward",
     "mga_gate_sample_forward", "mga_gate_sample_backward", "mga_collate_masks", "mga_cbam_concat_forward", "mga_cbam_concat_backward_elem",
-    "mga_cbam_concat_wgrad_reduce", "mga_cbam_concat_backward_dx",
+    "mga_cbam_concat_wgrad_reduce", "mga_cbam_concat_backward_dx", "mga_spade_forward", "mga_spade_backward",
 )
 
 
@@ -112,6 +112,10 @@ def load() -> C.CDLL:
     lib.mga_cbam_concat_wgrad_reduce.restype = C.c_int
     lib.mga_cbam_concat_backward_dx.argtypes = [C.POINTER(Desc)] + [C.c_void_p] * 15
     lib.mga_cbam_concat_backward_dx.restype = C.c_int
+    lib.mga_spade_forward.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_float, C.c_int32, C.c_int32, C.c_void_p]
+    lib.mga_spade_forward.restype = C.c_int
+    lib.mga_spade_backward.argtypes = [C.c_void_p] * 6 + [C.c_int32] * 6 + [C.c_void_p]
+    lib.mga_spade_backward.restype = C.c_int
     for fn in (lib.mga_eca_workspace, lib.mga_eca_forward, lib.mga_eca_backward, lib.mga_head_tail_forward, lib.mga_head_tail_backward,
                lib.mga_gate_sample_forward, lib.mga_gate_sample_backward, lib.mga_collate_masks):
         fn.restype = C.c_int

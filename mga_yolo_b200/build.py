@@ -18,7 +18,7 @@ CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = PKG / "libmga_cbam.so"
 LIB_TUNING = PKG / "libmga_cbam_tuning.so"  # same sources + -DMGA_TUNING: MGA_CL_* environment knobs and the phase timeline (tools/, geometry tests)
-SOURCES = ("mga_cbam.cu", "mask_ops.cu")
+SOURCES = ("mga_cbam.cu", "mask_ops.cu", "spade_ops.cu")
 ARCH = ("-gencode", "arch=compute_100a,code=sm_100a")
 
 

@@ -1,0 +1,297 @@
+// spade_ops.cu -- the feature side of MaskSPADE, C ABI in include/mga_cbam.h:
+//
+//   mga_spade_forward    y = gamma * IN(x) + beta           /root/reference/mga_yolo/nn/modules/masked_spade.py:73,126,143
+//                        (affine-free InstanceNorm2d: per (sample, channel) mean and biased variance over H*W, eps inside the root;
+//                        gamma == NULL: plain normalisation, masked_spade.py:128-130)
+//   mga_spade_backward   closed form of the same: d gamma = g * xhat, d beta = g (the caller's own tensor),
+//                        dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)) with dxhat = g * gamma
+//
+// HBM-bound streaming kernels: ONE CTA owns one (sample, channel) row, reads it from HBM once into shared memory (fp32), derives the two
+// statistics there (two-pass variance, fixed summation order, no atomics) and streams the modulation out -- x, gamma, beta are read once
+// and y written once (forward: 4 N elements of traffic; backward: x, g, gamma in, dx, d gamma out = 5 N).  Rows that do not fit the
+// staging budget are re-read through L2 instead.  The mask branch that PRODUCES gamma / beta (3x3 convolutions 1 -> hidden -> C,
+// masked_spade.py:78-84) is dense convolution work and stays with the caller's library.
+#include <cstdint>
+
+#include "common.cuh"
+#include "mga_cbam.h"
+
+namespace mga {
+
+constexpr int kSpNT = 256;
+constexpr size_t kSpStageBytes = 112 * 1024;  // two CTAs per SM keep their rows in shared memory
+
+template <int VEC>
+__device__ __forceinline__ void sp_lds(const float* p, float (&v)[VEC]) {  // shared-memory row, 128-bit reads
+    if constexpr (VEC == 1) {
+        v[0] = p[0];
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC / 4; ++i) {
+            const float4 t = reinterpret_cast<const float4*>(p)[i];
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+    }
+}
+template <typename TG, int VEC>
+__device__ __forceinline__ void sp_ld_mod(const TG* __restrict__ p, float (&v)[VEC]) {
+    if constexpr (VEC == 1) v[0] = to_f<TG>(p[0]);
+    else if constexpr (sizeof(TG) == 4) ldf<VEC>(reinterpret_cast<const float*>(p), v);
+    else ldv<TG, VEC, kLdStream>(p, v);
+}
+template <typename TG, int VEC>
+__device__ __forceinline__ void sp_st_mod(TG* __restrict__ p, const float (&v)[VEC]) {
+    if constexpr (VEC == 1) p[0] = from_f<TG>(v[0]);
+    else if constexpr (sizeof(TG) == 4) stf<VEC>(reinterpret_cast<float*>(p), v);
+    else stv<TG, VEC, true>(p, v);
+}
+
+// x: (R, S) rows of T; gamma / beta: (R, S) rows of TG or NULL; stats: (R, 2) = mean, rstd (saved for backward)
+template <typename T, typename TG, int VEC, bool STAGED>
+__global__ void __launch_bounds__(kSpNT) spade_fwd_kernel(const T* __restrict__ x, const TG* __restrict__ gamma, const TG* __restrict__ beta,
+                                                          T* __restrict__ out, float* __restrict__ stats, int S, float eps) {
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    __shared__ float red[32];
+    float* const rowf = reinterpret_cast<float*>(sp_smem);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const size_t base = (size_t)blockIdx.x * S;
+    const T* const xr = x + base;
+    const int nU = S / VEC;
+    const float invS = 1.0f / (float)S;
+
+    float sum = 0.0f;
+    for (int u = tid; u < nU; u += nt) {
+        float v[VEC];
+        ldv<T, VEC, STAGED ? kLdStream : kLdDefault>(xr + (size_t)u * VEC, v);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) sum += v[i];
+        if constexpr (STAGED) stf<VEC>(rowf + (size_t)u * VEC, v);  // every thread re-reads only what it wrote: no barrier needed
+    }
+    const float mean = block_sum(sum, red) * invS;
+    float sq = 0.0f;
+    for (int u = tid; u < nU; u += nt) {
+        float v[VEC];
+        if constexpr (STAGED) {
+            sp_lds<VEC>(rowf + (size_t)u * VEC, v);
+        } else {
+            ldv<T, VEC, kLdDefault>(xr + (size_t)u * VEC, v);
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float d = v[i] - mean;
+            sq = fmaf(d, d, sq);
+        }
+    }
+    const float var = block_sum(sq, red) * invS;
+    const float rstd = 1.0f / sqrtf(var + eps);
+    if (tid == 0) {
+        stats[2 * (size_t)blockIdx.x] = mean;
+        stats[2 * (size_t)blockIdx.x + 1] = rstd;
+    }
+    const bool mod = gamma != nullptr;
+    for (int u = tid; u < nU; u += nt) {
+        float v[VEC], o[VEC];
+        if constexpr (STAGED) {
+            sp_lds<VEC>(rowf + (size_t)u * VEC, v);
+        } else {
+            ldv<T, VEC, kLdStream>(xr + (size_t)u * VEC, v);
+        }
+        if (mod) {
+            float gm[VEC], bt[VEC];
+            sp_ld_mod<TG, VEC>(gamma + base + (size_t)u * VEC, gm);
+            sp_ld_mod<TG, VEC>(beta + base + (size_t)u * VEC, bt);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] = fmaf(gm[i], (v[i] - mean) * rstd, bt[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] = (v[i] - mean) * rstd;
+        }
+        stv<T, VEC, true>(out + base + (size_t)u * VEC, o);
+    }
+}
+
+template <typename T, typename TG, int VEC, bool STAGED>
+__global__ void __launch_bounds__(kSpNT) spade_bwd_kernel(const T* __restrict__ x, const T* __restrict__ g, const TG* __restrict__ gamma,
+                                                          const float* __restrict__ stats, T* __restrict__ dx, TG* __restrict__ dgamma, int S) {
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    __shared__ float red[32];
+    float* const xh_s = reinterpret_cast<float*>(sp_smem);  // STAGED: xhat row, then dxhat row
+    float* const dh_s = xh_s + S;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const size_t base = (size_t)blockIdx.x * S;
+    const int nU = S / VEC;
+    const float invS = 1.0f / (float)S;
+    const float mean = __ldg(stats + 2 * (size_t)blockIdx.x), rstd = __ldg(stats + 2 * (size_t)blockIdx.x + 1);
+    const bool mod = gamma != nullptr;
+
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int u = tid; u < nU; u += nt) {
+        const size_t o = base + (size_t)u * VEC;
+        float xv[VEC], gv[VEC], dh[VEC];
+        ldv<T, VEC, STAGED ? kLdStream : kLdDefault>(x + o, xv);
+        ldv<T, VEC, STAGED ? kLdStream : kLdDefault>(g + o, gv);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) xv[i] = (xv[i] - mean) * rstd;
+        if (mod) {
+            float gm[VEC], dg[VEC];
+            sp_ld_mod<TG, VEC>(gamma + o, gm);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                dh[i] = gv[i] * gm[i];
+                dg[i] = gv[i] * xv[i];
+            }
+            if (dgamma != nullptr) sp_st_mod<TG, VEC>(dgamma + o, dg);
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) dh[i] = gv[i];
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            s1 += dh[i];
+            s2 = fmaf(dh[i], xv[i], s2);
+        }
+        if constexpr (STAGED) {
+            stf<VEC>(xh_s + (size_t)u * VEC, xv);
+            stf<VEC>(dh_s + (size_t)u * VEC, dh);
+        }
+    }
+    const float m1 = block_sum(s1, red) * invS;
+    const float m2 = block_sum(s2, red) * invS;
+    for (int u = tid; u < nU; u += nt) {
+        const size_t o = base + (size_t)u * VEC;
+        float xv[VEC], dh[VEC], r[VEC];
+        if constexpr (STAGED) {
+            sp_lds<VEC>(xh_s + (size_t)u * VEC, xv);
+            sp_lds<VEC>(dh_s + (size_t)u * VEC, dh);
+        } else {
+            float gv[VEC];
+            ldv<T, VEC, kLdStream>(x + o, xv);
+            ldv<T, VEC, kLdStream>(g + o, gv);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) xv[i] = (xv[i] - mean) * rstd;
+            if (mod) {
+                float gm[VEC];
+                sp_ld_mod<TG, VEC>(gamma + o, gm);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) dh[i] = gv[i] * gm[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) dh[i] = gv[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) r[i] = rstd * (dh[i] - m1 - xv[i] * m2);
+        stv<T, VEC, true>(dx + o, r);
+    }
+}
+
+// small rows (P5: 20 x 20) take small CTAs so that the SM still holds many rows
+static int sp_threads(int units) { return units <= 128 ? 64 : (units <= 512 ? 128 : kSpNT); }
+static bool sp_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename Kern>
+static int sp_prepare(Kern kern, size_t smem) {
+    // per-device function state: set on every launch that needs it (cheap), never cached across devices
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MGA_ERR_CUDA, "cudaFuncSetAttribute(%zu bytes of shared memory) failed", smem);
+    }
+    return MGA_OK;
+}
+
+template <typename T, typename TG>
+static int spade_fwd_launch(const void* x, const void* gamma, const void* beta, void* out, float* stats, int R, int S, float eps, cudaStream_t st) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const bool vec = S % V == 0 && sp_aligned16(x) && sp_aligned16(out) && sp_aligned16(gamma) && sp_aligned16(beta);
+    const size_t stage = (size_t)S * sizeof(float);
+    const bool staged = stage <= kSpStageBytes;
+    const size_t smem = staged ? stage : 0;
+#define MGA_SP_F(VEC, STG)                                                                                                              \
+    do {                                                                                                                                \
+        auto kern = spade_fwd_kernel<T, TG, VEC, STG>;                                                                                  \
+        if (int rc = sp_prepare(kern, smem)) return rc;                                                                                 \
+        kern<<<R, sp_threads(S / VEC), smem, st>>>(static_cast<const T*>(x), static_cast<const TG*>(gamma), static_cast<const TG*>(beta), static_cast<T*>(out), \
+                                     stats, S, eps);                                                                                    \
+    } while (0)
+    if (vec) { if (staged) MGA_SP_F(V, true); else MGA_SP_F(V, false); }
+    else     { if (staged) MGA_SP_F(1, true); else MGA_SP_F(1, false); }
+#undef MGA_SP_F
+    return MGA_OK;
+}
+
+template <typename T, typename TG>
+static int spade_bwd_launch(const void* x, const void* g, const void* gamma, const float* stats, void* dx, void* dgamma, int R, int S, cudaStream_t st) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const bool vec = S % V == 0 && sp_aligned16(x) && sp_aligned16(g) && sp_aligned16(dx) && sp_aligned16(gamma) && sp_aligned16(dgamma);
+    const size_t stage = 2 * (size_t)S * sizeof(float);
+    const bool staged = stage <= kSpStageBytes;
+    const size_t smem = staged ? stage : 0;
+#define MGA_SP_B(VEC, STG)                                                                                                              \
+    do {                                                                                                                                \
+        auto kern = spade_bwd_kernel<T, TG, VEC, STG>;                                                                                  \
+        if (int rc = sp_prepare(kern, smem)) return rc;                                                                                 \
+        kern<<<R, sp_threads(S / VEC), smem, st>>>(static_cast<const T*>(x), static_cast<const T*>(g), static_cast<const TG*>(gamma), stats, static_cast<T*>(dx), \
+                                     static_cast<TG*>(dgamma), S);                                                                      \
+    } while (0)
+    if (vec) { if (staged) MGA_SP_B(V, true); else MGA_SP_B(V, false); }
+    else     { if (staged) MGA_SP_B(1, true); else MGA_SP_B(1, false); }
+#undef MGA_SP_B
+    return MGA_OK;
+}
+
+static int sp_launch_ok(const char* name) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(MGA_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e));
+    return MGA_OK;
+}
+
+}  // namespace mga
+
+using namespace mga;
+
+extern "C" {
+
+int mga_spade_forward(const void* x, const void* gamma, const void* beta, void* out, float* stats, int32_t B, int32_t C, int32_t H, int32_t W, float eps,
+                      int32_t dtype, int32_t mod_dtype, void* stream) {
+    if (!x || !out || !stats) return fail(MGA_ERR_ARG, "mga_spade_forward: null pointer argument");
+    if ((gamma == nullptr) != (beta == nullptr)) return fail(MGA_ERR_ARG, "mga_spade_forward: gamma and beta come together");
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || (long long)B * C > 0x7fffffffLL || (long long)H * W > (1 << 28)) return fail(MGA_ERR_ARG, "mga_spade_forward: bad shape");
+    if (!(eps >= 0.0f)) return fail(MGA_ERR_ARG, "mga_spade_forward: eps must be >= 0");
+    if (gamma && mod_dtype != dtype && mod_dtype != MGA_F32) return fail(MGA_ERR_UNSUPPORTED, "mga_spade_forward: gamma / beta must have the feature dtype or float32");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int R = B * C, S = H * W;
+    const bool modf32 = gamma && mod_dtype == MGA_F32;
+    int rc = MGA_OK;
+    switch (dtype) {
+        case MGA_F32: rc = spade_fwd_launch<float, float>(x, gamma, beta, out, stats, R, S, eps, st); break;
+        case MGA_BF16: rc = modf32 ? spade_fwd_launch<__nv_bfloat16, float>(x, gamma, beta, out, stats, R, S, eps, st)
+                                   : spade_fwd_launch<__nv_bfloat16, __nv_bfloat16>(x, gamma, beta, out, stats, R, S, eps, st); break;
+        case MGA_F16: rc = modf32 ? spade_fwd_launch<__half, float>(x, gamma, beta, out, stats, R, S, eps, st)
+                                  : spade_fwd_launch<__half, __half>(x, gamma, beta, out, stats, R, S, eps, st); break;
+        default: return fail(MGA_ERR_ARG, "mga_spade_forward: bad feature dtype %d", dtype);
+    }
+    return rc ? rc : sp_launch_ok("mga_spade_forward");
+}
+
+int mga_spade_backward(const void* x, const void* grad_out, const void* gamma, const float* stats, void* grad_x, void* grad_gamma, int32_t B, int32_t C,
+                       int32_t H, int32_t W, int32_t dtype, int32_t mod_dtype, void* stream) {
+    if (!x || !grad_out || !stats || !grad_x) return fail(MGA_ERR_ARG, "mga_spade_backward: null pointer argument");
+    if (!gamma && grad_gamma) return fail(MGA_ERR_ARG, "mga_spade_backward: grad_gamma without gamma");
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || (long long)B * C > 0x7fffffffLL || (long long)H * W > (1 << 28)) return fail(MGA_ERR_ARG, "mga_spade_backward: bad shape");
+    if (gamma && mod_dtype != dtype && mod_dtype != MGA_F32) return fail(MGA_ERR_UNSUPPORTED, "mga_spade_backward: gamma must have the feature dtype or float32");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int R = B * C, S = H * W;
+    const bool modf32 = gamma && mod_dtype == MGA_F32;
+    int rc = MGA_OK;
+    switch (dtype) {
+        case MGA_F32: rc = spade_bwd_launch<float, float>(x, grad_out, gamma, stats, grad_x, grad_gamma, R, S, st); break;
+        case MGA_BF16: rc = modf32 ? spade_bwd_launch<__nv_bfloat16, float>(x, grad_out, gamma, stats, grad_x, grad_gamma, R, S, st)
+                                   : spade_bwd_launch<__nv_bfloat16, __nv_bfloat16>(x, grad_out, gamma, stats, grad_x, grad_gamma, R, S, st); break;
+        case MGA_F16: rc = modf32 ? spade_bwd_launch<__half, float>(x, grad_out, gamma, stats, grad_x, grad_gamma, R, S, st)
+                                  : spade_bwd_launch<__half, __half>(x, grad_out, gamma, stats, grad_x, grad_gamma, R, S, st); break;
+        default: return fail(MGA_ERR_ARG, "mga_spade_backward: bad feature dtype %d", dtype);
+    }
+    return rc ? rc : sp_launch_ok("mga_spade_backward");
+}
+
+}  // extern "C"

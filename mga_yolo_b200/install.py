@@ -1,4 +1,4 @@
-"""Swap the reference's `MaskCBAM` (and its neighbours `MaskECA`, `MGAMaskHead`) for the B200 implementations, in place.
+"""Swap the reference's `MaskCBAM` (and its neighbours `MaskECA`, `MaskSPADE`, `MGAMaskHead`) for the B200 implementations, in place.
 
 parse_model resolves YAML class names through `globals()` of ultralytics/nn/tasks.py and
 then tests `m is MaskCBAM` (tasks.py:1676-1682,1733-1739), so the patched object has to be
@@ -16,12 +16,14 @@ import functools
 from .eca import MaskECA
 from .head import MGAMaskHead
 from .module import MaskCBAM, shape_probe
+from .spade import MaskSPADE
 
 # YAML class name -> replacement (ultralytics/nn/tasks.py:1724 `m is MGAMaskHead`, :1733 `m is MaskECA or ... m is MaskCBAM`)
-_CLASSES = {"MaskCBAM": MaskCBAM, "MaskECA": MaskECA, "MGAMaskHead": MGAMaskHead}
+_CLASSES = {"MaskCBAM": MaskCBAM, "MaskECA": MaskECA, "MaskSPADE": MaskSPADE, "MGAMaskHead": MGAMaskHead}
 _TARGETS = (
     "mga_yolo.nn.modules.masked_cbam",
     "mga_yolo.nn.modules.masked_eca",
+    "mga_yolo.nn.modules.masked_spade",
     "mga_yolo.nn.modules.segmentation",
     "mga_yolo.model.model",  # `isinstance(m, MGAMaskHead)` against its import-time global decides which layers feed "seg" (model.py:11,217-220)
     "ultralytics.nn.tasks",
@@ -55,7 +57,7 @@ def _unwrap_builder(cls) -> None:
         cls.__init__ = init._mga_original
 
 
-def install(strict: bool = False, classes=("MaskCBAM", "MaskECA", "MGAMaskHead")) -> list:
+def install(strict: bool = False, classes=("MaskCBAM", "MaskECA", "MaskSPADE", "MGAMaskHead")) -> list:
     """Patch every already-imported module that exposes one of `classes`; returns the patched module names.
     The graph builder's `DetectionModel.__init__` (the base of MGAModel, mga_yolo/model/model.py:40) is wrapped so that
     its CPU stride probe passes through the block as a shape-only call."""

@@ -4,6 +4,7 @@
     torch.ops.mga.head_tail_fwd / head_tail_bwd       MGAMaskHead.head        (mga_yolo/nn/modules/segmentation.py:94,107-110)
     torch.ops.mga.gate_sample / gate_sample_bwd       ProbMaskGater, training (mga_yolo/nn/modules/probmaskgater.py:59-95)
     torch.ops.mga.collate_masks                       masks_multi collate     (mga_yolo/data/dataset.py:149-169)
+    torch.ops.mga.spade_fwd / spade_bwd               MaskSPADE, feature side (mga_yolo/nn/modules/masked_spade.py:126-143)
 
 CUDA dispatch key (the kernels of csrc/next_ops.cuh through the C ABI) and Meta key (shapes only): CPU tensors fail in the dispatcher.
 """
@@ -29,6 +30,8 @@ _LIBDEF.define("head_tail_bwd(Tensor grad_logits, Tensor feat, Tensor weight) ->
 _LIBDEF.define("gate_sample(Tensor p, Tensor? noise, int mode, float tau, float p_min, float threshold, int seed, int offset) -> (Tensor, Tensor)")
 _LIBDEF.define("gate_sample_bwd(Tensor grad_out, Tensor p, Tensor soft, float tau, float p_min) -> Tensor")
 _LIBDEF.define("collate_masks(Tensor[] maps) -> Tensor")
+_LIBDEF.define("spade_fwd(Tensor x, Tensor? gamma, Tensor? beta, float eps) -> (Tensor, Tensor)")
+_LIBDEF.define("spade_bwd(Tensor grad_out, Tensor x, Tensor? gamma, Tensor stats, bool need_gamma_grad) -> (Tensor, Tensor?)")
 
 
 @lru_cache(maxsize=256)
@@ -175,6 +178,55 @@ def _collate_cuda(maps: List[torch.Tensor]):
     return out
 
 
+def _spade_prep(x, gamma, beta=None):
+    if x.dim() != 4 or x.dtype not in _DT:
+        raise RuntimeError(f"feature map must be (B,C,H,W) float32 / bfloat16 / float16, got {tuple(x.shape)} {x.dtype}")
+    for name, t in (("gamma", gamma), ("beta", beta)):
+        if t is None:
+            continue
+        if tuple(t.shape) != tuple(x.shape):
+            raise RuntimeError(f"{name} {tuple(t.shape)} does not match the feature map {tuple(x.shape)}")
+        if t.dtype not in (x.dtype, torch.float32):
+            raise RuntimeError(f"{name} must have the feature dtype or float32, got {t.dtype}")
+    if beta is not None and gamma is not None and beta.dtype != gamma.dtype:
+        raise RuntimeError("gamma and beta must share a dtype")
+    return _DT[x.dtype], (_DT[gamma.dtype] if gamma is not None else _DT[x.dtype])
+
+
+def _spade_fwd_cuda(x, gamma, beta, eps):
+    lib = _lib.load()
+    if (gamma is None) != (beta is None):
+        raise RuntimeError("gamma and beta come together")
+    dt, mdt = _spade_prep(x, gamma, beta)
+    x = x.contiguous()
+    gamma = None if gamma is None else gamma.contiguous()
+    beta = None if beta is None else beta.contiguous()
+    B, Cc, H, W = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty_like(x)
+        stats = torch.empty((B, Cc, 2), dtype=torch.float32, device=x.device)
+        rc = lib.mga_spade_forward(x.data_ptr(), None if gamma is None else gamma.data_ptr(), None if beta is None else beta.data_ptr(), out.data_ptr(),
+                                   stats.data_ptr(), B, Cc, H, W, float(eps), dt, mdt, _stream(x))
+    _lib.check(rc, "mga_spade_forward")
+    return out, stats
+
+
+def _spade_bwd_cuda(grad_out, x, gamma, stats, need_gamma_grad):
+    lib = _lib.load()
+    dt, mdt = _spade_prep(x, gamma)
+    x = x.contiguous()
+    grad_out = grad_out.contiguous().to(x.dtype)
+    gamma = None if gamma is None else gamma.contiguous()
+    B, Cc, H, W = x.shape
+    with torch.cuda.device(x.device):
+        dx = torch.empty_like(x)
+        dgamma = torch.empty_like(gamma) if (gamma is not None and need_gamma_grad) else None
+        rc = lib.mga_spade_backward(x.data_ptr(), grad_out.data_ptr(), None if gamma is None else gamma.data_ptr(), stats.data_ptr(), dx.data_ptr(),
+                                    None if dgamma is None else dgamma.data_ptr(), B, Cc, H, W, dt, mdt, _stream(x))
+    _lib.check(rc, "mga_spade_backward")
+    return dx, dgamma
+
+
 # ---- Meta kernels (shapes only)
 def _eca_fwd_meta(x, mask, w1d, beta, flags, tiny_thr, eps):
     _, ctx_bytes, _ = _eca_prep(x, mask, w1d, flags, tiny_thr, eps)
@@ -209,10 +261,21 @@ def _collate_meta(maps):
     return maps[0].new_empty((len(maps), 1, H, W), dtype=torch.float32)
 
 
+def _spade_fwd_meta(x, gamma, beta, eps):
+    _spade_prep(x, gamma, beta)
+    return torch.empty_like(x, memory_format=torch.contiguous_format), x.new_empty((x.shape[0], x.shape[1], 2), dtype=torch.float32)
+
+
+def _spade_bwd_meta(grad_out, x, gamma, stats, need_gamma_grad):
+    dgamma = torch.empty_like(gamma, memory_format=torch.contiguous_format) if (gamma is not None and need_gamma_grad) else None
+    return torch.empty_like(x, memory_format=torch.contiguous_format), dgamma
+
+
 for _name, _cuda, _meta in (("eca_fwd", _eca_fwd_cuda, _eca_fwd_meta), ("eca_bwd", _eca_bwd_cuda, _eca_bwd_meta),
                             ("head_tail_fwd", _head_tail_fwd_cuda, _head_tail_fwd_meta), ("head_tail_bwd", _head_tail_bwd_cuda, _head_tail_bwd_meta),
                             ("gate_sample", _gate_sample_cuda, _gate_sample_meta), ("gate_sample_bwd", _gate_sample_bwd_cuda, _gate_sample_bwd_meta),
-                            ("collate_masks", _collate_cuda, _collate_meta)):
+                            ("collate_masks", _collate_cuda, _collate_meta), ("spade_fwd", _spade_fwd_cuda, _spade_fwd_meta),
+                            ("spade_bwd", _spade_bwd_cuda, _spade_bwd_meta)):
     _LIBIMPL.impl(_name, _cuda, "CUDA")
     _LIBIMPL.impl(_name, _meta, "Meta")
 
@@ -243,6 +306,30 @@ class _EcaFn(torch.autograd.Function):
 def mask_eca(x, mask, w1d, beta, *, flags: int, tiny_mask_thr: float = 1e-4, eps: float = 1e-6):
     """out = MaskECA([x, mask]) with the given conv1d weight (1,1,k) and beta (autograd-aware)."""
     return _EcaFn.apply(x, mask, w1d, beta, int(flags), float(tiny_mask_thr), float(eps))
+
+
+class _SpadeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        _need_cuda(x, "MaskSPADE")
+        out, stats = torch.ops.mga.spade_fwd(x, gamma, beta, eps)
+        ctx.save_for_backward(x, gamma, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, gamma, stats = ctx.saved_tensors
+        need_gamma = gamma is not None and ctx.needs_input_grad[1]
+        dx, dgamma = torch.ops.mga.spade_bwd(grad_out, x, gamma, stats, need_gamma)
+        dbeta = None
+        if gamma is not None and ctx.needs_input_grad[2]:
+            dbeta = grad_out if grad_out.dtype == gamma.dtype else grad_out.to(gamma.dtype)  # d beta IS grad_out: nothing to compute
+        return dx, dgamma, dbeta, None
+
+
+def spade_modulate(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], eps: float = 1e-6) -> torch.Tensor:
+    """gamma * InstanceNorm(x) + beta (plain InstanceNorm when gamma is None) by the CUDA kernels of csrc/spade_ops.cu (autograd-aware)."""
+    return _SpadeFn.apply(x, gamma, beta, float(eps))
 
 
 class _HeadTailFn(torch.autograd.Function):

@@ -1,6 +1,6 @@
 """The drop-in, end to end, on the GPU: the reference's own `MGAModel('yolov8n_cbam.yaml')` -- built from baseline/_ref, the unmodified
 reference package laid out by oracle/build_full_ref.py -- run forward + backward with its own classes, then again after
-`mga_yolo_b200.install()` (MaskCBAM, MGAMaskHead swapped for the CUDA-library modules) with IDENTICAL weights and inputs.
+`mga_yolo_b200.install()` (MaskCBAM / MaskECA / MaskSPADE, MGAMaskHead swapped for the CUDA-library modules) with IDENTICAL weights and inputs.
 What must agree: every output of `model(x)` ({"det": 3 maps, "seg": 3 logit maps}) and the gradients that flow through and out of the
 swapped layers.  fp32 with TF32 off; differences are rounding-order only."""
 import copy
@@ -32,7 +32,7 @@ def _flat(out):
 
 @pytest.mark.skipif(not (REF / "mga_yolo" / "__init__.py").exists(), reason="baseline/_ref not laid out (python oracle/build_full_ref.py)")
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("yaml_name", ["yolov8n_cbam.yaml", "yolov8n_eca.yaml"])
+@pytest.mark.parametrize("yaml_name", ["yolov8n_cbam.yaml", "yolov8n_eca.yaml", "yolov8n_spade.yaml"])
 def test_reference_model_step_with_the_ops_swapped_in(yaml_name, monkeypatch):
     os.environ.setdefault("YOLO_CONFIG_DIR", "/tmp/ulcfg")
     monkeypatch.delenv("MGA_PROB_MODE", raising=False)
@@ -74,7 +74,7 @@ def test_reference_model_step_with_the_ops_swapped_in(yaml_name, monkeypatch):
     try:
         mb.install(strict=True)
         ours = MGAModel(cfg, nc=1, verbose=False)
-        swapped = [type(m) for m in ours.model if isinstance(m, (mb.MaskCBAM, mb.MaskECA, mb.MGAMaskHead))]
+        swapped = [type(m) for m in ours.model if isinstance(m, (mb.MaskCBAM, mb.MaskECA, mb.MaskSPADE, mb.MGAMaskHead))]
         assert len(swapped) == 6  # 3 mask heads + 3 attention blocks
         ours.load_state_dict(state, strict=True)  # same keys, same shapes: checkpoints interchange
         o_out, o_dx, o_g = step(ours)

@@ -87,6 +87,102 @@ def test_eca_module_contract():
         mod([x, torch.randn(2, 1, 4, 4, device=DEV)])
 
 
+# ---------------------------------------------------------------- MaskSPADE (feature side in CUDA: csrc/spade_ops.cu)
+SPADE_KEYS = ("shared.0.weight", "shared.0.bias", "conv_gamma.weight", "conv_gamma.bias", "conv_beta.weight", "conv_beta.bias")
+
+
+@pytest.mark.parametrize("tag", ["basic", "nomask", "raw3d", "odd", "resize", "p5"])
+def test_spade_golden_cases_match_reference(tag, monkeypatch):
+    """Module mirror with the reference's state_dict: out, dx, dmask and the six parameter gradients against the reference run."""
+    from mga_yolo_b200 import MaskSPADE
+
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    z = np.load(GOLDEN / f"spade_{tag}.npz")
+    C, hidden, use_sig = (int(v) for v in z["cfg"])
+    mod = MaskSPADE(C, hidden=hidden, use_sigmoid_mask=bool(use_sig))
+    mod.load_state_dict({k: t(z["p." + k]) for k in SPADE_KEYS}, strict=True)
+    mod.to(DEV)
+    x = t(z["x"]).to(DEV).requires_grad_(True)
+    mask = t(z["mask"]).to(DEV).requires_grad_(True) if bool(z["has_mask"]) else None
+    out = mod(x if mask is None else [x, mask])
+    out.backward(t(z["g"]).to(DEV))
+    assert rel_err(out.detach().cpu(), t(z["out"])) <= 1e-5
+    assert rel_err(x.grad.cpu(), t(z["dx"])) <= 1e-5
+    if mask is not None:
+        assert mask.grad.shape == mask.shape and rel_err(mask.grad.cpu(), t(z["dmask_f64"])) <= 2e-5
+        for k in SPADE_KEYS:
+            assert rel_err(dict(mod.named_parameters())[k].grad.cpu(), t(z["d." + k + "_f64"])) <= 2e-5, k
+
+
+@pytest.mark.parametrize("tag", ["basic", "p5", "odd"])
+def test_spade_op_given_the_reference_gamma_beta(tag):
+    """The CUDA op alone, fed the reference block's own gamma / beta: y, dx, d gamma, d beta (= g) against the fp64 oracle."""
+    from mga_yolo_b200 import next_ops
+    from oracle import spade_oracle as so
+
+    z = np.load(GOLDEN / f"spade_{tag}.npz")
+    x, g, gamma, beta = (t(z[k]).to(DEV) for k in ("x", "g", "gamma", "beta"))
+    x.requires_grad_(True), gamma.requires_grad_(True), beta.requires_grad_(True)
+    y = next_ops.spade_modulate(x, gamma, beta, 1e-6)
+    y.backward(g)
+    ref_y, sv = so.modulate_forward(t(z["x"]).double(), t(z["gamma"]).double(), t(z["beta"]).double(), 1e-6)
+    ref = so.modulate_backward(t(z["g"]).double(), sv)
+    assert rel_err(y.detach().cpu(), ref_y) <= 1e-5 and rel_err(y.detach().cpu(), t(z["out"])) <= 1e-5
+    assert rel_err(x.grad.cpu(), ref["dx"]) <= 1e-5
+    assert rel_err(gamma.grad.cpu(), ref["dgamma"]) <= 1e-5
+    assert torch.equal(beta.grad, g)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 80, 80), (2, 256, 20, 20), (2, 128, 40, 40), (1, 8, 128, 128), (1, 4, 150, 200), (2, 6, 9, 7)])
+@pytest.mark.parametrize("dtype,mod_dtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.float16, torch.float16),
+                                             (torch.bfloat16, torch.float32)])
+def test_spade_matches_oracle_at_neck_shapes(shape, dtype, mod_dtype):
+    """Every launch form: 64 / 128 / 256-thread CTAs, rows staged in shared memory and re-read through L2 (128 x 128: backward only;
+    150 x 200: both directions), the scalar path (odd row length), 16-bit features with 16-bit and with fp32 gamma / beta."""
+    from mga_yolo_b200 import next_ops
+    from oracle import spade_oracle as so
+
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(C + H)
+    x = (torch.randn(B, C, H, W, generator=gen) * 1.5 + 0.3).to(dtype)
+    gamma = (1.0 + 0.5 * torch.randn(B, C, H, W, generator=gen)).to(mod_dtype)
+    beta = (0.5 * torch.randn(B, C, H, W, generator=gen)).to(mod_dtype)
+    g = torch.randn(B, C, H, W, generator=gen).to(dtype)
+    xd, gd, bd = x.to(DEV).requires_grad_(True), gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    y = next_ops.spade_modulate(xd, gd, bd, 1e-6)
+    y.backward(g.to(DEV))
+    ref_y, sv = so.modulate_forward(x.double(), gamma.double(), beta.double(), 1e-6)
+    ref = so.modulate_backward(g.double(), sv)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert y.dtype == dtype and rel_err(y.detach().float().cpu(), ref_y) <= tol
+    assert xd.grad.dtype == dtype and rel_err(xd.grad.float().cpu(), ref["dx"]) <= tol
+    assert gd.grad.dtype == mod_dtype and rel_err(gd.grad.float().cpu(), ref["dgamma"]) <= tol
+    assert bd.grad.dtype == mod_dtype and rel_err(bd.grad.float().cpu(), g.double()) <= (0.0 if mod_dtype == dtype else 1e-6)
+    # mask-less branch: plain instance norm and its backward
+    xn = x.to(DEV).requires_grad_(True)
+    yn = next_ops.spade_modulate(xn, None, None, 1e-6)
+    yn.backward(g.to(DEV))
+    ref_n, svn = so.modulate_forward(x.double(), None, None, 1e-6)
+    assert rel_err(yn.detach().float().cpu(), ref_n) <= tol
+    assert rel_err(xn.grad.float().cpu(), so.modulate_backward(g.double(), svn)["dx"]) <= tol
+
+
+def test_spade_module_under_autocast_and_errors():
+    from mga_yolo_b200 import MaskSPADE, next_ops
+
+    torch.manual_seed(0)
+    mod = MaskSPADE(64, hidden=16).to(DEV)
+    x = torch.randn(2, 64, 40, 40, device=DEV, dtype=torch.float16)
+    mask = torch.randn(2, 1, 40, 40, device=DEV)
+    with torch.autocast("cuda", dtype=torch.float16):  # the reference's AMP training path: fp16 features, fp16 gamma / beta from the convs
+        y = mod([x, mask])
+    assert y.dtype == torch.float16 and y.shape == x.shape and torch.isfinite(y).all()
+    with pytest.raises(RuntimeError, match="does not match"):
+        next_ops.spade_modulate(x, torch.zeros(2, 64, 20, 20, device=DEV, dtype=torch.float16), torch.zeros(2, 64, 20, 20, device=DEV, dtype=torch.float16))
+    with pytest.raises(RuntimeError):
+        next_ops.spade_modulate(x, torch.zeros_like(x), None)
+
+
 @pytest.mark.parametrize("tag", ["p3", "odd"])
 def test_head_tail_matches_reference(tag):
     from mga_yolo_b200 import next_ops

@@ -315,6 +315,44 @@ def test_shape_probe_is_the_only_cpu_answer():
         m(x)
 
 
+def test_spade_module_contract_and_meta_propagation():
+    """MaskSPADE mirrors the reference constructor / state_dict (masked_spade.py:51-100); CPU tensors raise; Meta kernels
+    propagate shapes through forward and backward (the mask branch's library convolutions included)."""
+    from mga_yolo_b200 import MaskSPADE
+    from mga_yolo_b200.module import shape_probe
+
+    torch.manual_seed(5)
+    m = MaskSPADE(32, hidden=8)
+    assert list(m.state_dict()) == ["shared.0.weight", "shared.0.bias", "conv_gamma.weight", "conv_gamma.bias", "conv_beta.weight", "conv_beta.bias"]
+    assert m.shared[0].weight.shape == (8, 1, 3, 3) and m.conv_gamma.weight.shape == (32, 8, 3, 3) and m.conv_beta.weight.shape == (32, 8, 3, 3)
+    assert not m.conv_gamma.bias.any() and m.scale_name == "C32" and MaskSPADE(256).scale_name == "P3" and m.cfg.eps == 1e-6
+    with pytest.raises(NotImplementedError):
+        MaskSPADE(32, norm_type="bn")
+    if REF.exists():  # same construction / init order as the reference => same weights under the same seed
+        _import_reference()
+        from mga_yolo.nn.modules.masked_spade import MaskSPADE as RefSPADE
+
+        torch.manual_seed(5)
+        ref = RefSPADE(32, hidden=8)
+        assert list(ref.state_dict()) == list(m.state_dict())
+        assert all(torch.equal(a, b) for a, b in zip(ref.state_dict().values(), m.state_dict().values()))
+    x = torch.randn(1, 32, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m([x, torch.randn(1, 1, 8, 8)])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(x)
+    with shape_probe():
+        assert m([x, torch.randn(1, 1, 8, 8)]).shape == x.shape
+    mm = MaskSPADE(32, hidden=8).to("meta")
+    xm = torch.empty(2, 32, 20, 20, device="meta", dtype=torch.bfloat16, requires_grad=True)
+    mk = torch.empty(2, 1, 20, 20, device="meta", requires_grad=True)
+    out = mm([xm, mk])
+    assert out.device.type == "meta" and out.shape == xm.shape and out.dtype == torch.bfloat16
+    out.sum().backward()
+    assert xm.grad.shape == xm.shape and mk.grad.shape == mk.shape and mm.conv_gamma.weight.grad.shape == (32, 8, 3, 3)
+    assert mm(xm).shape == xm.shape  # mask-less branch: plain instance norm
+
+
 def test_flat_grad_reducer_survives_zero_grad_set_to_none():
     """optimizer.zero_grad() (set_to_none=True) detaches .grad from the flat buffer; all_reduce() must re-bind."""
     from mga_yolo_b200 import FlatGradReducer
@@ -380,6 +418,10 @@ def test_install_builds_the_reference_model_from_its_yaml():
         ecas = [m for m in eca.model if isinstance(m, mb.MaskECA)]
         assert [m.cfg.channels for m in ecas] == [64, 128, 256]
         assert set(copy.deepcopy(eca).to("meta")(torch.empty(1, 3, 64, 64, device="meta"))) == {"det", "seg"}
+        spade = MGAModel(str(REF / "configs/models/yolov8n_spade.yaml"), nc=1, verbose=False)
+        spades = [m for m in spade.model if isinstance(m, mb.MaskSPADE)]
+        assert [m.cfg.channels for m in spades] == [64, 128, 256] and [m.i for m in spades] == [23, 25, 27]
+        assert set(copy.deepcopy(spade).to("meta")(torch.empty(1, 3, 64, 64, device="meta"))) == {"det", "seg"}
     finally:
         mb.uninstall()
     from mga_yolo.external.ultralytics.ultralytics.nn import tasks

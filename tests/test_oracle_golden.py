@@ -181,3 +181,26 @@ def test_collate_oracle_matches_reference_rule():
     per = [rng.random((1, h, w)).astype(np.float32) for h, w in ((10, 8), (7, 12), (10, 12))]
     want = torch.stack([F.pad(torch.from_numpy(a), (0, 12 - a.shape[2], 0, 10 - a.shape[1]), value=0.0) for a in per], 0).numpy()
     assert np.array_equal(no.collate_masks([a[0] for a in per]), want)
+
+
+# ---------------------------------------------------------------- MaskSPADE
+SPADE_CASES = ("basic", "nomask", "raw3d", "odd", "resize", "p5")
+
+
+@pytest.mark.parametrize("tag", SPADE_CASES)
+@pytest.mark.parametrize("dtype,suffix,tol", [(torch.float64, "_f64", 1e-12), (torch.float32, "", 5e-6)])
+def test_spade_oracle_matches_reference(tag, dtype, suffix, tol):
+    from oracle import spade_oracle as so
+
+    z = np.load(GOLDEN / f"spade_{tag}.npz")
+    _, _, use_sig = (int(v) for v in z["cfg"])
+    params = {k: t(z["p." + k], dtype) for k in so.PARAM_KEYS}
+    mask = t(z["mask"], dtype) if bool(z["has_mask"]) else None
+    res = so.spade_forward_backward(t(z["x"], dtype), mask, params, t(z["g"], dtype), use_sigmoid_mask=bool(use_sig))
+    assert rel_err(res["out"], t(z["out" + suffix])) <= tol
+    assert rel_err(res["dx"], t(z["dx" + suffix])) <= tol
+    if mask is not None:
+        assert res["dmask"].shape == z["dmask" + suffix].shape and rel_err(res["dmask"], t(z["dmask" + suffix])) <= tol
+        assert rel_err(res["gamma"], t(z["gamma" + suffix])) <= tol and rel_err(res["beta"], t(z["beta" + suffix])) <= tol
+        for k in so.PARAM_KEYS:
+            assert rel_err(res[k], t(z["d." + k + "_f64"])) <= max(tol, 2e-5 if dtype == torch.float32 else 0.0), k
