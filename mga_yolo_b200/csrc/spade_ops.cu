@@ -58,6 +58,23 @@ __global__ void __launch_bounds__(kSpNT) spade_fwd_kernel(const T* __restrict__ 
     const T* const xr = x + base;
     const int nU = S / VEC;
     const float invS = 1.0f / (float)S;
+    const bool mod = gamma != nullptr;
+    if constexpr (VEC > 1) {
+        // gamma / beta are needed only after the two statistics: one bulk L2 prefetch per row (copy engine, no registers, no
+        // scoreboard) starts their HBM fetch now, so the modulation pass below reads them from L2 instead of paying a second
+        // serialized HBM round trip per CTA
+        if (mod && tid == 0) {
+            const size_t bytes = (size_t)S * sizeof(TG);
+            const char* const gp = reinterpret_cast<const char*>(gamma + base);
+            const char* const bp = reinterpret_cast<const char*>(beta + base);
+            constexpr size_t kChunk = 32768;
+            for (size_t o = 0; o < bytes; o += kChunk) {
+                const unsigned n = (unsigned)(bytes - o < kChunk ? bytes - o : kChunk);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gp + o), "r"(n) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(bp + o), "r"(n) : "memory");
+            }
+        }
+    }
 
     float sum = 0.0f;
     for (int u = tid; u < nU; u += nt) {
@@ -88,7 +105,6 @@ __global__ void __launch_bounds__(kSpNT) spade_fwd_kernel(const T* __restrict__ 
         stats[2 * (size_t)blockIdx.x] = mean;
         stats[2 * (size_t)blockIdx.x + 1] = rstd;
     }
-    const bool mod = gamma != nullptr;
     for (int u = tid; u < nU; u += nt) {
         float v[VEC], o[VEC];
         if constexpr (STAGED) {
