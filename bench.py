@@ -1160,18 +1160,19 @@ def spade_block(dev, levels, B, dtype, peak):
     torch.cuda.synchronize(dev)
     reps = 10
     per = []
-    for li, (x, gm, bt, g) in enumerate(sets):  # per-kernel durations (P3 alone touches 0.9 GB per pass: nothing stays in L2)
+    for li, (x, gm, bt, g) in enumerate(sets):  # per-kernel durations: back-to-back launches of one kernel (P3 touches 0.4-0.5 GB per launch: nothing stays in L2)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        tf = tb = 0.0
+        _, stats = torch.ops.mga.spade_fwd(x, gm, bt, 1e-6)
+        torch.cuda.synchronize(dev)
+        ev[0].record()
         for _ in range(reps):
-            ev[0].record()
-            _, stats = torch.ops.mga.spade_fwd(x, gm, bt, 1e-6)
-            ev[1].record()
+            torch.ops.mga.spade_fwd(x, gm, bt, 1e-6)
+        ev[1].record()
+        for _ in range(reps):
             torch.ops.mga.spade_bwd(g, x, gm, stats, True)
-            ev[2].record()
-            torch.cuda.synchronize(dev)
-            tf += ev[0].elapsed_time(ev[1])
-            tb += ev[1].elapsed_time(ev[2])
+        ev[2].record()
+        torch.cuda.synchronize(dev)
+        tf, tb = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
         n = B * levels[li][0] * levels[li][1] * levels[li][2] * e
         per.append({"level": f"P{3 + li}", "fwd_ms": round(tf / reps, 5), "bwd_ms": round(tb / reps, 5),
                     "fwd_frac": round(4 * n / (tf / reps * 1e-3) / 1e9 / peak, 4), "bwd_frac": round(5 * n / (tb / reps * 1e-3) / 1e9 / peak, 4)})

@@ -201,6 +201,128 @@ __global__ void __launch_bounds__(kSpNT) spade_bwd_kernel(const T* __restrict__ 
     }
 }
 
+// Short rows (P5: 20 x 20): ONE WARP per row, the row lives in registers (up to kSpKW 16-byte units per lane), the statistics are
+// warp shuffles -- no shared memory, no block barrier, eight rows per CTA instead of one small CTA per row.
+constexpr int kSpKW = 4;
+template <typename T, typename TG, int VEC>
+__global__ void __launch_bounds__(kSpNT) spade_fwd_warp_kernel(const T* __restrict__ x, const TG* __restrict__ gamma, const TG* __restrict__ beta,
+                                                               T* __restrict__ out, float* __restrict__ stats, int R, int S, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= R) return;
+    const size_t base = (size_t)row * S;
+    const int nU = S / VEC;
+    const float invS = 1.0f / (float)S;
+    const bool mod = gamma != nullptr;
+    if (mod && lane == 0) {
+        const unsigned bytes = (unsigned)S * (unsigned)sizeof(TG);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gamma + base), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(beta + base), "r"(bytes) : "memory");
+    }
+    float v[kSpKW][VEC];
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kSpKW; ++k) {
+        const int u = lane + 32 * k;
+        if (u < nU) {
+            ldv<T, VEC, kLdStream>(x + base + (size_t)u * VEC, v[k]);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) sum += v[k][i];
+        }
+    }
+    const float mean = warp_sum(sum) * invS;
+    float sq = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kSpKW; ++k)
+        if (lane + 32 * k < nU) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float d = v[k][i] - mean;
+                sq = fmaf(d, d, sq);
+            }
+        }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) * invS + eps);
+    if (lane == 0) {
+        stats[2 * (size_t)row] = mean;
+        stats[2 * (size_t)row + 1] = rstd;
+    }
+#pragma unroll
+    for (int k = 0; k < kSpKW; ++k) {
+        const int u = lane + 32 * k;
+        if (u < nU) {
+            const size_t o = base + (size_t)u * VEC;
+            float r[VEC];
+            if (mod) {
+                float gm[VEC], bt[VEC];
+                sp_ld_mod<TG, VEC>(gamma + o, gm);
+                sp_ld_mod<TG, VEC>(beta + o, bt);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) r[i] = fmaf(gm[i], (v[k][i] - mean) * rstd, bt[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) r[i] = (v[k][i] - mean) * rstd;
+            }
+            stv<T, VEC, true>(out + o, r);
+        }
+    }
+}
+
+template <typename T, typename TG, int VEC>
+__global__ void __launch_bounds__(kSpNT) spade_bwd_warp_kernel(const T* __restrict__ x, const T* __restrict__ g, const TG* __restrict__ gamma,
+                                                               const float* __restrict__ stats, T* __restrict__ dx, TG* __restrict__ dgamma, int R, int S) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= R) return;
+    const size_t base = (size_t)row * S;
+    const int nU = S / VEC;
+    const float invS = 1.0f / (float)S;
+    const float mean = __ldg(stats + 2 * (size_t)row), rstd = __ldg(stats + 2 * (size_t)row + 1);
+    const bool mod = gamma != nullptr;
+    float xh[kSpKW][VEC], dh[kSpKW][VEC];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kSpKW; ++k) {
+        const int u = lane + 32 * k;
+        if (u < nU) {
+            const size_t o = base + (size_t)u * VEC;
+            float gv[VEC];
+            ldv<T, VEC, kLdStream>(x + o, xh[k]);
+            ldv<T, VEC, kLdStream>(g + o, gv);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) xh[k][i] = (xh[k][i] - mean) * rstd;
+            if (mod) {
+                float gm[VEC], dg[VEC];
+                sp_ld_mod<TG, VEC>(gamma + o, gm);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    dh[k][i] = gv[i] * gm[i];
+                    dg[i] = gv[i] * xh[k][i];
+                }
+                if (dgamma != nullptr) sp_st_mod<TG, VEC>(dgamma + o, dg);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) dh[k][i] = gv[i];
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                s1 += dh[k][i];
+                s2 = fmaf(dh[k][i], xh[k][i], s2);
+            }
+        }
+    }
+    const float m1 = warp_sum(s1) * invS, m2 = warp_sum(s2) * invS;
+#pragma unroll
+    for (int k = 0; k < kSpKW; ++k) {
+        const int u = lane + 32 * k;
+        if (u < nU) {
+            float r[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) r[i] = rstd * (dh[k][i] - m1 - xh[k][i] * m2);
+            stv<T, VEC, true>(dx + base + (size_t)u * VEC, r);
+        }
+    }
+}
+
 // small rows (P5: 20 x 20) take small CTAs so that the SM still holds many rows
 static int sp_threads(int units) { return units <= 128 ? 64 : (units <= 512 ? 128 : kSpNT); }
 static bool sp_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -229,6 +351,11 @@ static int spade_fwd_launch(const void* x, const void* gamma, const void* beta, 
         kern<<<R, sp_threads(S / VEC), smem, st>>>(static_cast<const T*>(x), static_cast<const TG*>(gamma), static_cast<const TG*>(beta), static_cast<T*>(out), \
                                      stats, S, eps);                                                                                    \
     } while (0)
+    if (vec && S / V <= 32 * kSpKW) {  // short rows: one warp per row, eight rows per CTA
+        spade_fwd_warp_kernel<T, TG, V><<<(R + kSpNT / 32 - 1) / (kSpNT / 32), kSpNT, 0, st>>>(
+            static_cast<const T*>(x), static_cast<const TG*>(gamma), static_cast<const TG*>(beta), static_cast<T*>(out), stats, R, S, eps);
+        return MGA_OK;
+    }
     if (vec) { if (staged) MGA_SP_F(V, true); else MGA_SP_F(V, false); }
     else     { if (staged) MGA_SP_F(1, true); else MGA_SP_F(1, false); }
 #undef MGA_SP_F
@@ -249,6 +376,11 @@ static int spade_bwd_launch(const void* x, const void* g, const void* gamma, con
         kern<<<R, sp_threads(S / VEC), smem, st>>>(static_cast<const T*>(x), static_cast<const T*>(g), static_cast<const TG*>(gamma), stats, static_cast<T*>(dx), \
                                      static_cast<TG*>(dgamma), S);                                                                      \
     } while (0)
+    if (vec && S / V <= 32 * kSpKW) {
+        spade_bwd_warp_kernel<T, TG, V><<<(R + kSpNT / 32 - 1) / (kSpNT / 32), kSpNT, 0, st>>>(
+            static_cast<const T*>(x), static_cast<const T*>(g), static_cast<const TG*>(gamma), stats, static_cast<T*>(dx), static_cast<TG*>(dgamma), R, S);
+        return MGA_OK;
+    }
     if (vec) { if (staged) MGA_SP_B(V, true); else MGA_SP_B(V, false); }
     else     { if (staged) MGA_SP_B(1, true); else MGA_SP_B(1, false); }
 #undef MGA_SP_B
