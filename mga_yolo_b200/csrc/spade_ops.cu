@@ -12,6 +12,7 @@
 // staging budget are re-read through L2 instead.  The mask branch that PRODUCES gamma / beta (3x3 convolutions 1 -> hidden -> C,
 // masked_spade.py:78-84) is dense convolution work and stays with the caller's library.
 #include <cstdint>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "mga_cbam.h"
@@ -49,7 +50,7 @@ __device__ __forceinline__ void sp_st_mod(TG* __restrict__ p, const float (&v)[V
 // x: (R, S) rows of T; gamma / beta: (R, S) rows of TG or NULL; stats: (R, 2) = mean, rstd (saved for backward)
 template <typename T, typename TG, int VEC, bool STAGED>
 __global__ void __launch_bounds__(kSpNT) spade_fwd_kernel(const T* __restrict__ x, const TG* __restrict__ gamma, const TG* __restrict__ beta,
-                                                          T* __restrict__ out, float* __restrict__ stats, int S, float eps) {
+                                                          T* __restrict__ out, float* __restrict__ stats, int S, float eps, int pf) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
     __shared__ float red[32];
     float* const rowf = reinterpret_cast<float*>(sp_smem);
@@ -59,31 +60,46 @@ __global__ void __launch_bounds__(kSpNT) spade_fwd_kernel(const T* __restrict__ 
     const int nU = S / VEC;
     const float invS = 1.0f / (float)S;
     const bool mod = gamma != nullptr;
-    if constexpr (VEC > 1) {
-        // gamma / beta are needed only after the two statistics: one bulk L2 prefetch per row (copy engine, no registers, no
-        // scoreboard) starts their HBM fetch now, so the modulation pass below reads them from L2 instead of paying a second
-        // serialized HBM round trip per CTA
-        if (mod && tid == 0) {
-            const size_t bytes = (size_t)S * sizeof(TG);
-            const char* const gp = reinterpret_cast<const char*>(gamma + base);
-            const char* const bp = reinterpret_cast<const char*>(beta + base);
-            constexpr size_t kChunk = 32768;
-            for (size_t o = 0; o < bytes; o += kChunk) {
-                const unsigned n = (unsigned)(bytes - o < kChunk ? bytes - o : kChunk);
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gp + o), "r"(n) : "memory");
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(bp + o), "r"(n) : "memory");
+    // gamma / beta are needed only after the two statistics: bulk L2 prefetches of the two rows (copy engine, no registers, no
+    // scoreboard) start their HBM fetch early, so the modulation pass reads them from L2 instead of paying a second serialized HBM
+    // round trip per CTA.  pf = 1: at kernel entry; pf = 2: once the x row is in (shorter stay in L2); 0: none.
+    auto prefetch_mod = [&]() {
+        if constexpr (VEC > 1) {
+            if (mod && tid == 0) {
+                const size_t bytes = (size_t)S * sizeof(TG);
+                const char* const gp = reinterpret_cast<const char*>(gamma + base);
+                const char* const bp = reinterpret_cast<const char*>(beta + base);
+                constexpr size_t kChunk = 32768;
+                for (size_t o = 0; o < bytes; o += kChunk) {
+                    const unsigned n = (unsigned)(bytes - o < kChunk ? bytes - o : kChunk);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gp + o), "r"(n) : "memory");
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(bp + o), "r"(n) : "memory");
+                }
+            }
+        }
+    };
+    if (pf == 1) prefetch_mod();
+
+    float sum = 0.0f;
+    constexpr int KU1 = (VEC == 1) ? 1 : 4;  // 16-byte loads in flight per thread
+    for (int u0 = tid; u0 < nU; u0 += KU1 * nt) {
+        RawV raw[KU1];
+#pragma unroll
+        for (int k = 0; k < KU1; ++k)
+            if (u0 + k * nt < nU) raw[k] = ldraw<T, VEC, STAGED ? kLdStream : kLdDefault>(xr + (size_t)(u0 + k * nt) * VEC);
+#pragma unroll
+        for (int k = 0; k < KU1; ++k) {
+            const int u = u0 + k * nt;
+            if (u < nU) {
+                float v[VEC];
+                unpackv<T, VEC>(raw[k], v);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) sum += v[i];
+                if constexpr (STAGED) stf<VEC>(rowf + (size_t)u * VEC, v);  // every thread re-reads only what it wrote: no barrier needed
             }
         }
     }
-
-    float sum = 0.0f;
-    for (int u = tid; u < nU; u += nt) {
-        float v[VEC];
-        ldv<T, VEC, STAGED ? kLdStream : kLdDefault>(xr + (size_t)u * VEC, v);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) sum += v[i];
-        if constexpr (STAGED) stf<VEC>(rowf + (size_t)u * VEC, v);  // every thread re-reads only what it wrote: no barrier needed
-    }
+    if (pf == 2) prefetch_mod();
     const float mean = block_sum(sum, red) * invS;
     float sq = 0.0f;
     for (int u = tid; u < nU; u += nt) {
@@ -105,24 +121,36 @@ __global__ void __launch_bounds__(kSpNT) spade_fwd_kernel(const T* __restrict__ 
         stats[2 * (size_t)blockIdx.x] = mean;
         stats[2 * (size_t)blockIdx.x + 1] = rstd;
     }
-    for (int u = tid; u < nU; u += nt) {
-        float v[VEC], o[VEC];
-        if constexpr (STAGED) {
-            sp_lds<VEC>(rowf + (size_t)u * VEC, v);
-        } else {
-            ldv<T, VEC, kLdStream>(xr + (size_t)u * VEC, v);
-        }
-        if (mod) {
-            float gm[VEC], bt[VEC];
-            sp_ld_mod<TG, VEC>(gamma + base + (size_t)u * VEC, gm);
-            sp_ld_mod<TG, VEC>(beta + base + (size_t)u * VEC, bt);
+    constexpr int KU3 = (VEC == 1) ? 1 : 2;
+    for (int u0 = tid; u0 < nU; u0 += KU3 * nt) {
+        float gm[KU3][VEC], bt[KU3][VEC], v[KU3][VEC];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) o[i] = fmaf(gm[i], (v[i] - mean) * rstd, bt[i]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) o[i] = (v[i] - mean) * rstd;
+        for (int k = 0; k < KU3; ++k) {
+            const int u = u0 + k * nt;
+            if (u < nU) {
+                if (mod) {
+                    sp_ld_mod<TG, VEC>(gamma + base + (size_t)u * VEC, gm[k]);
+                    sp_ld_mod<TG, VEC>(beta + base + (size_t)u * VEC, bt[k]);
+                }
+                if constexpr (!STAGED) ldv<T, VEC, kLdStream>(xr + (size_t)u * VEC, v[k]);
+            }
         }
-        stv<T, VEC, true>(out + base + (size_t)u * VEC, o);
+#pragma unroll
+        for (int k = 0; k < KU3; ++k) {
+            const int u = u0 + k * nt;
+            if (u < nU) {
+                float o[VEC];
+                if constexpr (STAGED) sp_lds<VEC>(rowf + (size_t)u * VEC, v[k]);
+                if (mod) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) o[i] = fmaf(gm[k][i], (v[k][i] - mean) * rstd, bt[k][i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) o[i] = (v[k][i] - mean) * rstd;
+                }
+                stv<T, VEC, true>(out + base + (size_t)u * VEC, o);
+            }
+        }
     }
 }
 
@@ -141,34 +169,52 @@ __global__ void __launch_bounds__(kSpNT) spade_bwd_kernel(const T* __restrict__ 
     const bool mod = gamma != nullptr;
 
     float s1 = 0.0f, s2 = 0.0f;
-    for (int u = tid; u < nU; u += nt) {
-        const size_t o = base + (size_t)u * VEC;
-        float xv[VEC], gv[VEC], dh[VEC];
-        ldv<T, VEC, STAGED ? kLdStream : kLdDefault>(x + o, xv);
-        ldv<T, VEC, STAGED ? kLdStream : kLdDefault>(g + o, gv);
+    constexpr int KU = (VEC == 1) ? 1 : 2;  // units per batch: 6 loads of 16 bytes in flight per thread
+    for (int u0 = tid; u0 < nU; u0 += KU * nt) {
+        RawV rx[KU], rg[KU];
+        float gm[KU][VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) xv[i] = (xv[i] - mean) * rstd;
-        if (mod) {
-            float gm[VEC], dg[VEC];
-            sp_ld_mod<TG, VEC>(gamma + o, gm);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                dh[i] = gv[i] * gm[i];
-                dg[i] = gv[i] * xv[i];
+        for (int k = 0; k < KU; ++k) {
+            const int u = u0 + k * nt;
+            if (u < nU) {
+                const size_t o = base + (size_t)u * VEC;
+                rx[k] = ldraw<T, VEC, STAGED ? kLdStream : kLdDefault>(x + o);
+                rg[k] = ldraw<T, VEC, STAGED ? kLdStream : kLdDefault>(g + o);
+                if (mod) sp_ld_mod<TG, VEC>(gamma + o, gm[k]);
             }
-            if (dgamma != nullptr) sp_st_mod<TG, VEC>(dgamma + o, dg);
-        } else {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) dh[i] = gv[i];
         }
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            s1 += dh[i];
-            s2 = fmaf(dh[i], xv[i], s2);
-        }
-        if constexpr (STAGED) {
-            stf<VEC>(xh_s + (size_t)u * VEC, xv);
-            stf<VEC>(dh_s + (size_t)u * VEC, dh);
+        for (int k = 0; k < KU; ++k) {
+            const int u = u0 + k * nt;
+            if (u < nU) {
+                const size_t o = base + (size_t)u * VEC;
+                float xv[VEC], gv[VEC], dh[VEC];
+                unpackv<T, VEC>(rx[k], xv);
+                unpackv<T, VEC>(rg[k], gv);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) xv[i] = (xv[i] - mean) * rstd;
+                if (mod) {
+                    float dg[VEC];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        dh[i] = gv[i] * gm[k][i];
+                        dg[i] = gv[i] * xv[i];
+                    }
+                    if (dgamma != nullptr) sp_st_mod<TG, VEC>(dgamma + o, dg);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) dh[i] = gv[i];
+                }
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    s1 += dh[i];
+                    s2 = fmaf(dh[i], xv[i], s2);
+                }
+                if constexpr (STAGED) {
+                    stf<VEC>(xh_s + (size_t)u * VEC, xv);
+                    stf<VEC>(dh_s + (size_t)u * VEC, dh);
+                }
+            }
         }
     }
     const float m1 = block_sum(s1, red) * invS;
@@ -323,6 +369,26 @@ __global__ void __launch_bounds__(kSpNT) spade_bwd_warp_kernel(const T* __restri
     }
 }
 
+// tuning builds read MGA_SP_PREFETCH (0 none, 1 at kernel entry, 2 after the first pass); the product library has no knobs
+static int sp_prefetch_mode() {
+#ifdef MGA_TUNING
+    static const int m = [] { const char* e = getenv("MGA_SP_PREFETCH"); return (e && *e) ? atoi(e) : 2; }();
+    return m;
+#else
+    return 2;  // measured on B200 (profiles/r2g_spade.md): 74 us at P3 fp32 against 79 (none) and 84 (at entry: the rows are evicted again before use)
+#endif
+}
+// rows up to this many bytes of fp32 staging live in shared memory (tuning builds: MGA_SP_STAGE_KB_F / _B)
+static size_t sp_stage_limit(bool bwd) {
+#ifdef MGA_TUNING
+    static const long f = [] { const char* e = getenv("MGA_SP_STAGE_KB_F"); return (e && *e) ? atol(e) * 1024 : (long)kSpStageBytes; }();
+    static const long b = [] { const char* e = getenv("MGA_SP_STAGE_KB_B"); return (e && *e) ? atol(e) * 1024 : (long)kSpStageBytes; }();
+    return (size_t)(bwd ? b : f);
+#else
+    (void)bwd;
+    return kSpStageBytes;
+#endif
+}
 // small rows (P5: 20 x 20) take small CTAs so that the SM still holds many rows
 static int sp_threads(int units) { return units <= 128 ? 64 : (units <= 512 ? 128 : kSpNT); }
 static bool sp_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -342,14 +408,14 @@ static int spade_fwd_launch(const void* x, const void* gamma, const void* beta, 
     constexpr int V = 16 / (int)sizeof(T);
     const bool vec = S % V == 0 && sp_aligned16(x) && sp_aligned16(out) && sp_aligned16(gamma) && sp_aligned16(beta);
     const size_t stage = (size_t)S * sizeof(float);
-    const bool staged = stage <= kSpStageBytes;
+    const bool staged = stage <= sp_stage_limit(false);
     const size_t smem = staged ? stage : 0;
 #define MGA_SP_F(VEC, STG)                                                                                                              \
     do {                                                                                                                                \
         auto kern = spade_fwd_kernel<T, TG, VEC, STG>;                                                                                  \
         if (int rc = sp_prepare(kern, smem)) return rc;                                                                                 \
         kern<<<R, sp_threads(S / VEC), smem, st>>>(static_cast<const T*>(x), static_cast<const TG*>(gamma), static_cast<const TG*>(beta), static_cast<T*>(out), \
-                                     stats, S, eps);                                                                                    \
+                                     stats, S, eps, sp_prefetch_mode());                                                                \
     } while (0)
     if (vec && S / V <= 32 * kSpKW) {  // short rows: one warp per row, eight rows per CTA
         spade_fwd_warp_kernel<T, TG, V><<<(R + kSpNT / 32 - 1) / (kSpNT / 32), kSpNT, 0, st>>>(
@@ -367,7 +433,7 @@ static int spade_bwd_launch(const void* x, const void* g, const void* gamma, con
     constexpr int V = 16 / (int)sizeof(T);
     const bool vec = S % V == 0 && sp_aligned16(x) && sp_aligned16(g) && sp_aligned16(dx) && sp_aligned16(gamma) && sp_aligned16(dgamma);
     const size_t stage = 2 * (size_t)S * sizeof(float);
-    const bool staged = stage <= kSpStageBytes;
+    const bool staged = stage <= sp_stage_limit(true);
     const size_t smem = staged ? stage : 0;
 #define MGA_SP_B(VEC, STG)                                                                                                              \
     do {                                                                                                                                \
