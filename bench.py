@@ -1183,7 +1183,34 @@ def spade_block(dev, levels, B, dtype, peak):
     e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / reps
-    return {"workload": f"MaskSPADE feature side (mga_spade_forward / mga_spade_backward), levels {levels}, batch {B}, {str(dtype).split('.')[-1]}",
+    # comparator: the same math as the reference block runs it (masked_spade.py:126,143): F.instance_norm + gamma * xhat + beta under torch autograd
+    lib_ms = None
+    try:
+        import torch.nn.functional as F
+
+        leaves = [tuple(t.clone().requires_grad_(True) for t in (x, gm, bt)) + (g,) for x, gm, bt, g in sets]
+
+        def lib_step():
+            for x, gm, bt, g in leaves:
+                y = gm * F.instance_norm(x, eps=1e-6) + bt
+                torch.autograd.backward(y, g, inputs=[x, gm, bt])
+                x.grad = gm.grad = bt.grad = None
+
+        for _ in range(2):
+            lib_step()
+        torch.cuda.synchronize(dev)
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(5):
+            lib_step()
+        l1.record()
+        torch.cuda.synchronize(dev)
+        lib_ms = l0.elapsed_time(l1) / 5
+        del leaves
+    except Exception as ex:  # pragma: no cover
+        print(f"[bench] spade library comparator failed: {ex}", file=sys.stderr)
+    return {"library_composition_ms_per_step": None if lib_ms is None else round(lib_ms, 4),
+            "workload": f"MaskSPADE feature side (mga_spade_forward / mga_spade_backward), levels {levels}, batch {B}, {str(dtype).split('.')[-1]}",
             "ms_per_step": round(ms, 5), "value": round(alg / (ms * 1e-3) / 1e9, 1), "unit": "GB/s", "algorithmic_bytes_per_step": alg,
             "roofline": {"bound": "hbm", "achieved": round(alg / (ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s", "frac": round(alg / (ms * 1e-3) / 1e9 / peak, 4)},
             "kernels": per, "launches_per_step": 2 * len(levels),
