@@ -247,12 +247,16 @@ __global__ void __launch_bounds__(kSpNT) spade_bwd_kernel(const T* __restrict__ 
     }
 }
 
-// Short rows (P5: 20 x 20): ONE WARP per row, the row lives in registers (up to kSpKW 16-byte units per lane), the statistics are
+// Short rows (P5: 20 x 20): ONE WARP per row, the row lives in registers (up to sp_kw<VEC>() 16-byte units per lane), the statistics are
 // warp shuffles -- no shared memory, no block barrier, eight rows per CTA instead of one small CTA per row.
-constexpr int kSpKW = 4;
+template <int VEC> __host__ __device__ constexpr int sp_kw() { return VEC == 8 ? 2 : 4; }  // 512 pixels per row either way; 16-bit rows keep the register count of fp32 ones
+// ROWS = 1: one warp per row (P5), rows of <= 32 * sp_kw units; the CTA-wide form below (`short`) is the same idea for rows of up to
+// two units per THREAD (P4): the whole row and its gamma / beta live in registers, every operand is requested in ONE batch at kernel
+// entry (no second HBM round trip, no shared-memory staging), the statistics are shuffles (+ one block sum in the CTA-wide form).
 template <typename T, typename TG, int VEC>
 __global__ void __launch_bounds__(kSpNT) spade_fwd_warp_kernel(const T* __restrict__ x, const TG* __restrict__ gamma, const TG* __restrict__ beta,
                                                                T* __restrict__ out, float* __restrict__ stats, int R, int S, float eps) {
+    constexpr int KW = sp_kw<VEC>();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= R) return;
@@ -260,26 +264,33 @@ __global__ void __launch_bounds__(kSpNT) spade_fwd_warp_kernel(const T* __restri
     const int nU = S / VEC;
     const float invS = 1.0f / (float)S;
     const bool mod = gamma != nullptr;
-    if (mod && lane == 0) {
-        const unsigned bytes = (unsigned)S * (unsigned)sizeof(TG);
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gamma + base), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(beta + base), "r"(bytes) : "memory");
-    }
-    float v[kSpKW][VEC];
-    float sum = 0.0f;
+    RawV rx[KW];
+    float gm[KW][VEC], bt[KW][VEC];
 #pragma unroll
-    for (int k = 0; k < kSpKW; ++k) {
+    for (int k = 0; k < KW; ++k) {
         const int u = lane + 32 * k;
         if (u < nU) {
-            ldv<T, VEC, kLdStream>(x + base + (size_t)u * VEC, v[k]);
+            const size_t o = base + (size_t)u * VEC;
+            rx[k] = ldraw<T, VEC, kLdStream>(x + o);
+            if (mod) {
+                sp_ld_mod<TG, VEC>(gamma + o, gm[k]);
+                sp_ld_mod<TG, VEC>(beta + o, bt[k]);
+            }
+        }
+    }
+    float v[KW][VEC];
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KW; ++k)
+        if (lane + 32 * k < nU) {
+            unpackv<T, VEC>(rx[k], v[k]);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) sum += v[k][i];
         }
-    }
     const float mean = warp_sum(sum) * invS;
     float sq = 0.0f;
 #pragma unroll
-    for (int k = 0; k < kSpKW; ++k)
+    for (int k = 0; k < KW; ++k)
         if (lane + 32 * k < nU) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
@@ -293,22 +304,85 @@ __global__ void __launch_bounds__(kSpNT) spade_fwd_warp_kernel(const T* __restri
         stats[2 * (size_t)row + 1] = rstd;
     }
 #pragma unroll
-    for (int k = 0; k < kSpKW; ++k) {
+    for (int k = 0; k < KW; ++k) {
         const int u = lane + 32 * k;
         if (u < nU) {
-            const size_t o = base + (size_t)u * VEC;
             float r[VEC];
             if (mod) {
-                float gm[VEC], bt[VEC];
-                sp_ld_mod<TG, VEC>(gamma + o, gm);
-                sp_ld_mod<TG, VEC>(beta + o, bt);
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) r[i] = fmaf(gm[i], (v[k][i] - mean) * rstd, bt[i]);
+                for (int i = 0; i < VEC; ++i) r[i] = fmaf(gm[k][i], (v[k][i] - mean) * rstd, bt[k][i]);
             } else {
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) r[i] = (v[k][i] - mean) * rstd;
             }
-            stv<T, VEC, true>(out + o, r);
+            stv<T, VEC, true>(out + base + (size_t)u * VEC, r);
+        }
+    }
+}
+
+// one CTA (128 / 256 threads) per row of at most two units per thread; see above
+template <typename T, typename TG, int VEC>
+__global__ void __launch_bounds__(kSpNT) spade_fwd_short_kernel(const T* __restrict__ x, const TG* __restrict__ gamma, const TG* __restrict__ beta,
+                                                                T* __restrict__ out, float* __restrict__ stats, int S, float eps) {
+    __shared__ float red[32];
+    constexpr int KS = 2;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const size_t base = (size_t)blockIdx.x * S;
+    const int nU = S / VEC;
+    const float invS = 1.0f / (float)S;
+    const bool mod = gamma != nullptr;
+    RawV rx[KS];
+    float gm[KS][VEC], bt[KS][VEC];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        const int u = tid + k * nt;
+        if (u < nU) {
+            const size_t o = base + (size_t)u * VEC;
+            rx[k] = ldraw<T, VEC, kLdStream>(x + o);
+            if (mod) {
+                sp_ld_mod<TG, VEC>(gamma + o, gm[k]);
+                sp_ld_mod<TG, VEC>(beta + o, bt[k]);
+            }
+        }
+    }
+    float v[KS][VEC];
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KS; ++k)
+        if (tid + k * nt < nU) {
+            unpackv<T, VEC>(rx[k], v[k]);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) sum += v[k][i];
+        }
+    const float mean = block_sum(sum, red) * invS;
+    float sq = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KS; ++k)
+        if (tid + k * nt < nU) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float d = v[k][i] - mean;
+                sq = fmaf(d, d, sq);
+            }
+        }
+    const float rstd = 1.0f / sqrtf(block_sum(sq, red) * invS + eps);
+    if (tid == 0) {
+        stats[2 * (size_t)blockIdx.x] = mean;
+        stats[2 * (size_t)blockIdx.x + 1] = rstd;
+    }
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        const int u = tid + k * nt;
+        if (u < nU) {
+            float r[VEC];
+            if (mod) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) r[i] = fmaf(gm[k][i], (v[k][i] - mean) * rstd, bt[k][i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) r[i] = (v[k][i] - mean) * rstd;
+            }
+            stv<T, VEC, true>(out + base + (size_t)u * VEC, r);
         }
     }
 }
@@ -324,6 +398,7 @@ __global__ void __launch_bounds__(kSpNT) spade_bwd_warp_kernel(const T* __restri
     const float invS = 1.0f / (float)S;
     const float mean = __ldg(stats + 2 * (size_t)row), rstd = __ldg(stats + 2 * (size_t)row + 1);
     const bool mod = gamma != nullptr;
+    constexpr int kSpKW = sp_kw<VEC>();
     float xh[kSpKW][VEC], dh[kSpKW][VEC];
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
@@ -369,6 +444,74 @@ __global__ void __launch_bounds__(kSpNT) spade_bwd_warp_kernel(const T* __restri
     }
 }
 
+// backward of a row of at most two units per thread: xhat and dxhat stay in registers, no shared-memory staging
+template <typename T, typename TG, int VEC>
+__global__ void __launch_bounds__(kSpNT) spade_bwd_short_kernel(const T* __restrict__ x, const T* __restrict__ g, const TG* __restrict__ gamma,
+                                                                const float* __restrict__ stats, T* __restrict__ dx, TG* __restrict__ dgamma, int S) {
+    __shared__ float red[32];
+    constexpr int KS = 2;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const size_t base = (size_t)blockIdx.x * S;
+    const int nU = S / VEC;
+    const float invS = 1.0f / (float)S;
+    const float mean = __ldg(stats + 2 * (size_t)blockIdx.x), rstd = __ldg(stats + 2 * (size_t)blockIdx.x + 1);
+    const bool mod = gamma != nullptr;
+    RawV rx[KS], rg[KS];
+    float gm[KS][VEC];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        const int u = tid + k * nt;
+        if (u < nU) {
+            const size_t o = base + (size_t)u * VEC;
+            rx[k] = ldraw<T, VEC, kLdStream>(x + o);
+            rg[k] = ldraw<T, VEC, kLdStream>(g + o);
+            if (mod) sp_ld_mod<TG, VEC>(gamma + o, gm[k]);
+        }
+    }
+    float xh[KS][VEC], dh[KS][VEC];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        const int u = tid + k * nt;
+        if (u < nU) {
+            float gv[VEC];
+            unpackv<T, VEC>(rx[k], xh[k]);
+            unpackv<T, VEC>(rg[k], gv);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) xh[k][i] = (xh[k][i] - mean) * rstd;
+            if (mod) {
+                float dg[VEC];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    dh[k][i] = gv[i] * gm[k][i];
+                    dg[i] = gv[i] * xh[k][i];
+                }
+                if (dgamma != nullptr) sp_st_mod<TG, VEC>(dgamma + base + (size_t)u * VEC, dg);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) dh[k][i] = gv[i];
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                s1 += dh[k][i];
+                s2 = fmaf(dh[k][i], xh[k][i], s2);
+            }
+        }
+    }
+    const float m1 = block_sum(s1, red) * invS;
+    const float m2 = block_sum(s2, red) * invS;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        const int u = tid + k * nt;
+        if (u < nU) {
+            float r[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) r[i] = rstd * (dh[k][i] - m1 - xh[k][i] * m2);
+            stv<T, VEC, true>(dx + base + (size_t)u * VEC, r);
+        }
+    }
+}
+
 // tuning builds read MGA_SP_PREFETCH (0 none, 1 at kernel entry, 2 after the first pass); the product library has no knobs
 static int sp_prefetch_mode() {
 #ifdef MGA_TUNING
@@ -376,6 +519,15 @@ static int sp_prefetch_mode() {
     return m;
 #else
     return 2;  // measured on B200 (profiles/r2g_spade.md): 74 us at P3 fp32 against 79 (none) and 84 (at entry: the rows are evicted again before use)
+#endif
+}
+// tuning builds: MGA_SP_SHORT=0 sends rows of <= two units per thread through the general (staged) kernels
+static bool sp_short_rows() {
+#ifdef MGA_TUNING
+    static const int m = [] { const char* e = getenv("MGA_SP_SHORT"); return (e && *e) ? atoi(e) : 1; }();
+    return m != 0;
+#else
+    return true;
 #endif
 }
 // rows up to this many bytes of fp32 staging live in shared memory (tuning builds: MGA_SP_STAGE_KB_F / _B)
@@ -417,9 +569,14 @@ static int spade_fwd_launch(const void* x, const void* gamma, const void* beta, 
         kern<<<R, sp_threads(S / VEC), smem, st>>>(static_cast<const T*>(x), static_cast<const TG*>(gamma), static_cast<const TG*>(beta), static_cast<T*>(out), \
                                      stats, S, eps, sp_prefetch_mode());                                                                \
     } while (0)
-    if (vec && S / V <= 32 * kSpKW) {  // short rows: one warp per row, eight rows per CTA
+    if (vec && S / V <= 32 * sp_kw<V>()) {  // short rows: one warp per row, eight rows per CTA
         spade_fwd_warp_kernel<T, TG, V><<<(R + kSpNT / 32 - 1) / (kSpNT / 32), kSpNT, 0, st>>>(
             static_cast<const T*>(x), static_cast<const TG*>(gamma), static_cast<const TG*>(beta), static_cast<T*>(out), stats, R, S, eps);
+        return MGA_OK;
+    }
+    if (vec && S / V <= 2 * kSpNT && sp_short_rows()) {  // rows of at most two units per thread: everything in registers, one load batch
+        spade_fwd_short_kernel<T, TG, V><<<R, S / V <= 256 ? 128 : kSpNT, 0, st>>>(
+            static_cast<const T*>(x), static_cast<const TG*>(gamma), static_cast<const TG*>(beta), static_cast<T*>(out), stats, S, eps);
         return MGA_OK;
     }
     if (vec) { if (staged) MGA_SP_F(V, true); else MGA_SP_F(V, false); }
@@ -442,9 +599,14 @@ static int spade_bwd_launch(const void* x, const void* g, const void* gamma, con
         kern<<<R, sp_threads(S / VEC), smem, st>>>(static_cast<const T*>(x), static_cast<const T*>(g), static_cast<const TG*>(gamma), stats, static_cast<T*>(dx), \
                                      static_cast<TG*>(dgamma), S);                                                                      \
     } while (0)
-    if (vec && S / V <= 32 * kSpKW) {
+    if (vec && S / V <= 32 * sp_kw<V>()) {
         spade_bwd_warp_kernel<T, TG, V><<<(R + kSpNT / 32 - 1) / (kSpNT / 32), kSpNT, 0, st>>>(
             static_cast<const T*>(x), static_cast<const T*>(g), static_cast<const TG*>(gamma), stats, static_cast<T*>(dx), static_cast<TG*>(dgamma), R, S);
+        return MGA_OK;
+    }
+    if (vec && S / V <= 2 * kSpNT && sp_short_rows()) {
+        spade_bwd_short_kernel<T, TG, V><<<R, S / V <= 256 ? 128 : kSpNT, 0, st>>>(
+            static_cast<const T*>(x), static_cast<const T*>(g), static_cast<const TG*>(gamma), stats, static_cast<T*>(dx), static_cast<TG*>(dgamma), S);
         return MGA_OK;
     }
     if (vec) { if (staged) MGA_SP_B(V, true); else MGA_SP_B(V, false); }
