@@ -568,6 +568,11 @@ def gpu_arm(args, rank, world, local_rank):
         except Exception as e:  # pragma: no cover
             line["spade_block"] = {"error": f"{type(e).__name__}: {e}"}
         torch.cuda.empty_cache()
+        try:
+            line["eca_block"] = eca_block(dev, levels, B, dtype, peak)
+        except Exception as e:  # pragma: no cover
+            line["eca_block"] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
     if solo and not args.no_workloads and args.workload == "cfg2":
         # the other BASELINE configs that fit one GPU: same step, same rules, fewer timed steps
         wl = {}
@@ -1215,6 +1220,55 @@ def spade_block(dev, levels, B, dtype, peak):
             "roofline": {"bound": "hbm", "achieved": round(alg / (ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s", "frac": round(alg / (ms * 1e-3) / 1e9 / peak, 4)},
             "kernels": per, "launches_per_step": 2 * len(levels),
             "note": "eager op calls on one stream (6 launches per step); the mask branch that produces gamma / beta is library convolution work and not timed here"}
+
+
+def eca_block(dev, levels, B, dtype, peak):
+    """SURVEY 8f-4 neighbour: MaskECA forward + backward (mga_eca_forward / mga_eca_backward through the nn.Module) at the same pyramid
+    shapes.  Algorithmic bytes per level: forward (2 N + B S) e, backward (3 N + 2 B S) e  (x, mask in, out; x, g in, dx, dmask out)."""
+    from mga_yolo_b200 import MaskECA
+
+    e = torch.empty((), dtype=dtype).element_size()
+    items = []
+    for (C, H, W) in levels:
+        gen = torch.Generator(device=dev).manual_seed(C)
+        mod = MaskECA(C).to(dev)
+        x = torch.randn(B, C, H, W, device=dev, dtype=dtype, generator=gen).requires_grad_(True)
+        m = torch.randn(B, 1, H, W, device=dev, generator=gen).requires_grad_(True)
+        g = torch.randn(B, C, H, W, device=dev, dtype=dtype, generator=gen)
+        items.append((mod, x, m, g))
+    alg = sum((5 * B * C * H * W) * e + 3 * B * H * W * 4 for (C, H, W) in levels)
+
+    def step():
+        for mod, x, m, g in items:
+            out = mod([x, m])
+            torch.autograd.backward(out, g, inputs=[x, m, *mod.parameters()])
+            x.grad = m.grad = None
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    gph = torch.cuda.CUDAGraph()
+    cap = torch.cuda.Stream(dev)
+    with torch.cuda.stream(cap):
+        step()
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(gph, stream=cap):
+            step()
+        for _ in range(2):
+            gph.replay()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record(cap)
+        for _ in range(reps):
+            gph.replay()
+        e1.record(cap)
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    return {"workload": f"MaskECA block (nn.Module -> mga_eca_forward / mga_eca_backward), levels {levels}, batch {B}, {str(dtype).split('.')[-1]}",
+            "ms_per_step": round(ms, 5), "value": round(alg / (ms * 1e-3) / 1e9, 1), "unit": "GB/s", "algorithmic_bytes_per_step": alg,
+            "roofline": {"bound": "hbm", "achieved": round(alg / (ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s", "frac": round(alg / (ms * 1e-3) / 1e9 / peak, 4)},
+            "note": "module calls + torch.autograd.backward on one stream, captured in a CUDA graph and replayed; 8 kernels per level"}
 
 
 def inference_b1(dev, levels, dtype, threads):
