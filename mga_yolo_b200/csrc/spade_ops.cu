@@ -6,11 +6,15 @@
 //   mga_spade_backward   closed form of the same: d gamma = g * xhat, d beta = g (the caller's own tensor),
 //                        dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)) with dxhat = g * gamma
 //
-// HBM-bound streaming kernels: ONE CTA owns one (sample, channel) row, reads it from HBM once into shared memory (fp32), derives the two
-// statistics there (two-pass variance, fixed summation order, no atomics) and streams the modulation out -- x, gamma, beta are read once
-// and y written once (forward: 4 N elements of traffic; backward: x, g, gamma in, dx, d gamma out = 5 N).  Rows that do not fit the
-// staging budget are re-read through L2 instead.  The mask branch that PRODUCES gamma / beta (3x3 convolutions 1 -> hidden -> C,
-// masked_spade.py:78-84) is dense convolution work and stays with the caller's library.
+// HBM-bound streaming kernels; one (sample, channel) row is always owned by ONE CTA (or warp), so both statistics are fixed-order sums
+// with no atomics, x / gamma / beta are read from HBM once and y written once (forward 4 N elements of traffic; backward x, g, gamma in,
+// dx, d gamma out = 5 N).  Three forms by row length (16-byte units = 4 fp32 / 8 16-bit pixels), measured in profiles/r2g_spade.md:
+//   * long rows (P3: 80 x 80):  one CTA per row, the row staged in shared memory as fp32 (loads issued in batches and held raw; gamma /
+//     beta announced to L2 by a bulk prefetch once the x row is in); rows above the staging budget are re-read through L2 instead;
+//   * rows of <= two units per thread (P4: 40 x 40): one CTA per row, row AND gamma / beta in registers, one load batch, no staging;
+//   * rows of <= 512 pixels (P5: 20 x 20): one WARP per row, eight rows per CTA, shuffles only.
+// The mask branch that PRODUCES gamma / beta (3x3 convolutions 1 -> hidden -> C, masked_spade.py:78-84) is dense convolution work and
+// stays with the caller's library.
 #include <cstdint>
 #include <cstdlib>
 
